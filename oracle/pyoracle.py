@@ -1,0 +1,562 @@
+"""Pure-Python big-integer restatement of HElib's DoubleCRT hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under helib_b200/ may import this module;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg use it,
+and there only as the checker.
+
+This is the *slow, obviously-correct* oracle (Python ints, O(N^2) or simple
+O(N log N) loops).  It pins the fast C++ oracle (oracle/oracle.cpp) and the
+CUDA engine on small cases.  Every function cites the reference file:line
+whose semantics it restates (paths relative to /root/reference).
+
+Parity status: the reference publishes no golden integer vectors for this
+path and cannot be built here (NTL/GMP not vendored),
+so two inputs are "parity unpinned": the per-prime 2N-th root psi (NTL derives
+it from its PRG, src/CModulus.cpp:93-98,118-119) and the pseudo-random a_i
+rows of a key-switching matrix (NTL PRG, src/Ctxt.cpp:196-206).  Both are
+taken as *inputs* by the engine.  Everything else is a pure function of
+(primes, psi, inputs) and is pinned by this restatement plus the
+psi-independent algebraic invariants in tests/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+HELIB_SP_NBITS = 60  # src/macro.h:21 (NTL_SP_NBITS on 64-bit, no HEXL)
+PRIMEGEN_B = 3       # src/PrimeGenerator.h:51
+
+# ---------------------------------------------------------------------------
+# number theory helpers
+# ---------------------------------------------------------------------------
+
+_MR_BASES = (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37)
+
+
+def is_prime(n: int) -> bool:
+    """Deterministic Miller-Rabin for n < 3.3e24 (replaces NTL::ProbPrime(cand, 60),
+    src/PrimeGenerator.h:121 -- a correct test has a deterministic outcome)."""
+    if n < 2:
+        return False
+    for p in _MR_BASES:
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in _MR_BASES:
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def divc(a: int, b: int) -> int:
+    """ceil(a/b) for positive ints (helib divc, include/helib/NumbTh.h)."""
+    return -((-a) // b)
+
+
+def bal(x: int, M: int) -> int:
+    """Balanced remainder in [-(M-1)/2, (M-1)/2] for odd M; matches
+    src/DoubleCRT.cpp:1048-1051,1096-1099 (prod_half=(prod+1)/2; tmp>=prod_half -> tmp-=prod)."""
+    x %= M
+    if x >= (M + 1) // 2:
+        x -= M
+    return x
+
+
+# ---------------------------------------------------------------------------
+# prime chain  (src/PrimeGenerator.h:39-127, src/Context.cpp:728-1092)
+# ---------------------------------------------------------------------------
+
+
+class PrimeGenerator:
+    """src/PrimeGenerator.h:39-127."""
+
+    def __init__(self, length: int, m: int):
+        if not (PRIMEGEN_B <= length <= HELIB_SP_NBITS):
+            raise ValueError("PrimeGenerator: len is not in [B, HELIB_SP_NBITS]")
+        if not (1 <= m < (1 << HELIB_SP_NBITS)):
+            raise ValueError("PrimeGenerator: m is not in [1, NTL_SP_BOUND)")
+        self.len, self.m = length, m
+        k = 0
+        while (m << k) <= (1 << (length - PRIMEGEN_B)):
+            k += 1
+        self.k = k
+        self.t = divc((1 << length) - 1, m << k)
+
+    def next(self) -> int:
+        L, m = self.len, self.m
+        t_upper = divc((1 << L) - 1, m << self.k)
+        while True:
+            self.t += 1
+            if self.t >= t_upper:
+                self.k -= 1
+                k_lower = 0 if m % 2 == 0 else 1
+                if self.k < k_lower:
+                    raise RuntimeError("Prime generator ran out of primes")
+                self.t = divc((1 << L) - (1 << (L - PRIMEGEN_B)) - 1, m << self.k)
+                t_upper = divc((1 << L) - 1, m << self.k)
+            if self.t % 2 == 0:
+                continue
+            cand = ((self.t * m) << self.k) + 1
+            assert (1 << L) - (1 << (L - PRIMEGEN_B)) <= cand < (1 << L)
+            if is_prime(cand):
+                return cand
+
+
+def _bit_loss() -> float:
+    return -math.log1p(-1.0 / float(1 << PRIMEGEN_B)) / math.log(2.0)
+
+
+def ctxt_prime_size(nbits: int) -> int:
+    """src/Context.cpp:816-843."""
+    bit_loss = _bit_loss()
+    max_psize = HELIB_SP_NBITS - bit_loss
+    nprimes = int(math.ceil(nbits / max_psize))
+    target = HELIB_SP_NBITS
+    while (10 * (target - 1) >= 9 * HELIB_SP_NBITS and (target - 1) >= 30
+           and ((target - 1) - bit_loss) * nprimes >= nbits):
+        target -= 1
+    return target
+
+
+def euler_phi(m: int) -> int:
+    r, n, p = m, m, 2
+    while p * p <= n:
+        if n % p == 0:
+            while n % p == 0:
+                n //= p
+            r -= r // p
+        p += 1
+    if n > 1:
+        r -= r // n
+    return r
+
+
+@dataclass
+class Chain:
+    """The part of helib::Context the hot path needs (include/helib/Context.h:120-180)."""
+    m: int
+    p: int            # plaintext prime; -1 for CKKS
+    r: int
+    phim: int
+    primes: list = field(default_factory=list)     # q_i in chain (index) order
+    small: list = field(default_factory=list)      # indices
+    ctxt: list = field(default_factory=list)
+    special: list = field(default_factory=list)
+    digits: list = field(default_factory=list)     # list of lists of indices
+
+    @property
+    def ckks(self) -> bool:
+        return self.p == -1
+
+    @property
+    def pow2(self) -> bool:
+        return self.m & (self.m - 1) == 0
+
+    def product(self, idxs) -> int:
+        out = 1
+        for i in idxs:
+            out *= self.primes[i]
+        return out
+
+    def log_of_product(self, idxs) -> float:
+        """Context::logOfProduct -- sum of ln(q) in index order (include/helib/Context.h)."""
+        s = 0.0
+        for i in sorted(idxs):
+            s += math.log(float(self.primes[i]))
+        return s
+
+
+def build_mod_chain(m: int, p: int, r: int, bits: int, c: int, *, sk_hwt: int = 0,
+                    resolution: int = 3, bits_in_special: int = 0,
+                    bootstrappable: bool = False, stdev: float = 3.2) -> Chain:
+    """Context::buildModChain (src/Context.cpp:1037-1070) =
+    addSmallPrimes (:728-790) + addCtxtPrimes (:845-872) + addSpecialPrimes (:874-1035).
+    p = -1 selects CKKS (m must then be a power of two)."""
+    if bits <= 0:
+        raise ValueError("Cannot initialise modulus chain with nBits < 1")
+    if bootstrappable and p != -1:
+        raise NotImplementedError("bootstrappable chains (RecryptData::setAE) are out of scope")
+    ch = Chain(m=m, p=p, r=r, phim=euler_phi(m))
+    ckks = p == -1
+
+    def in_chain(q):
+        return q in ch.primes
+
+    # ---- addSmallPrimes (src/Context.cpp:728-790)
+    cp = ctxt_prime_size(bits)
+    assert cp >= 30 and 9 * HELIB_SP_NBITS <= cp * 10 <= 10 * HELIB_SP_NBITS
+    if m <= 0 or m > (1 << 20):
+        raise RuntimeError("addSmallPrimes: m undefined or larger than 2^20")
+    if resolution < 1 or resolution > 10:
+        resolution = 3
+    sizes = []
+    if cp >= 54:
+        smallest = divc(2 * cp, 3)
+    elif cp >= 45:
+        smallest = divc(7 * cp, 10)
+    else:
+        smallest = divc(11 * cp, 15)
+        sizes.append(smallest)
+    sizes += [smallest, smallest]
+    delta = resolution
+    while cp - delta > smallest:
+        sizes.append(cp - delta)
+        delta *= 2
+    if cp - 3 * resolution > smallest:
+        sizes.append(cp - 3 * resolution)
+    if resolution == 1 and cp - 11 > smallest:
+        sizes.append(cp - 11)
+    sizes.sort()
+    last, gen = 0, None
+    for sz in sizes:
+        if sz != last:
+            gen = PrimeGenerator(sz, m)
+        q = gen.next()
+        assert not in_chain(q)
+        ch.small.append(len(ch.primes))
+        ch.primes.append(q)
+        last = sz
+
+    # ---- addCtxtPrimes (src/Context.cpp:845-872)
+    gen = PrimeGenerator(cp, m)
+    bitlen = 0.0
+    while bitlen < bits - 0.5:
+        q = gen.next()
+        assert not in_chain(q)
+        ch.ctxt.append(len(ch.primes))
+        ch.primes.append(q)
+        bitlen += math.log2(float(q))
+
+    # ---- addSpecialPrimes (src/Context.cpp:874-1035)
+    pabs = abs(p)
+    phim = ch.phim
+    p2r = 1 if ckks else pabs ** r
+    p2e = p2r
+    ndg = c
+    if ndg > len(ch.ctxt):
+        ndg = len(ch.ctxt)
+    if ndg <= 0:
+        ndg = 1
+    digits = [[] for _ in range(ndg)]
+    if ndg > 1:
+        remaining = list(ch.ctxt)
+        for d in range(ndg - 1):
+            card = divc(len(remaining), ndg - d)
+            for i in remaining:
+                digits[d].append(i)
+                if len(digits[d]) >= card:
+                    break
+            remaining = [i for i in remaining if i not in digits[d]]
+        if not remaining:
+            ndg -= 1
+            digits = digits[:ndg]
+        else:
+            digits[ndg - 1] = remaining
+    else:
+        digits[0] = list(ch.ctxt)
+    ch.digits = digits
+    max_digit_log = 0.0
+    for dg in digits:
+        s = ch.log_of_product(dg)
+        if s > max_digit_log:
+            max_digit_log = s
+
+    if bits_in_special:
+        nbits = float(bits_in_special)
+    else:
+        h = phim / 2.0 if sk_hwt == 0 else float(sk_hwt)
+        log_phim = math.log(phim)
+        if log_phim < 1:
+            log_phim = 1
+        if ckks:
+            nbits = (max_digit_log + math.log(stdev) + math.log(ndg) - 0.5 * math.log(h)) / math.log(2.0)
+        elif ch.pow2:
+            nbits = (max_digit_log + math.log(p2e) + math.log(stdev) + 0.5 * math.log(12.0)
+                     + math.log(ndg) - 0.5 * math.log(log_phim) - 2 * math.log(pabs)
+                     - math.log(h)) / math.log(2.0)
+        else:
+            nbits = (max_digit_log + math.log(m) + math.log(p2e) + math.log(stdev)
+                     + 0.5 * math.log(12.0) + math.log(ndg) - 0.5 * log_phim
+                     - 0.5 * math.log(log_phim) - 2 * math.log(pabs) - math.log(h)) / math.log(2.0)
+    if nbits < 1:
+        nbits = 1
+    bit_loss = _bit_loss()
+    max_psize = HELIB_SP_NBITS - bit_loss
+    nprimes = int(math.ceil(nbits / max_psize))
+    target = HELIB_SP_NBITS
+    while ((target - 1) >= 0.55 * HELIB_SP_NBITS and (target - 1) >= 30
+           and ((target - 1) - bit_loss) * nprimes >= nbits):
+        target -= 1
+    gen = PrimeGenerator(target, m)
+    while nprimes > 0:
+        q = gen.next()
+        if in_chain(q):
+            continue
+        ch.special.append(len(ch.primes))
+        ch.primes.append(q)
+        nprimes -= 1
+    return ch
+
+
+# ---------------------------------------------------------------------------
+# per-prime transform  (src/CModulus.cpp:358-553)
+# ---------------------------------------------------------------------------
+
+
+def find_psi(q: int, two_n: int) -> int:
+    """A primitive (two_n)-th root of unity mod q, two_n a power of two.
+
+    The reference takes whatever NTL's zz_pContext(INIT_USER_FFT,q) derives after a
+    fixed SetSeed (src/CModulus.cpp:93-98,118-119): *parity unpinned*.  We pin a
+    deterministic choice instead: psi = g^((q-1)/two_n) for the smallest g >= 2 that
+    is a quadratic non-residue mod q.  The engine takes psi as an input, so a real
+    HElib deployment hands over its own (SURVEY.md section 8c calibration trick)."""
+    assert (q - 1) % two_n == 0
+    g = 2
+    while pow(g, (q - 1) // 2, q) != q - 1:
+        g += 1
+    psi = pow(g, (q - 1) // two_n, q)
+    assert pow(psi, two_n // 2, q) == q - 1
+    return psi
+
+
+def ntt_fwd(coeffs, q: int, psi: int):
+    """Cmodulus::FFT pow-2 branch (src/CModulus.cpp:362-429): y[i]=x[i]*psi^i, cyclic
+    length-N DFT with omega=psi^2, natural order out => row[j] = f(psi^(2j+1)) mod q."""
+    n = len(coeffs)
+    a = [(int(c) % q) * pow(psi, i, q) % q for i, c in enumerate(coeffs)]
+    return _cyclic_dft(a, q, psi * psi % q)
+
+
+def ntt_inv(row, q: int, psi: int):
+    """Cmodulus::iFFT pow-2 branch (src/CModulus.cpp:486-553): inverse cyclic DFT
+    (including 1/N) then multiply by psi^-i; coefficients in [0,q)."""
+    n = len(row)
+    om_inv = pow(psi * psi % q, q - 2, q)
+    a = _cyclic_dft([int(x) % q for x in row], q, om_inv)
+    ninv = pow(n, q - 2, q)
+    ipsi = pow(psi, q - 2, q)
+    return [a[i] * ninv % q * pow(ipsi, i, q) % q for i in range(n)]
+
+
+def _cyclic_dft(a, q, omega):
+    """X[k] = sum_n a[n] omega^(nk), natural order in and out (recursive radix-2)."""
+    n = len(a)
+    if n == 1:
+        return list(a)
+    ev = _cyclic_dft(a[0::2], q, omega * omega % q)
+    od = _cyclic_dft(a[1::2], q, omega * omega % q)
+    out = [0] * n
+    w = 1
+    h = n // 2
+    for k in range(h):
+        t = w * od[k] % q
+        out[k] = (ev[k] + t) % q
+        out[k + h] = (ev[k] - t) % q
+        w = w * omega % q
+    return out
+
+
+def negacyclic_mul_schoolbook(f, g, mod=None):
+    """f*g mod (X^N+1) over the integers (optionally mod `mod`)."""
+    n = len(f)
+    out = [0] * n
+    for i, fi in enumerate(f):
+        if fi == 0:
+            continue
+        for j, gj in enumerate(g):
+            k = i + j
+            if k < n:
+                out[k] += fi * gj
+            else:
+                out[k - n] -= fi * gj
+    if mod is not None:
+        out = [x % mod for x in out]
+    return out
+
+
+# ---------------------------------------------------------------------------
+# DoubleCRT as {prime index -> row}  (include/helib/DoubleCRT.h:87-94)
+# ---------------------------------------------------------------------------
+
+
+class PyDCRT:
+    """A DoubleCRT: dict prime-index -> list of N residues (evaluation form)."""
+
+    def __init__(self, chain: Chain, psis, rows=None):
+        self.ch, self.psis = chain, psis
+        self.rows = dict(rows or {})
+
+    def copy(self):
+        return PyDCRT(self.ch, self.psis, {i: list(r) for i, r in self.rows.items()})
+
+    @property
+    def index_set(self):
+        return sorted(self.rows)
+
+    @classmethod
+    def from_poly(cls, chain, psis, poly, idxs):
+        """DoubleCRT(poly, context, s) -> FFT (src/DoubleCRT.cpp:68-85,
+        src/CModulus.cpp:453-457: coefficients reduced into [0,q) first)."""
+        n = chain.phim
+        poly = list(poly) + [0] * (n - len(poly))
+        return cls(chain, psis, {i: ntt_fwd(poly, chain.primes[i], psis[i]) for i in idxs})
+
+    def to_poly(self, idxs=None, positive=False):
+        """DoubleCRT::toPoly (src/DoubleCRT.cpp:925-1113)."""
+        s1 = [i for i in self.index_set if idxs is None or i in idxs]
+        n = self.ch.phim
+        if not s1:
+            return [0] * n
+        Q = self.ch.product(s1)
+        coefs = {i: ntt_inv(self.rows[i], self.ch.primes[i], self.psis[i]) for i in s1}
+        out = []
+        for k in range(n):
+            acc = 0
+            for i in s1:
+                q = self.ch.primes[i]
+                Qi = Q // q
+                t = pow(Qi % q, q - 2, q)
+                acc += Qi * (coefs[i][k] * t % q)
+            acc %= Q
+            out.append(acc if positive else bal(acc, Q))
+        return out
+
+    # -- pointwise (src/DoubleCRT.cpp:216-384)
+    def _op(self, other, fn):
+        if not set(self.rows) <= set(other.rows):
+            raise RuntimeError("DoubleCRT::Op: !(map.getIndexSet() <= other.map.getIndexSet())")
+        for i in self.rows:
+            q = self.ch.primes[i]
+            self.rows[i] = [fn(a, b) % q for a, b in zip(self.rows[i], other.rows[i])]
+        return self
+
+    def add(self, o):
+        return self._op(o, lambda a, b: a + b)
+
+    def sub(self, o):
+        return self._op(o, lambda a, b: a - b)
+
+    def mul(self, o):
+        return self._op(o, lambda a, b: a * b)
+
+    def mul_scalar(self, c: int):
+        for i in self.rows:
+            q = self.ch.primes[i]
+            cc = c % q
+            self.rows[i] = [a * cc % q for a in self.rows[i]]
+        return self
+
+    def div_scalar(self, c: int):
+        """operator/= (src/DoubleCRT.cpp:1122-1139)."""
+        for i in self.rows:
+            q = self.ch.primes[i]
+            inv = pow(c % q, q - 2, q)
+            self.rows[i] = [a * inv % q for a in self.rows[i]]
+        return self
+
+    def remove_primes(self, idxs):
+        for i in idxs:
+            self.rows.pop(i, None)
+        return self
+
+    def add_primes(self, idxs):
+        """DoubleCRT::addPrimes (src/DoubleCRT.cpp:565-599). Returns the balanced poly."""
+        idxs = list(idxs)
+        assert not (set(idxs) & set(self.rows))
+        poly = self.to_poly()
+        for i in idxs:
+            self.rows[i] = ntt_fwd(poly, self.ch.primes[i], self.psis[i])
+        return poly
+
+    def add_primes_and_scale(self, idxs):
+        """DoubleCRT::addPrimesAndScale (src/DoubleCRT.cpp:603-647)."""
+        idxs = list(idxs)
+        assert not (set(idxs) & set(self.rows))
+        f = self.ch.product(idxs)
+        self.mul_scalar(f)
+        for i in idxs:
+            self.rows[i] = [0] * self.ch.phim
+        return self
+
+    def scale_down_to_set(self, keep, ptxt_space: int):
+        """DoubleCRT::scaleDownToSet (src/DoubleCRT.cpp:1464-1516). Returns delta."""
+        diff = [i for i in self.index_set if i not in keep]
+        if not diff:
+            return None
+        assert ptxt_space >= 1 and len(diff) < len(self.rows)
+        P = self.ch.product(diff)
+        delta = self.to_poly(diff)
+        if ptxt_space > 1:
+            p = ptxt_space
+            p_over_2, p_mod_2 = p // 2, p % 2
+            prod_inv = pow(P % p, -1, p)
+            for k, d in enumerate(delta):
+                u = d % p
+                if u != 0:
+                    u = u * prod_inv % p
+                    if u > p_over_2 or (p_mod_2 == 0 and u == p_over_2 and d < 0):
+                        u -= p
+                    delta[k] = d - P * u
+        self.remove_primes(diff)
+        dd = PyDCRT.from_poly(self.ch, self.psis, delta, self.index_set)
+        self.sub(dd)
+        self.div_scalar(P)
+        return delta
+
+    def break_into_digits(self):
+        """DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:479-561). Returns (digits, polys)."""
+        ch = self.ch
+        assert set(self.rows) <= set(ch.ctxt)
+        remaining = set(self.rows)
+        n = 0
+        while remaining:
+            remaining -= set(ch.digits[n])
+            n += 1
+        all_primes = sorted(set(self.rows) | set(ch.special))
+        digits = []
+        for i in range(n):
+            d = self.copy()
+            d.remove_primes([j for j in d.index_set if j not in ch.digits[i]])
+            digits.append(d)
+        polys = []
+        for i in range(n):
+            not_in = [j for j in all_primes if j not in digits[i].rows]
+            polys.append(digits[i].add_primes(not_in))
+            pi = ch.product(ch.digits[i])
+            for j in range(i + 1, n):
+                digits[j].sub(digits[i])
+                digits[j].div_scalar(pi)
+        return digits, polys
+
+    def automorph(self, k: int):
+        """DoubleCRT::automorph, power-of-two m (src/DoubleCRT.cpp:1160-1202):
+        new[j] = old[idx(rep(j)*k mod m)], rep(j) = 2j+1."""
+        m = self.ch.m
+        assert self.ch.pow2 and k % 2 == 1
+        for i in self.rows:
+            old = self.rows[i]
+            self.rows[i] = [old[(((2 * j + 1) * k) % m - 1) // 2] for j in range(len(old))]
+        return self
+
+
+def key_switch_digits(digits, evk_a, evk_b):
+    """Ctxt::keySwitchDigits (src/Ctxt.cpp:191-230): returns (sum D_i*b_i, sum D_i*a_i)
+    over the digits' index set (the evk rows cover all ctxt+special primes)."""
+    out0 = out1 = None
+    for d, a, b in zip(digits, evk_a, evk_b):
+        ta = d.copy().mul(a)
+        tb = d.copy().mul(b)
+        out1 = ta if out1 is None else out1.add(ta)
+        out0 = tb if out0 is None else out0.add(tb)
+    return out0, out1
