@@ -1,0 +1,764 @@
+// hb_engine.cu -- host side of the B200 DoubleCRT engine and its C ABI (include/helib_b200.h).
+//
+// Host C++ owns the chain metadata (primes, psi, digit partition), builds the per-prime twiddle
+// tables and the exact-CRT conversion tables, and issues stream-ordered launches of the kernels
+// in hb_device.cuh.  There is no CPU compute path: without a CUDA device hb_ctx_create fails.
+#include "hb_device.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/helib_b200.h"
+
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_err[512] = "";
+static int hb_fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define HB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return hb_fail(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define HB_TRY(x) do { int r_ = (x); if (r_ != HB_OK) return r_; } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host modular arithmetic
+static inline u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)((u128)a * b % q); }
+static inline u64 h_powmod(u64 a, u64 e, u64 q) {
+  u64 r = 1 % q; a %= q;
+  while (e) { if (e & 1) r = h_mulmod(r, a, q); a = h_mulmod(a, a, q); e >>= 1; }
+  return r;
+}
+static inline u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static bool h_invmod(u64 a, u64 m, u64* out) {  // extended Euclid, m need not be prime
+  __int128 t0 = 0, t1 = 1, r0 = m, r1 = a % m;
+  while (r1 != 0) { __int128 qq = r0 / r1, t2 = t0 - qq * t1, r2 = r0 - qq * r1; t0 = t1; t1 = t2; r0 = r1; r1 = r2; }
+  if (r0 != 1) return false;
+  *out = (u64)(((t0 % (__int128)m) + (__int128)m) % (__int128)m);
+  return true;
+}
+static int h_bitlen(u64 x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
+
+// ------------------------------------------------------------------------------------------
+struct ConvEntry {
+  HbConvDev h;          // host copy of the descriptor (device pointers inside)
+  HbConvDev* d;         // device descriptor
+  void* blob;           // device blob
+  const u64* d_t; const u64* d_t_s;  // (Q/q_j)^-1 without N^-1 (for k_crt)
+};
+
+struct hb_ctx {
+  int device;
+  u64 m; size_t N; int logN, log_blk, nprimes;
+  std::vector<u64> q, psi;
+  std::vector<HbPrimeDev> h_primes;
+  HbPrimeDev* d_primes;
+  ulonglong2* d_tw;
+  cudaStream_t stream;
+  std::vector<int> digit_of; int ndigits; std::vector<int> special;
+  u64* tmpA; u64* tmpB;
+  u64* d_stats;
+  std::map<std::string, ConvEntry> convs;
+  std::vector<hb_poly*> pool;
+  size_t bytes; u64 launches;
+  cudaEvent_t ev0, ev1;
+  size_t max_smem;
+};
+struct hb_poly { hb_ctx* ctx; u64* d; };
+
+static int ctx_alloc(hb_ctx* c, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return hb_fail(HB_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  c->bytes += bytes;
+  return HB_OK;
+}
+static int ctx_scratch(hb_ctx* c) {
+  if (c->tmpA) return HB_OK;
+  size_t sz = (size_t)HB_MAXB * c->nprimes * c->N * sizeof(u64);
+  HB_TRY(ctx_alloc(c, (void**)&c->tmpA, sz));
+  HB_TRY(ctx_alloc(c, (void**)&c->tmpB, sz));
+  return HB_OK;
+}
+static int post_launch(hb_ctx* c, const char* what) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return hb_fail(HB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int hb_version(void) { return 100; }
+extern "C" const char* hb_last_error(void) { return g_err; }
+extern "C" int hb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static u64 find_psi(u64 q, u64 two_n) {
+  u64 g = 2;
+  while (h_powmod(g, (q - 1) / 2, q) != q - 1) g++;
+  return h_powmod(g, (q - 1) / two_n, q);
+}
+
+extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi) {
+  if (!out || !q || nprimes <= 0) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: null argument or nprimes <= 0");
+  if (m < 4 || (m & (m - 1))) return hb_fail(HB_ERR_UNSUPPORTED, "hb_ctx_create: m=%llu is not a power of two >= 4 (Bluestein rows not built yet)", (unsigned long long)m);
+  int ndev = hb_device_count();
+  if (ndev <= 0) return hb_fail(HB_ERR_NO_DEVICE, "hb_ctx_create: no CUDA device (the engine has no CPU path)");
+  if (device < 0 || device >= ndev) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: device %d out of range [0,%d)", device, ndev);
+  HB_CUDA(cudaSetDevice(device));
+  hb_ctx* c = new hb_ctx();
+  c->device = device; c->m = m; c->N = m / 2; c->nprimes = nprimes;
+  c->logN = 0; while (((size_t)1 << c->logN) < c->N) c->logN++;
+  c->log_blk = c->logN >= 11 ? 8 : 0;
+  c->tmpA = c->tmpB = nullptr; c->bytes = 0; c->launches = 0; c->ndigits = 0;
+  c->d_primes = nullptr; c->d_tw = nullptr; c->d_stats = nullptr;
+  c->digit_of.assign(nprimes, -1);
+  c->max_smem = 200 * 1024;
+  const size_t N = c->N;
+  for (int i = 0; i < nprimes; i++) {
+    u64 qi = q[i];
+    if (qi < 3 || qi >= (1ULL << 62) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^62 with m | q-1", i, (unsigned long long)qi); }
+    u64 ps = psi ? psi[i] : find_psi(qi, m);
+    if (h_powmod(ps, N, qi) != qi - 1) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
+    c->q.push_back(qi); c->psi.push_back(ps);
+  }
+  HB_CUDA(cudaStreamCreate(&c->stream));
+#ifndef HB_SIM
+  HB_CUDA(cudaEventCreate(&c->ev0)); HB_CUDA(cudaEventCreate(&c->ev1));
+#endif
+  // twiddle tables: fw[k] = psi^brev(k), iw[k] = psi^-brev(k)
+  std::vector<ulonglong2> tw((size_t)nprimes * 2 * N);
+  std::vector<u64> pw(N);
+  std::vector<unsigned> brev(N);
+  for (size_t k = 0; k < N; k++) { unsigned r = 0; for (int b = 0; b < c->logN; b++) if (k >> b & 1) r |= 1u << (c->logN - 1 - b); brev[k] = r; }
+  HB_TRY(ctx_alloc(c, (void**)&c->d_tw, tw.size() * sizeof(ulonglong2)));
+  c->h_primes.resize(nprimes);
+  for (int i = 0; i < nprimes; i++) {
+    u64 qi = c->q[i];
+    for (int dir = 0; dir < 2; dir++) {
+      u64 base = dir == 0 ? c->psi[i] : h_powmod(c->psi[i], qi - 2, qi);
+      u64 w = 1;
+      for (size_t e = 0; e < N; e++) { pw[e] = w; w = h_mulmod(w, base, qi); }
+      ulonglong2* t = &tw[((size_t)i * 2 + dir) * N];
+      for (size_t k = 0; k < N; k++) { u64 v = pw[brev[k]]; t[k] = make_ulonglong2(v, h_shoup(v, qi)); }
+    }
+    HbPrimeDev& P = c->h_primes[i];
+    P.q = qi;
+    P.ninv = h_powmod((u64)N % qi, qi - 2, qi); P.ninv_s = h_shoup(P.ninv, qi);
+    P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi);
+    P.one_s = (u64)(((u128)1 << 64) / qi);
+    P.fw = c->d_tw + ((size_t)i * 2 + 0) * N;
+    P.iw = c->d_tw + ((size_t)i * 2 + 1) * N;
+  }
+  HB_CUDA(cudaMemcpy(c->d_tw, tw.data(), tw.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&c->d_primes, sizeof(HbPrimeDev) * nprimes));
+  HB_CUDA(cudaMemcpy(c->d_primes, c->h_primes.data(), sizeof(HbPrimeDev) * nprimes, cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&c->d_stats, 4 * sizeof(u64)));
+  HB_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(u64)));
+#ifndef HB_SIM
+  HB_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem + 1024));
+  HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+#endif
+  *out = c;
+  return HB_OK;
+}
+
+extern "C" void hb_ctx_destroy(hb_ctx* c) {
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
+  for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
+  cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int hb_ctx_set_chain(hb_ctx* c, const int32_t* digit_of, int ndigits, const int32_t* special, int nspecial) {
+  if (!c || !digit_of || ndigits < 0 || ndigits > HB_MAXDIG || nspecial < 0 || (nspecial && !special))
+    return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_chain: bad argument (ndigits must be <= %d)", HB_MAXDIG);
+  for (int i = 0; i < c->nprimes; i++) if (digit_of[i] < -1 || digit_of[i] >= ndigits) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_chain: digit_of[%d] out of range", i);
+  for (int i = 0; i < nspecial; i++) if (special[i] < 0 || special[i] >= c->nprimes || digit_of[special[i]] != -1) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_chain: bad special prime index");
+  c->digit_of.assign(digit_of, digit_of + c->nprimes); c->ndigits = ndigits;
+  c->special.assign(special, special + nspecial);
+  std::sort(c->special.begin(), c->special.end());
+  return HB_OK;
+}
+extern "C" int hb_ctx_get_psi(hb_ctx* c, uint64_t* out) {
+  if (!c || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_get_psi: null");
+  for (int i = 0; i < c->nprimes; i++) out[i] = c->psi[i];
+  return HB_OK;
+}
+extern "C" int hb_ctx_sync(hb_ctx* c) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_sync: null");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return HB_OK;
+}
+extern "C" int hb_ctx_stats(hb_ctx* c, uint64_t* out3) {
+  if (!c || !out3) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_stats: null");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  u64 s[4];
+  HB_CUDA(cudaMemcpy(s, c->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+  out3[0] = s[0]; out3[1] = c->launches; out3[2] = c->bytes;
+  return HB_OK;
+}
+extern "C" int hb_ctx_reset_stats(hb_ctx* c) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_reset_stats: null");
+  HB_CUDA(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(u64), c->stream));
+  c->launches = 0;
+  return HB_OK;
+}
+extern "C" int hb_ctx_mark_begin(hb_ctx* c) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_mark_begin: null");
+#ifndef HB_SIM
+  HB_CUDA(cudaEventRecord(c->ev0, c->stream));
+#endif
+  return HB_OK;
+}
+extern "C" int hb_ctx_mark_end(hb_ctx* c, float* ms) {
+  if (!c || !ms) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_mark_end: null");
+#ifndef HB_SIM
+  HB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  HB_CUDA(cudaEventSynchronize(c->ev1));
+  HB_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+#else
+  *ms = 0.f;
+#endif
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// polys
+extern "C" int hb_poly_create(hb_ctx* c, hb_poly** out) {
+  if (!c || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_create: null");
+  hb_poly* p = new hb_poly();
+  p->ctx = c; p->d = nullptr;
+  size_t sz = (size_t)c->nprimes * c->N * sizeof(u64);
+  int r = ctx_alloc(c, (void**)&p->d, sz);
+  if (r != HB_OK) { delete p; return r; }
+  HB_CUDA(cudaMemsetAsync(p->d, 0, sz, c->stream));
+  *out = p;
+  return HB_OK;
+}
+extern "C" void hb_poly_destroy(hb_poly* p) {
+  if (!p) return;
+  cudaStreamSynchronize(p->ctx->stream);
+  p->ctx->bytes -= (size_t)p->ctx->nprimes * p->ctx->N * sizeof(u64);
+  cudaFree(p->d);
+  delete p;
+}
+static int check_idx(hb_ctx* c, const int32_t* idx, int n, const char* who, bool allow_empty = false) {
+  if (n < 0 || (n > 0 && !idx) || (n == 0 && !allow_empty)) return hb_fail(HB_ERR_BAD_ARG, "%s: empty or null index list", who);
+  for (int i = 0; i < n; i++) {
+    if (idx[i] < 0 || idx[i] >= c->nprimes) return hb_fail(HB_ERR_BAD_ARG, "%s: prime index %d out of range", who, idx[i]);
+    for (int j = 0; j < i; j++) if (idx[j] == idx[i]) return hb_fail(HB_ERR_BAD_ARG, "%s: duplicate prime index %d", who, idx[i]);
+  }
+  return HB_OK;
+}
+static int check_polys(hb_poly* const* p, int n, hb_ctx** c, const char* who) {
+  if (!p || n <= 0) return hb_fail(HB_ERR_BAD_ARG, "%s: no polynomials", who);
+  for (int i = 0; i < n; i++) {
+    if (!p[i]) return hb_fail(HB_ERR_BAD_ARG, "%s: null polynomial handle", who);
+    if (*c == nullptr) *c = p[i]->ctx;
+    if (p[i]->ctx != *c) return hb_fail(HB_ERR_INDEX_SET, "%s: incompatible objects (different contexts)", who);  // src/DoubleCRT.cpp:222-223
+  }
+  return HB_OK;
+}
+extern "C" int hb_poly_upload(hb_poly* p, const int32_t* idx, int n, const uint64_t* host) {
+  if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_upload: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_poly_upload"));
+  for (int j = 0; j < n; j++) {
+    size_t off = (size_t)idx[j] * c->N;
+    HB_CUDA(cudaMemcpyAsync(p->d + off, host + off, c->N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+  }
+  return HB_OK;
+}
+extern "C" int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t* host) {
+  if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_download: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_poly_download"));
+  for (int j = 0; j < n; j++) {
+    size_t off = (size_t)idx[j] * c->N;
+    HB_CUDA(cudaMemcpyAsync(host + off, p->d + off, c->N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return HB_OK;
+}
+static int pool_get(hb_ctx* c, int n, std::vector<hb_poly*>& out) {
+  while ((int)c->pool.size() < n) { hb_poly* p; HB_TRY(hb_poly_create(c, &p)); c->pool.push_back(p); }
+  out.assign(c->pool.begin(), c->pool.begin() + n);
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+static void fill_rows(HbRows& r, const int32_t* idx, int n) { r.n = n; for (int i = 0; i < n; i++) r.prime[i] = idx[i]; }
+static int logwb_of(hb_ctx* c) { int n1 = c->logN - c->log_blk; return std::min(n1, 10 - c->log_blk); }
+static int logw_cols(hb_ctx* c) { int n1 = c->logN - c->log_blk; int lw = 10 - n1; if (lw < 0) lw = 0; return std::min(lw, c->log_blk); }
+
+// direction: +1 forward blk (src -> dst, optional epilogue), -1 inverse blk
+static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
+                      int epi, const u64* scal) {
+  const int lwb = logwb_of(c);
+  const int n1 = c->logN - c->log_blk;
+  const size_t smem = ((size_t)1 << lwb) * (((size_t)1 << c->log_blk) + 1) * sizeof(u64);
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    HbBlkJob J; memset(&J, 0, sizeof(J));
+    J.logN = c->logN; J.log_blk = c->log_blk; J.logwb = lwb; J.epi = epi;
+    fill_rows(J.rows, idx + r0, nr);
+    for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    dim3 grid(1u << (n1 - lwb), nr, nitems);
+    if (dir > 0) { HB_LAUNCH(k_fwd_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_fwd_blk")); }
+    else { HB_LAUNCH(k_inv_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_blk")); }
+  }
+  return HB_OK;
+}
+static int launch_cols(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n) {
+  const int lw = logw_cols(c);
+  const int n1 = c->logN - c->log_blk;
+  const size_t smem = ((size_t)1 << (n1 + lw)) * sizeof(u64);
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    HbColsJob J; memset(&J, 0, sizeof(J));
+    J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw;
+    fill_rows(J.rows, idx + r0, nr);
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    dim3 grid(1u << (c->log_blk - lw), nr, nitems);
+    if (dir > 0) { HB_LAUNCH(k_fwd_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_fwd_cols")); }
+    else { HB_LAUNCH(k_inv_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_cols")); }
+  }
+  return HB_OK;
+}
+
+struct PwArgs {
+  int op;
+  u64* const* dst; u64* const* dst1; u64* const* dst2;
+  const u64* const* a; const u64* const* b; const u64* const* cc; const u64* const* d;
+  const u64* scal; u64 k, m;
+};
+static int launch_pw(hb_ctx* c, const PwArgs& A, int nitems, const int32_t* idx, int n) {
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    HbPwJob J; memset(&J, 0, sizeof(J));
+    J.op = A.op; J.logN = c->logN; J.k = A.k; J.m = A.m;
+    fill_rows(J.rows, idx + r0, nr);
+    for (int i = 0; i < nr; i++) if (A.scal) { J.scal[i] = A.scal[r0 + i]; J.scal_s[i] = h_shoup(A.scal[r0 + i], c->q[idx[r0 + i]]); }
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) {
+      J.dst[i] = A.dst[i];
+      if (A.dst1) J.dst1[i] = A.dst1[i];
+      if (A.dst2) J.dst2[i] = A.dst2[i];
+      if (A.a) J.a[i] = A.a[i];
+      if (A.b) J.b[i] = A.b[i];
+      if (A.cc) J.c[i] = A.cc[i];
+      if (A.d) J.d[i] = A.d[i];
+    }
+    unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
+    dim3 grid(gx, nr, nitems);
+    HB_LAUNCH(k_pointwise, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+    HB_TRY(post_launch(c, "k_pointwise"));
+  }
+  return HB_OK;
+}
+
+// run f(item0, count) over chunks of at most HB_MAXB items
+template <class F> static int for_items(int nitems, F f) {
+  for (int i0 = 0; i0 < nitems; i0 += HB_MAXB) HB_TRY(f(i0, std::min(HB_MAXB, nitems - i0)));
+  return HB_OK;
+}
+static void ptrs_of(hb_poly* const* p, int i0, int n, u64** out) { for (int i = 0; i < n; i++) out[i] = p[i0 + i]->d; }
+static void tmp_ptrs(hb_ctx* c, u64* base, int n, u64** out) { for (int i = 0; i < n; i++) out[i] = base + (size_t)i * c->nprimes * c->N; }
+
+// ------------------------------------------------------------------------------------------
+// conversion tables
+static std::string conv_key(const int32_t* src, int n, const int32_t* tgt, int nt, u64 p) {
+  std::string k;
+  for (int i = 0; i < n; i++) k += std::to_string(src[i]) + ",";
+  k += "|";
+  for (int i = 0; i < nt; i++) k += std::to_string(tgt[i]) + ",";
+  k += "|" + std::to_string(p);
+  return k;
+}
+static void limbs_mul_small(std::vector<u64>& a, u64 s) {
+  u128 carry = 0;
+  for (size_t i = 0; i < a.size(); i++) { carry += (u128)a[i] * s; a[i] = (u64)carry; carry >>= 64; }
+}
+static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p, ConvEntry** out) {
+  std::string key = conv_key(src, n, tgt, nt, p);
+  auto it = c->convs.find(key);
+  if (it != c->convs.end()) { *out = &it->second; return HB_OK; }
+  if (n > HB_MAXROWS || n > HB_MAXL) return hb_fail(HB_ERR_UNSUPPORTED, "base conversion from %d source primes (max %d)", n, HB_MAXROWS);
+  const int L = n;
+  std::vector<u64> qs(n);
+  for (int j = 0; j < n; j++) qs[j] = c->q[src[j]];
+  auto prod_mod_excl = [&](int excl, u64 M) { u64 r = 1 % M; for (int k = 0; k < n; k++) if (k != excl) r = h_mulmod(r, qs[k] % M, M); return r; };
+  std::vector<int> h_src(src, src + n), h_tgt(std::max(nt, 1), 0), fshift(n);
+  for (int i = 0; i < nt; i++) h_tgt[i] = tgt[i];
+  std::vector<u64> t(n), t_s(n), tn(n), tn_s(n), fmul(n), cmat(std::max<size_t>((size_t)nt * n, 1)), negQ(std::max(nt, 1)), Qmod(std::max(nt, 1)), cp(n);
+  std::vector<u64> Q(L, 0), Qhalf(L), Qj((size_t)n * L, 0);
+  for (int j = 0; j < n; j++) {
+    u64 qj = qs[j];
+    u64 r = prod_mod_excl(j, qj);
+    t[j] = h_powmod(r, qj - 2, qj); t_s[j] = h_shoup(t[j], qj);
+    tn[j] = h_mulmod(t[j], c->h_primes[src[j]].ninv, qj); tn_s[j] = h_shoup(tn[j], qj);
+    int b = h_bitlen(qj);
+    fmul[j] = (u64)(((u128)1 << (63 + b)) / qj);
+    fshift[j] = b - 1;
+    std::vector<u64> lj(L, 0); lj[0] = 1;
+    for (int k = 0; k < n; k++) if (k != j) limbs_mul_small(lj, qs[k]);
+    memcpy(&Qj[(size_t)j * L], lj.data(), sizeof(u64) * L);
+  }
+  Q[0] = 1; for (int k = 0; k < n; k++) limbs_mul_small(Q, qs[k]);
+  { // Qhalf = (Q-1)/2  (Q odd)
+    std::vector<u64> h = Q; h[0] -= 1;
+    for (int l = 0; l < L; l++) Qhalf[l] = (h[l] >> 1) | (l + 1 < L ? h[l + 1] << 63 : 0);
+  }
+  for (int tt = 0; tt < nt; tt++) {
+    u64 qt = c->q[tgt[tt]];
+    for (int j = 0; j < n; j++) cmat[(size_t)tt * n + j] = prod_mod_excl(j, qt);
+    u64 Qm = prod_mod_excl(-1, qt);
+    Qmod[tt] = Qm; negQ[tt] = Qm ? qt - Qm : 0;
+  }
+  ConvEntry E; memset(&E, 0, sizeof(E));
+  HbConvDev& H = E.h;
+  H.n = n; H.nt = nt; H.L = L; H.has_p = p > 1 ? 1 : 0;
+  if (p > 1) {
+    if (p >= (1ULL << 62)) return hb_fail(HB_ERR_UNSUPPORTED, "ptxt_space >= 2^62");
+    u64 Qp = prod_mod_excl(-1, p), Qinv;
+    if (!h_invmod(Qp, p, &Qinv)) return hb_fail(HB_ERR_BAD_ARG, "ptxt_space %llu is not coprime to the dropped primes", (unsigned long long)p);
+    H.p = p; H.p_c64 = (u64)(((u128)1 << 64) % p); H.p_c64_s = h_shoup(H.p_c64, p); H.p_one_s = (u64)(((u128)1 << 64) / p);
+    H.Qinv_p = Qinv; H.Qinv_p_s = h_shoup(Qinv, p);
+    H.negQ_p = Qp ? p - Qp : 0;
+    for (int j = 0; j < n; j++) cp[j] = prod_mod_excl(j, p);
+  }
+  // pack into one blob
+  std::vector<unsigned char> blob;
+  auto put = [&](const void* src_, size_t bytes) { size_t off = (blob.size() + 15) & ~(size_t)15; blob.resize(off + bytes); memcpy(&blob[off], src_, bytes); return off; };
+  size_t o_src = put(h_src.data(), sizeof(int) * n), o_tgt = put(h_tgt.data(), sizeof(int) * std::max(nt, 1));
+  size_t o_fs = put(fshift.data(), sizeof(int) * n);
+  size_t o_t = put(t.data(), 8 * n), o_ts = put(t_s.data(), 8 * n), o_tn = put(tn.data(), 8 * n), o_tns = put(tn_s.data(), 8 * n);
+  size_t o_fm = put(fmul.data(), 8 * n), o_c = put(cmat.data(), 8 * std::max<size_t>(cmat.size(), 1));
+  size_t o_nq = put(negQ.data(), 8 * std::max(nt, 1)), o_qm = put(Qmod.data(), 8 * std::max(nt, 1)), o_cp = put(cp.data(), 8 * n);
+  size_t o_Q = put(Q.data(), 8 * L), o_Qh = put(Qhalf.data(), 8 * L), o_Qj = put(Qj.data(), 8 * (size_t)n * L);
+  HB_TRY(ctx_alloc(c, &E.blob, blob.size()));
+  HB_CUDA(cudaMemcpy(E.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  unsigned char* B = (unsigned char*)E.blob;
+  H.src_prime = (const int*)(B + o_src); H.tgt_prime = (const int*)(B + o_tgt); H.fshift = (const int*)(B + o_fs);
+  E.d_t = (const u64*)(B + o_t); E.d_t_s = (const u64*)(B + o_ts);
+  H.tn = (const u64*)(B + o_tn); H.tn_s = (const u64*)(B + o_tns); H.fmul = (const u64*)(B + o_fm);
+  H.c = (const u64*)(B + o_c); H.negQ = (const u64*)(B + o_nq); H.Qmod = (const u64*)(B + o_qm); H.cp = (const u64*)(B + o_cp);
+  H.Q = (const u64*)(B + o_Q); H.Qhalf = (const u64*)(B + o_Qh); H.Qj = (const u64*)(B + o_Qj);
+  HB_TRY(ctx_alloc(c, (void**)&E.d, sizeof(HbConvDev)));
+  HB_CUDA(cudaMemcpy(E.d, &H, sizeof(HbConvDev), cudaMemcpyHostToDevice));
+  auto ins = c->convs.emplace(key, E);
+  *out = &ins.first->second;
+  return HB_OK;
+}
+
+// inverse-blk (polys -> tmpA), fused conversion (tmpA -> tmpB), for one chunk of items
+static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p) {
+  HB_TRY(ctx_scratch(c));
+  ConvEntry* E; HB_TRY(get_conv(c, src, n, tgt, nt, p, &E));
+  u64* tA[HB_MAXB]; u64* tB[HB_MAXB];
+  tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
+  HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
+  const int n1 = c->logN - c->log_blk;
+  int lw = logw_cols(c);
+  while (lw > 0 && ((size_t)(n + 2) << (n1 + lw)) * sizeof(u64) > c->max_smem) lw--;
+  size_t smem = ((size_t)(n + 2) << (n1 + lw)) * sizeof(u64);
+  if (smem > c->max_smem) return hb_fail(HB_ERR_UNSUPPORTED, "base conversion tile needs %zu bytes of shared memory", smem);
+  HbConvJob J; memset(&J, 0, sizeof(J));
+  J.cv = E->d; J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw; J.nitems = nit; J.stats = c->d_stats;
+  for (int i = 0; i < nit; i++) { J.src[i] = tA[i]; J.dst[i] = tB[i]; }
+  dim3 grid(1u << (c->log_blk - lw), nit);
+  HB_LAUNCH(k_conv, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J);
+  return post_launch(c, "k_conv");
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI: transforms and pointwise
+extern "C" int hb_ntt_fwd(hb_poly* const* polys, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_ntt_fwd")); HB_TRY(check_idx(c, idx, n, "hb_ntt_fwd"));
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpA, nit, tA);
+    HB_TRY(launch_cols(c, +1, (const u64* const*)P, tA, nit, idx, n));
+    return launch_blk(c, +1, (const u64* const*)tA, P, nit, idx, n, 0, nullptr);
+  });
+}
+extern "C" int hb_ntt_inv(hb_poly* const* polys, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_ntt_inv")); HB_TRY(check_idx(c, idx, n, "hb_ntt_inv"));
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpA, nit, tA);
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, idx, n, 0, nullptr));
+    return launch_cols(c, -1, (const u64* const*)tA, P, nit, idx, n);
+  });
+}
+
+static int pw_simple(int op, hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, const u64* scal, hb_ctx* c) {
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* D[HB_MAXB]; u64* S[HB_MAXB]; ptrs_of(dst, i0, nit, D); if (src) ptrs_of(src, i0, nit, S);
+    PwArgs A; memset(&A, 0, sizeof(A));
+    A.op = op; A.dst = D; A.a = src ? (const u64* const*)S : nullptr; A.scal = scal;
+    return launch_pw(c, A, nit, idx, n);
+  });
+}
+extern "C" int hb_pointwise(int op, hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(dst, nitems, &c, "hb_pointwise")); HB_TRY(check_polys(src, nitems, &c, "hb_pointwise"));
+  HB_TRY(check_idx(c, idx, n, "hb_pointwise"));
+  int dop;
+  switch (op) {
+    case HB_OP_ADD: dop = HB_PW_ADD; break; case HB_OP_SUB: dop = HB_PW_SUB; break; case HB_OP_MUL: dop = HB_PW_MUL; break;
+    case HB_OP_NEG: dop = HB_PW_NEG; break; case HB_OP_COPY: dop = HB_PW_COPY; break;
+    default: return hb_fail(HB_ERR_BAD_ARG, "hb_pointwise: unknown op %d", op);
+  }
+  return pw_simple(dop, dst, src, nitems, idx, n, nullptr, c);
+}
+extern "C" int hb_scale_rows(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const uint64_t* scalars) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_scale_rows")); HB_TRY(check_idx(c, idx, n, "hb_scale_rows"));
+  if (!scalars) return hb_fail(HB_ERR_BAD_ARG, "hb_scale_rows: null scalars");
+  for (int i = 0; i < n; i++) if (scalars[i] >= c->q[idx[i]]) return hb_fail(HB_ERR_BAD_ARG, "hb_scale_rows: scalar %d not reduced", i);
+  return pw_simple(HB_PW_SCALE, polys, nullptr, nitems, idx, n, (const u64*)scalars, c);
+}
+static u64 prod_mod(hb_ctx* c, const int32_t* fidx, int nf, u64 q) {
+  u64 r = 1 % q; for (int k = 0; k < nf; k++) r = h_mulmod(r, c->q[fidx[k]] % q, q); return r;
+}
+static int scalars_by_primes(hb_ctx* c, const int32_t* idx, int n, const int32_t* fidx, int nf, int inverse, std::vector<u64>& out) {
+  out.resize(n);
+  for (int i = 0; i < n; i++) {
+    u64 q = c->q[idx[i]]; u64 f = prod_mod(c, fidx, nf, q);
+    if (inverse) { if (f == 0) return hb_fail(HB_ERR_BAD_ARG, "division by a multiple of prime %d", idx[i]); f = h_powmod(f, q - 2, q); }
+    out[i] = f;
+  }
+  return HB_OK;
+}
+extern "C" int hb_scale_by_primes(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const int32_t* fidx, int nf, int inverse) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_scale_by_primes")); HB_TRY(check_idx(c, idx, n, "hb_scale_by_primes"));
+  HB_TRY(check_idx(c, fidx, nf, "hb_scale_by_primes(factor)", true));
+  std::vector<u64> sc; HB_TRY(scalars_by_primes(c, idx, n, fidx, nf, inverse, sc));
+  return pw_simple(HB_PW_SCALE, polys, nullptr, nitems, idx, n, sc.data(), c);
+}
+extern "C" int hb_zero_rows(hb_poly* const* polys, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_zero_rows")); HB_TRY(check_idx(c, idx, n, "hb_zero_rows"));
+  return pw_simple(HB_PW_ZERO, polys, nullptr, nitems, idx, n, nullptr, c);
+}
+static int check_disjoint(const int32_t* a, int na, const int32_t* b, int nb, const char* who) {
+  for (int i = 0; i < na; i++) for (int j = 0; j < nb; j++) if (a[i] == b[j]) return hb_fail(HB_ERR_INDEX_SET, "%s: can only be called on a disjoint set (prime %d)", who, a[i]);
+  return HB_OK;
+}
+extern "C" int hb_add_primes_and_scale(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_add_primes_and_scale"));
+  HB_TRY(check_idx(c, cur, ncur, "hb_add_primes_and_scale", true)); HB_TRY(check_idx(c, add, nadd, "hb_add_primes_and_scale", true));
+  if (nadd == 0) return HB_OK;  // src/DoubleCRT.cpp:605-606
+  HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimesAndScale"));
+  if (ncur > 0) HB_TRY(hb_scale_by_primes(polys, nitems, cur, ncur, add, nadd, 0));
+  return hb_zero_rows(polys, nitems, add, nadd);
+}
+extern "C" int hb_add_primes(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_add_primes"));
+  HB_TRY(check_idx(c, cur, ncur, "hb_add_primes", true)); HB_TRY(check_idx(c, add, nadd, "hb_add_primes", true));
+  if (nadd == 0) return HB_OK;  // src/DoubleCRT.cpp:569-572
+  HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimes"));
+  if (ncur == 0) return hb_zero_rows(polys, nitems, add, nadd);  // src/DoubleCRT.cpp:577-583
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
+    HB_TRY(conv_chunk(c, P, nit, cur, ncur, add, nadd, 1));
+    return launch_blk(c, +1, (const u64* const*)tB, P, nit, add, nadd, 0, nullptr);
+  });
+}
+extern "C" int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_scale_down"));
+  HB_TRY(check_idx(c, cur, ncur, "hb_scale_down")); HB_TRY(check_idx(c, keep, nkeep, "hb_scale_down(keep)", true));
+  if (ptxt_space < 1) return hb_fail(HB_ERR_BAD_ARG, "ptxtSpace must be at least 1");  // src/DoubleCRT.cpp:1472
+  std::vector<int32_t> diff, kept;
+  for (int i = 0; i < ncur; i++) {
+    bool k = std::find(keep, keep + nkeep, cur[i]) != keep + nkeep;
+    (k ? kept : diff).push_back(cur[i]);
+  }
+  if (diff.empty()) return HB_OK;  // src/DoubleCRT.cpp:1468-1470
+  if (kept.empty()) return hb_fail(HB_ERR_INDEX_SET, "scaleDownToSet: s and the index set must have some intersection");  // :1474-1476
+  std::vector<u64> sc; HB_TRY(scalars_by_primes(c, kept.data(), (int)kept.size(), diff.data(), (int)diff.size(), 1, sc));
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
+    HB_TRY(conv_chunk(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space));
+    return launch_blk(c, +1, (const u64* const*)tB, P, nit, kept.data(), (int)kept.size(), 1, sc.data());
+  });
+}
+extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, uint64_t* out, int Lout) {
+  if (!p || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_to_poly", true));
+  if (n == 0) { memset(out, 0, sizeof(u64) * c->N * Lout); return HB_OK; }  // src/DoubleCRT.cpp:931-935
+  if (Lout < n) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly: Lout=%d limbs cannot hold a %d-prime product", Lout, n);
+  HB_TRY(ctx_scratch(c));
+  ConvEntry* E; HB_TRY(get_conv(c, idx, n, nullptr, 0, 1, &E));
+  u64* P[1] = {p->d}; u64* tA[1] = {c->tmpA}; u64* tB[1] = {c->tmpB};
+  HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, 1, idx, n, 0, nullptr));
+  HB_TRY(launch_cols(c, -1, (const u64* const*)tA, tB, 1, idx, n));
+  u64* d_out; size_t bytes = c->N * (size_t)Lout * sizeof(u64);
+  HB_CUDA(cudaMalloc((void**)&d_out, bytes));
+  HbCrtJob J; J.cv = E->d; J.N = (int)c->N; J.Lout = Lout; J.positive = positive; J.src = c->tmpB; J.out = d_out;
+  HbCrtTabs T; T.t = E->d_t; T.t_s = E->d_t_s;
+  dim3 grid((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS));
+  HB_LAUNCH(k_crt, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J, T);
+  int r = post_launch(c, "k_crt");
+  if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_to_poly: copy failed: %s", cudaGetErrorString(e)); }
+  cudaFree(d_out);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// digits and key switching
+extern "C" int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(src, nitems, &c, "hb_break_into_digits")); HB_TRY(check_idx(c, cur, ncur, "hb_break_into_digits"));
+  if (!digits || !ndig_out) return hb_fail(HB_ERR_BAD_ARG, "hb_break_into_digits: null");
+  // index set must be a subset of ctxt primes (src/DoubleCRT.cpp:497-498)
+  for (int i = 0; i < ncur; i++) if (c->digit_of[cur[i]] < 0) return hb_fail(HB_ERR_INDEX_SET, "breakIntoDigits: index set must be a subset of ctxt primes (prime %d)", cur[i]);
+  // number of digits: src/DoubleCRT.cpp:485-493
+  std::vector<char> rem(c->nprimes, 0); int left = ncur, nd = 0;
+  for (int i = 0; i < ncur; i++) rem[cur[i]] = 1;
+  for (; left > 0; nd++) for (int i = 0; i < c->nprimes; i++) if (rem[i] && c->digit_of[i] == nd) { rem[i] = 0; left--; }
+  if (nd > c->ndigits || nd > maxdig) return hb_fail(HB_ERR_BAD_ARG, "breakIntoDigits: n cannot be larger than the size of context.digits");
+  hb_ctx* c2 = c; HB_TRY(check_polys(digits, nitems * maxdig, &c2, "hb_break_into_digits(digits)"));
+  std::vector<int32_t> all(cur, cur + ncur);
+  all.insert(all.end(), c->special.begin(), c->special.end());
+  std::sort(all.begin(), all.end());
+  std::vector<std::vector<int32_t>> dset(nd), notin(nd), full(nd);
+  for (int i = 0; i < nd; i++) {
+    for (int j = 0; j < ncur; j++) if (c->digit_of[cur[j]] == i) dset[i].push_back(cur[j]);
+    for (int a : all) if (std::find(dset[i].begin(), dset[i].end(), a) == dset[i].end()) notin[i].push_back(a);
+    for (int k = 0; k < c->nprimes; k++) if (c->digit_of[k] == i) full[i].push_back(k);
+  }
+  std::vector<hb_poly*> col(nitems), col2(nitems);
+  for (int i = 0; i < nd; i++) {  // digits[i] = *this restricted to digit i  (src/DoubleCRT.cpp:509-513)
+    for (int it = 0; it < nitems; it++) col[it] = digits[it * maxdig + i];
+    HB_TRY(pw_simple(HB_PW_COPY, col.data(), src, nitems, dset[i].data(), (int)dset[i].size(), nullptr, c));
+  }
+  for (int i = 0; i < nd; i++) {
+    for (int it = 0; it < nitems; it++) col[it] = digits[it * maxdig + i];
+    HB_TRY(hb_add_primes(col.data(), nitems, dset[i].data(), (int)dset[i].size(), notin[i].data(), (int)notin[i].size()));
+    for (int j = i + 1; j < nd; j++) {  // digits[j] -= digits[i]; digits[j] /= pi  (src/DoubleCRT.cpp:551-556)
+      for (int it = 0; it < nitems; it++) col2[it] = digits[it * maxdig + j];
+      std::vector<u64> sc; HB_TRY(scalars_by_primes(c, dset[j].data(), (int)dset[j].size(), full[i].data(), (int)full[i].size(), 1, sc));
+      HB_TRY(pw_simple(HB_PW_SUBSCALE, col2.data(), col.data(), nitems, dset[j].data(), (int)dset[j].size(), sc.data(), c));
+    }
+  }
+  *ndig_out = nd;
+  return HB_OK;
+}
+
+extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                                   hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1) {
+  hb_ctx* c = nullptr;
+  HB_TRY(check_polys(out0, nitems, &c, "hb_keyswitch_digits")); HB_TRY(check_polys(out1, nitems, &c, "hb_keyswitch_digits"));
+  if (ndig <= 0 || ndig > HB_MAXDIG || ndig > maxdig) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits: ndig=%d out of range", ndig);
+  HB_TRY(check_polys(evk_a, ndig, &c, "hb_keyswitch_digits(evk_a)")); HB_TRY(check_polys(evk_b, ndig, &c, "hb_keyswitch_digits(evk_b)"));
+  HB_TRY(check_polys(digits, nitems * maxdig, &c, "hb_keyswitch_digits(digits)"));
+  HB_TRY(check_idx(c, idx, n, "hb_keyswitch_digits"));
+  return for_items(nitems, [&](int i0, int nit) {
+    for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+      int nr = std::min(HB_MAXROWS, n - r0);
+      HbKsJob J; memset(&J, 0, sizeof(J));
+      J.logN = c->logN; J.ndig = ndig; J.nitems = nit;
+      fill_rows(J.rows, idx + r0, nr);
+      for (int i = 0; i < ndig; i++) { J.evk_a[i] = evk_a[i]->d; J.evk_b[i] = evk_b[i]->d; }
+      for (int it = 0; it < nit; it++) {
+        J.out0[it] = out0[i0 + it]->d; J.out1[it] = out1[i0 + it]->d;
+        for (int i = 0; i < ndig; i++) J.dig[it][i] = digits[(i0 + it) * maxdig + i]->d;
+      }
+      unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
+      HB_LAUNCH(k_ks_inner, dim3(gx, nr, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+      HB_TRY(post_launch(c, "k_ks_inner"));
+    }
+    return HB_OK;
+  });
+}
+
+extern "C" int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1,
+                         hb_poly* const* o0, hb_poly* const* o1, hb_poly* const* o2, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr;
+  HB_TRY(check_polys(a0, nitems, &c, "hb_tensor")); HB_TRY(check_polys(a1, nitems, &c, "hb_tensor"));
+  HB_TRY(check_polys(b0, nitems, &c, "hb_tensor")); HB_TRY(check_polys(b1, nitems, &c, "hb_tensor"));
+  HB_TRY(check_polys(o0, nitems, &c, "hb_tensor")); HB_TRY(check_polys(o1, nitems, &c, "hb_tensor")); HB_TRY(check_polys(o2, nitems, &c, "hb_tensor"));
+  HB_TRY(check_idx(c, idx, n, "hb_tensor"));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64 *A0[HB_MAXB], *A1[HB_MAXB], *B0[HB_MAXB], *B1[HB_MAXB], *O0[HB_MAXB], *O1[HB_MAXB], *O2[HB_MAXB];
+    ptrs_of(a0, i0, nit, A0); ptrs_of(a1, i0, nit, A1); ptrs_of(b0, i0, nit, B0); ptrs_of(b1, i0, nit, B1);
+    ptrs_of(o0, i0, nit, O0); ptrs_of(o1, i0, nit, O1); ptrs_of(o2, i0, nit, O2);
+    PwArgs A; memset(&A, 0, sizeof(A));
+    A.op = HB_PW_TENSOR; A.dst = O0; A.dst1 = O1; A.dst2 = O2;
+    A.a = (const u64* const*)A0; A.b = (const u64* const*)A1; A.cc = (const u64* const*)B0; A.d = (const u64* const*)B1;
+    return launch_pw(c, A, nit, idx, n);
+  });
+}
+
+extern "C" int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, uint64_t k) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(dst, nitems, &c, "hb_automorph")); HB_TRY(check_polys(src, nitems, &c, "hb_automorph"));
+  HB_TRY(check_idx(c, idx, n, "hb_automorph"));
+  if ((k & 1) == 0 || k >= c->m) return hb_fail(HB_ERR_INDEX_SET, "DoubleCRT::automorph: k not in Zm*");  // src/DoubleCRT.cpp:1165-1167
+  for (int i = 0; i < nitems; i++) if (dst[i] == src[i]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph: dst must differ from src");
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* D[HB_MAXB]; u64* S[HB_MAXB]; ptrs_of(dst, i0, nit, D); ptrs_of(src, i0, nit, S);
+    PwArgs A; memset(&A, 0, sizeof(A));
+    A.op = HB_PW_AUTOMORPH; A.dst = D; A.a = (const u64* const*)S; A.k = k; A.m = c->m;
+    return launch_pw(c, A, nit, idx, n);
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// fused ciphertext-level paths
+extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* const* c2, int nitems,
+                              const int32_t* S, int nS, hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk) {
+  hb_ctx* c = nullptr;
+  HB_TRY(check_polys(c0, nitems, &c, "hb_relinearize")); HB_TRY(check_polys(c1, nitems, &c, "hb_relinearize")); HB_TRY(check_polys(c2, nitems, &c, "hb_relinearize"));
+  HB_TRY(check_idx(c, S, nS, "hb_relinearize"));
+  if (c->special.empty()) return hb_fail(HB_ERR_BAD_ARG, "hb_relinearize: context has no special primes");
+  const int maxdig = c->ndigits;
+  std::vector<hb_poly*> dig; HB_TRY(pool_get(c, nitems * maxdig, dig));
+  std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
+  // parts with handle 1 / base s: addPrimesAndScale(special)  (src/Ctxt.cpp:764-768)
+  HB_TRY(hb_add_primes_and_scale(c0, nitems, S, nS, c->special.data(), (int)c->special.size()));
+  HB_TRY(hb_add_primes_and_scale(c1, nitems, S, nS, c->special.data(), (int)c->special.size()));
+  // keySwitchPart (src/Ctxt.cpp:805-842)
+  int nd = 0;
+  HB_TRY(hb_break_into_digits(c2, nitems, S, nS, dig.data(), maxdig, &nd));
+  if (nd > ndig_evk) return hb_fail(HB_ERR_BAD_ARG, "hb_relinearize: key-switching matrix has %d columns, need %d", ndig_evk, nd);
+  return hb_keyswitch_digits(dig.data(), maxdig, nd, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0, c1);
+}
+
+extern "C" int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1, int nitems,
+                                    const int32_t* S_in, int nS_in, const int32_t* S, int nS, uint64_t ptxt_space,
+                                    hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk) {
+  hb_ctx* c = nullptr;
+  HB_TRY(check_polys(a0, nitems, &c, "hb_mul_relin_moddown")); HB_TRY(check_polys(a1, nitems, &c, "hb_mul_relin_moddown"));
+  HB_TRY(check_polys(b0, nitems, &c, "hb_mul_relin_moddown")); HB_TRY(check_polys(b1, nitems, &c, "hb_mul_relin_moddown"));
+  // bringToSet(common) on both operands: modDownToSet -> scaleDownToSet per part (src/Ctxt.cpp:393-562)
+  std::vector<hb_poly*> allp;
+  for (int i = 0; i < nitems; i++) { allp.push_back(a0[i]); allp.push_back(a1[i]); allp.push_back(b0[i]); allp.push_back(b1[i]); }
+  HB_TRY(hb_scale_down(allp.data(), (int)allp.size(), S_in, nS_in, S, nS, ptxt_space));
+  // tensorProduct in place: (a0,a1,b0) <- (a0*b0, a0*b1+a1*b0, a1*b1)   (src/Ctxt.cpp:1563-1608)
+  HB_TRY(hb_tensor(a0, a1, b0, b1, a0, a1, b0, nitems, S, nS));
+  // reLinearize (src/Ctxt.cpp:720-786)
+  HB_TRY(hb_relinearize(a0, a1, b0, nitems, S, nS, evk_a, evk_b, ndig_evk));
+  // drop the special primes again: modDownToSet(ctxtPrimes) (src/Ctxt.cpp:589-593)
+  std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
+  std::vector<hb_poly*> two;
+  for (int i = 0; i < nitems; i++) { two.push_back(a0[i]); two.push_back(a1[i]); }
+  return hb_scale_down(two.data(), (int)two.size(), Sp.data(), (int)Sp.size(), S, nS, ptxt_space);
+}

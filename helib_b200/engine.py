@@ -1,0 +1,241 @@
+"""ctypes binding of the C ABI in include/helib_b200.h (plumbing for tests and bench)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+vpp = C.POINTER(C.c_void_p)
+
+OPS = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "copy": 7}
+
+
+class HbError(RuntimeError):
+    """Raised for a negative return code of the C ABI; .code holds HB_ERR_*."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"helib_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libhelib_b200.so")
+
+
+def _declare(lib):
+    lib.hb_last_error.restype = C.c_char_p
+    lib.hb_poly_destroy.restype = None
+    lib.hb_ctx_destroy.restype = None
+    lib.hb_poly_destroy.argtypes = [C.c_void_p]
+    lib.hb_ctx_destroy.argtypes = [C.c_void_p]
+    return lib
+
+
+_LIB = None
+
+
+def load_library(path: str | None = None):
+    """Load the CUDA engine.  Fails loudly if the library has not been built."""
+    global _LIB
+    if path is not None:
+        return _declare(C.CDLL(path))
+    if _LIB is None:
+        p = library_path()
+        if not os.path.exists(p):
+            raise HbError(-3, f"{p} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "the engine has no CPU fallback")
+        _LIB = _declare(C.CDLL(p))
+    return _LIB
+
+
+def _idx(idx):
+    a = np.ascontiguousarray(np.asarray(list(idx), dtype=np.int32))
+    return a, a.ctypes.data_as(i32p), len(a)
+
+
+class Poly:
+    """A device DoubleCRT matrix [nprimes][N] (hb_poly)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        h = C.c_void_p()
+        eng._ck(eng.lib.hb_poly_create(eng.h, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.eng.h:
+                self.eng.lib.hb_poly_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def upload(self, dense, idx):
+        assert dense.dtype == np.uint64 and dense.flags["C_CONTIGUOUS"] and dense.shape == (self.eng.np, self.eng.N)
+        a, p, n = _idx(idx)
+        self.eng._ck(self.eng.lib.hb_poly_upload(self.h, p, n, dense.ctypes.data_as(u64p)))
+        return self
+
+    def download(self, idx, out=None):
+        if out is None:
+            out = np.zeros((self.eng.np, self.eng.N), dtype=np.uint64)
+        a, p, n = _idx(idx)
+        self.eng._ck(self.eng.lib.hb_poly_download(self.h, p, n, out.ctypes.data_as(u64p)))
+        return out
+
+
+def _arr(polys):
+    arr = (C.c_void_p * len(polys))(*[p.h for p in polys])
+    return arr
+
+
+class Engine:
+    """Device image of a prime chain + the DoubleCRT operations of the hot path."""
+
+    def __init__(self, m, primes, psis=None, digits=None, special=None, device=0, lib=None):
+        self.lib = lib if lib is not None else load_library()
+        self.m = int(m)
+        self.N = self.m // 2
+        self.primes = [int(q) for q in primes]
+        self.np = len(self.primes)
+        self.h = C.c_void_p()
+        q = np.array(self.primes, dtype=np.uint64)
+        ps = np.array([int(x) for x in psis], dtype=np.uint64) if psis is not None else None
+        self._ck(self.lib.hb_ctx_create(C.byref(self.h), int(device), C.c_uint64(self.m), self.np,
+                                        q.ctypes.data_as(u64p), ps.ctypes.data_as(u64p) if ps is not None else None))
+        out = np.zeros(self.np, dtype=np.uint64)
+        self._ck(self.lib.hb_ctx_get_psi(self.h, out.ctypes.data_as(u64p)))
+        self.psis = [int(x) for x in out]
+        self.digits = [list(d) for d in (digits or [])]
+        self.special = list(special or [])
+        if self.digits or self.special:
+            digit_of = np.full(self.np, -1, dtype=np.int32)
+            for d, lst in enumerate(self.digits):
+                for i in lst:
+                    digit_of[i] = d
+            sp = np.ascontiguousarray(np.array(self.special, dtype=np.int32))
+            self._ck(self.lib.hb_ctx_set_chain(self.h, digit_of.ctypes.data_as(i32p), len(self.digits),
+                                               sp.ctypes.data_as(i32p), len(sp)))
+
+    def close(self):
+        if self.h:
+            self.lib.hb_ctx_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HbError(rc, self.lib.hb_last_error().decode())
+
+    # ---- plumbing
+    def poly(self, dense=None, idx=None):
+        p = Poly(self)
+        if dense is not None:
+            p.upload(dense, idx)
+        return p
+
+    def sync(self):
+        self._ck(self.lib.hb_ctx_sync(self.h))
+
+    def stats(self):
+        out = np.zeros(3, dtype=np.uint64)
+        self._ck(self.lib.hb_ctx_stats(self.h, out.ctypes.data_as(u64p)))
+        return {"exact_fallbacks": int(out[0]), "launches": int(out[1]), "device_bytes": int(out[2])}
+
+    def reset_stats(self):
+        self._ck(self.lib.hb_ctx_reset_stats(self.h))
+
+    def mark_begin(self):
+        self._ck(self.lib.hb_ctx_mark_begin(self.h))
+
+    def mark_end(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.hb_ctx_mark_end(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- operations (lists of Poly = batch items)
+    def ntt_fwd(self, polys, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_ntt_fwd(_arr(polys), len(polys), p, n))
+
+    def ntt_inv(self, polys, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_ntt_inv(_arr(polys), len(polys), p, n))
+
+    def pointwise(self, op, dst, src, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_pointwise(OPS[op], _arr(dst), _arr(src), len(dst), p, n))
+
+    def scale_rows(self, polys, idx, scalars):
+        a, p, n = _idx(idx)
+        sc = np.array([int(s) for s in scalars], dtype=np.uint64)
+        self._ck(self.lib.hb_scale_rows(_arr(polys), len(polys), p, n, sc.ctypes.data_as(u64p)))
+
+    def scale_by_primes(self, polys, idx, fidx, inv=False):
+        a, p, n = _idx(idx)
+        b, pf, nf = _idx(fidx)
+        self._ck(self.lib.hb_scale_by_primes(_arr(polys), len(polys), p, n, pf, nf, int(inv)))
+
+    def zero_rows(self, polys, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_zero_rows(_arr(polys), len(polys), p, n))
+
+    def add_primes_and_scale(self, polys, cur, add):
+        a, pc, nc = _idx(cur)
+        b, pa, na = _idx(add)
+        self._ck(self.lib.hb_add_primes_and_scale(_arr(polys), len(polys), pc, nc, pa, na))
+
+    def add_primes(self, polys, cur, add):
+        a, pc, nc = _idx(cur)
+        b, pa, na = _idx(add)
+        self._ck(self.lib.hb_add_primes(_arr(polys), len(polys), pc, nc, pa, na))
+
+    def scale_down(self, polys, cur, keep, ptxt_space=1):
+        a, pc, nc = _idx(cur)
+        b, pk, nk = _idx(keep)
+        self._ck(self.lib.hb_scale_down(_arr(polys), len(polys), pc, nc, pk, nk, C.c_uint64(int(ptxt_space))))
+
+    def to_poly(self, poly, idx, positive=False, L=None):
+        a, p, n = _idx(idx)
+        L = L or (n + 1)
+        out = np.zeros((self.N, L), dtype=np.uint64)
+        self._ck(self.lib.hb_to_poly(poly.h, p, n, int(positive), out.ctypes.data_as(u64p), L))
+        return out
+
+    def break_into_digits(self, src, cur, digits=None):
+        """digits: list (per item) of lists (per digit) of Poly; allocated if None."""
+        a, pc, nc = _idx(cur)
+        maxdig = len(self.digits)
+        if digits is None:
+            digits = [[Poly(self) for _ in range(maxdig)] for _ in src]
+        flat = [d for item in digits for d in item]
+        nd = C.c_int()
+        self._ck(self.lib.hb_break_into_digits(_arr(src), len(src), pc, nc, _arr(flat), maxdig, C.byref(nd)))
+        return [item[:nd.value] for item in digits]
+
+    def keyswitch_digits(self, digits, idx, evk_a, evk_b, out0, out1):
+        a, p, n = _idx(idx)
+        nd = len(digits[0])
+        flat = [d for item in digits for d in item]
+        self._ck(self.lib.hb_keyswitch_digits(_arr(flat), nd, nd, len(digits), p, n, _arr(evk_a), _arr(evk_b), _arr(out0), _arr(out1)))
+
+    def tensor(self, a0, a1, b0, b1, o0, o1, o2, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_tensor(_arr(a0), _arr(a1), _arr(b0), _arr(b1), _arr(o0), _arr(o1), _arr(o2), len(a0), p, n))
+
+    def automorph(self, dst, src, idx, k):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_automorph(_arr(dst), _arr(src), len(dst), p, n, C.c_uint64(int(k))))
+
+    def relinearize(self, c0, c1, c2, S, evk_a, evk_b):
+        a, p, n = _idx(S)
+        self._ck(self.lib.hb_relinearize(_arr(c0), _arr(c1), _arr(c2), len(c0), p, n, _arr(evk_a), _arr(evk_b), len(evk_a)))
+
+    def mul_relin_moddown(self, a0, a1, b0, b1, S_in, S, ptxt_space, evk_a, evk_b):
+        x, pi, ni = _idx(S_in)
+        y, ps, ns = _idx(S)
+        self._ck(self.lib.hb_mul_relin_moddown(_arr(a0), _arr(a1), _arr(b0), _arr(b1), len(a0), pi, ni, ps, ns,
+                                               C.c_uint64(int(ptxt_space)), _arr(evk_a), _arr(evk_b), len(evk_a)))

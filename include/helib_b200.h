@@ -1,0 +1,134 @@
+/* helib_b200.h -- C ABI of the B200-native DoubleCRT / NTT / key-switch engine.
+ *
+ * This is the drop-in boundary for HElib's hot path.  HElib itself has no
+ * plugin/FFI seam above row granularity (src/intelExt.h:22-58 is per-row and CPU-only), so the
+ * boundary sits at the helib::DoubleCRT method level: each entry point below replaces the body of
+ * one DoubleCRT / Cmodulus / Ctxt method, cited as `reference: path:line` (paths relative to the
+ * HElib source tree, v2.2.0).
+ *
+ * Conventions
+ *  - Opaque handles.  The engine owns device memory; the caller owns host buffers.
+ *  - Every function returns 0 on success or a negative HB_ERR_* code; nothing throws across the
+ *    ABI.  hb_last_error() returns a thread-local message for the last failure.
+ *  - A device polynomial (hb_poly) is a dense matrix uint64[nprimes][N]: the row of chain prime i
+ *    holds canonical residues in [0, q_i) in HElib's evaluation order row[j] = f(psi_i^(2j+1))
+ *    (reference: src/CModulus.cpp:392-426, src/PAlgebra.cpp:535-540).  Which rows are live is
+ *    the caller's metadata (helib::IndexSet), passed to every call as an index list.
+ *  - Host-side dense matrices use the same [nprimes][N] layout; only the rows named by the index
+ *    list are read or written.
+ *  - Calls are stream-ordered on the context's CUDA stream and asynchronous unless stated;
+ *    hb_ctx_sync() or any download synchronises.  A context may be used by one host thread at a
+ *    time (the reference's DoubleCRT has the same value-semantic rule).
+ *  - There is no CPU fallback: without a CUDA device hb_ctx_create fails with HB_ERR_NO_DEVICE.
+ */
+#ifndef HELIB_B200_H
+#define HELIB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_BAD_ARG (-1)      /* helib::InvalidArgument / LogicError */
+#define HB_ERR_INDEX_SET (-2)    /* helib::RuntimeError: index-set precondition violated */
+#define HB_ERR_NO_DEVICE (-3)
+#define HB_ERR_CUDA (-4)
+#define HB_ERR_OOM (-5)
+#define HB_ERR_UNSUPPORTED (-6)
+
+#define HB_OP_ADD 0
+#define HB_OP_SUB 1
+#define HB_OP_MUL 2
+#define HB_OP_NEG 3
+#define HB_OP_COPY 7
+
+typedef struct hb_ctx hb_ctx;
+typedef struct hb_poly hb_poly;
+
+int hb_version(void);
+const char* hb_last_error(void);
+int hb_device_count(void);
+
+/* ---- context: the device image of helib::Context's prime chain ---------------------------
+ * reference: include/helib/Context.h:120-180 (moduli, smallPrimes/ctxtPrimes/specialPrimes,
+ * digits), src/CModulus.cpp:62-135 (per-prime tables).  m must be a power of two (phi(m)=m/2);
+ * q[i] are the chain primes in index order; psi[i] a primitive m-th root of unity mod q[i]
+ * (i.e. 2N-th root, N = m/2), or psi == NULL to let the engine derive one deterministically
+ * (smallest quadratic non-residue g, psi = g^((q-1)/m)). */
+int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi);
+void hb_ctx_destroy(hb_ctx* ctx);
+/* digit_of[i] = digit number of ctxt prime i or -1; special = indices of the special primes.
+ * reference: src/Context.cpp:902-928 (digits), :1014-1028 (special primes). */
+int hb_ctx_set_chain(hb_ctx* ctx, const int32_t* digit_of, int ndigits, const int32_t* special, int nspecial);
+int hb_ctx_get_psi(hb_ctx* ctx, uint64_t* psi_out);
+int hb_ctx_sync(hb_ctx* ctx);
+/* out[0] = exact-CRT fallback evaluations, out[1] = kernels launched, out[2] = bytes of device memory held */
+int hb_ctx_stats(hb_ctx* ctx, uint64_t* out3);
+int hb_ctx_reset_stats(hb_ctx* ctx);
+/* Launch-timing hooks for bench.py: elapsed GPU milliseconds on the context's stream between the
+ * two marks (CUDA events on the launching stream). */
+int hb_ctx_mark_begin(hb_ctx* ctx);
+int hb_ctx_mark_end(hb_ctx* ctx, float* ms_out);
+
+/* ---- device polynomials (helib::DoubleCRT storage, include/helib/DoubleCRT.h:87-94) ---- */
+int hb_poly_create(hb_ctx* ctx, hb_poly** out);          /* zero-filled [nprimes][N] */
+void hb_poly_destroy(hb_poly* p);
+int hb_poly_upload(hb_poly* p, const int32_t* idx, int n, const uint64_t* host_dense);
+int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t* host_dense);  /* synchronises */
+
+/* ---- per-prime transforms: Cmodulus::FFT / iFFT (src/CModulus.cpp:362-429, 486-553) -----
+ * In place on rows idx of each poly: coefficient rows (values in [0,q)) <-> evaluation rows. */
+int hb_ntt_fwd(hb_poly* const* polys, int nitems, const int32_t* idx, int n);
+int hb_ntt_inv(hb_poly* const* polys, int nitems, const int32_t* idx, int n);
+
+/* ---- row-wise ring operations: DoubleCRT::Op<Add|Sub|Mul>, Negate, operator=
+ * (src/DoubleCRT.cpp:216-384).  dst op= src on rows idx. */
+int hb_pointwise(int op, hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n);
+/* rows idx *= scalars[r] (already reduced mod q): DoubleCRT::Op(ZZ, MulFun) (src/DoubleCRT.cpp:339-361) */
+int hb_scale_rows(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const uint64_t* scalars);
+/* rows idx *= prod(q_k : k in fidx) or its inverse: DoubleCRT::operator/= (src/DoubleCRT.cpp:1122-1139) */
+int hb_scale_by_primes(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const int32_t* fidx, int nf, int inverse);
+int hb_zero_rows(hb_poly* const* polys, int nitems, const int32_t* idx, int n);
+
+/* DoubleCRT::addPrimesAndScale (src/DoubleCRT.cpp:603-647) */
+int hb_add_primes_and_scale(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd);
+/* DoubleCRT::addPrimes (src/DoubleCRT.cpp:565-599): exact base extension of rows cur to rows add */
+int hb_add_primes(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd);
+/* DoubleCRT::scaleDownToSet (src/DoubleCRT.cpp:1464-1516): rows keep <- (x - delta)/P, rows cur\keep dropped
+ * (left as garbage; the caller's index set shrinks).  ptxt_space = 1 for CKKS. */
+int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space);
+/* DoubleCRT::toPoly (src/DoubleCRT.cpp:925-1113): balanced (or positive) big integers,
+ * out[N][Lout] little-endian two's-complement limbs.  Synchronises. */
+int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, uint64_t* out_limbs, int Lout);
+/* DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:479-561).  src rows cur (ctxt primes only);
+ * digits[item*maxdig + i] receives digit i over cur | special.  *ndig_out = number of digits. */
+int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out);
+/* Ctxt::keySwitchDigits (src/Ctxt.cpp:191-230): out0 += sum_i D_i*b_i, out1 += sum_i D_i*a_i on rows idx.
+ * evk_a[i]: the expanded pseudo-random a_i rows (the reference regenerates them from prgSeed on
+ * every call, src/Ctxt.cpp:196-206; here they are expanded once by the host and cached). */
+int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                        hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1);
+/* Ctxt::tensorProduct of two canonical 2-part ciphertexts (src/Ctxt.cpp:1563-1608) */
+int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1,
+              hb_poly* const* o0, hb_poly* const* o1, hb_poly* const* o2, int nitems, const int32_t* idx, int n);
+/* DoubleCRT::automorph (src/DoubleCRT.cpp:1160-1202): dst[j] = src[idx(rep(j)*k mod m)], dst != src */
+int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, uint64_t k);
+
+/* ---- fused ciphertext-level paths (host orchestration of Ctxt::reLinearize / keySwitchPart,
+ * src/Ctxt.cpp:720-842, and Ctxt::multLowLvl + reLinearize + modDownToSet, src/Ctxt.cpp:393-562,
+ * 1681-1774) with explicit prime sets (the noise-driven choice stays in the host Ctxt layer).
+ * hb_relinearize: (c0,c1,c2) over ctxt primes S  ->  (c0,c1) over S | special   (c2 is consumed). */
+int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* const* c2, int nitems,
+                   const int32_t* S, int nS, hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk);
+/* hb_mul_relin_moddown: operands (a0,a1),(b0,b1) over S_in; mod-down both to S (ptxt_space),
+ * tensor, relinearise over S | special, mod-down the result to S.  Result in (a0,a1) rows S. */
+int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1, int nitems,
+                         const int32_t* S_in, int nS_in, const int32_t* S, int nS, uint64_t ptxt_space,
+                         hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELIB_B200_H */
