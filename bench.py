@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- Ctxt x Ctxt multiply (+ rescale, relinearise, mod-down) throughput on B200.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): CKKS m=2^17 (N=2^16),
+bits=1190, c=2 -> 20 ctxt + 10 special 60-bit primes ("L~30").  One *step* = one batch of B
+independent ciphertext pairs through the hot path
+    modDownToSet(20 -> 19 ctxt primes) of both operands  ->  tensorProduct  ->  reLinearize
+    (breakIntoDigits, keySwitchDigits over 29 rows)  ->  modDownToSet (drop the 10 special primes)
+with explicit prime sets and synthetic uniform residues (the path is data-oblivious).
+
+JSON line (one, rank 0): value = whole-job multiplies/s with operands resident in HBM; e2e = the
+same through the C ABI with pinned HOST buffers (H2D of the operands and D2H of the result inside
+the timed region); roofline = dominant kernel vs the measured HBM peak; cpu_baseline = the C++
+oracle (restated NTL-path HElib) on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {"name": "ckks_m2^17_bits1190_c2", "m": 1 << 17, "p": -1, "r": 1, "bits": 1190, "c": 2}
+SEED = 20260922 + 2  # Philox, seed = 20260922 + config index
+ROW_BYTES = (1 << 16) * 8
+
+
+def alg_bytes_per_mult(l_in, l, K, d):
+    """B_mul = 8N*[4*l_in + 2d(l+K) + 2l] (each input/evk/output row moved once)."""
+    return ROW_BYTES * (4 * l_in + 2 * d * (l + K) + 2 * l)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            seen = set()
+            for r in rows:
+                for k, nm in enumerate(names):
+                    if len(r) >= 9 and r[5 + k].strip().lower().startswith("active"):
+                        seen.add(nm)
+            out["reasons"] = sorted(seen)
+            out["samples"] = len(sm)
+        return out
+
+
+def oracle_setup(nthreads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import orc
+    import pyoracle as po
+    w = WORKLOAD
+    ch = po.build_mod_chain(w["m"], w["p"], w["r"], w["bits"], w["c"])
+    psis = [po.find_psi(q, ch.m) for q in ch.primes]
+    O = orc.Oracle(ch.phim, ch.m, ch.primes, psis, ch.digits, ch.special, nthreads=nthreads)
+    rng = np.random.Generator(np.random.Philox(SEED))
+    full = ch.ctxt + ch.special
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    ops = [O.random(rng, ch.ctxt) for _ in range(4)]
+    return ch, O, evk_a, evk_b, ops
+
+
+def oracle_one_mult(ch, O, evk_a, evk_b, ops):
+    """Host orchestration of Ctxt::multLowLvl + reLinearize + modDownToSet with explicit prime sets
+    (reference: src/Ctxt.cpp:393-562,720-786,1681-1774) over the C++ oracle."""
+    S_in, S = ch.ctxt, ch.ctxt[:-1]
+    Sp = sorted(S + ch.special)
+    parts = [x.copy() for x in ops]
+    for x in parts:
+        O.scale_down(x, S_in, S, 1)
+    t0, t1, t2 = O.tensor(*parts, S)
+    r0, r1 = O.relinearize(t0, t1, t2, S, evk_a, evk_b)
+    O.scale_down(r0, Sp, S, 1)
+    O.scale_down(r1, Sp, S, 1)
+    return r0, r1
+
+
+def time_oracle(steps, warmup, nthreads):
+    ch, O, evk_a, evk_b, ops = oracle_setup(nthreads)
+    for _ in range(warmup):
+        oracle_one_mult(ch, O, evk_a, evk_b, ops)
+    t = time.perf_counter()
+    for _ in range(steps):
+        oracle_one_mult(ch, O, evk_a, evk_b, ops)
+    dt = time.perf_counter() - t
+    return steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for this path (the C++ oracle: HElib itself
+    cannot be built here) on all host cores; each step = 1 multiply."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    v, dt = time_oracle(args.steps, max(1, min(args.warmup, 2)), cores)
+    l_in, l, K, d = 20, 19, 10, 2
+    line = {
+        "impl": "reference", "metric": "ctxt_mults_per_s", "value": v, "unit": "mult/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 (60-bit RNS limbs)", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "N": 1 << 16, "l_in": l_in, "l": l, "K": K, "digits": d, "batch": 1},
+        "cpu_baseline": {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} multiplies (1 per step), C++ oracle restating NTL-path HElib, threads across primes/coefficients"},
+        "e2e": {"value": v, "unit": "mult/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="independent ciphertext pairs per step and GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=6, help="multiplies timed for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    from helib_b200 import Chain, Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = WORKLOAD
+    ch = Chain(w["m"], w["p"], w["r"], w["bits"], w["c"])
+    assert (len(ch.ctxt), len(ch.special), len(ch.digits)) == (20, 10, 2), "chain shape differs from SURVEY section 8"
+    E = Engine(w["m"], ch.primes, None, ch.digits, ch.special, device=local)
+    N, npr = E.N, E.np
+    S_in, S = ch.ctxt, ch.ctxt[:-1]
+    full = ch.ctxt + ch.special
+    nd = len(ch.digits)
+    B = args.batch
+    rng = np.random.Generator(np.random.Philox(SEED + 1000 * rank))
+
+    def rand_dense(idx):
+        out = np.zeros((npr, N), dtype=np.uint64)
+        for i in idx:
+            out[i] = rng.integers(0, ch.primes[i], size=N, dtype=np.uint64)
+        return out
+
+    EA = [E.poly(rand_dense(full), full) for _ in range(nd)]
+    EB = [E.poly(rand_dense(full), full) for _ in range(nd)]
+    # pinned host staging (torch is plumbing for pinned memory only)
+    host_in = torch.empty((B, 4, npr, N), dtype=torch.int64, pin_memory=True)
+    host_out = torch.empty((B, 2, npr, N), dtype=torch.int64, pin_memory=True)
+    hin = host_in.numpy().view(np.uint64)
+    for b in range(B):
+        for k in range(4):
+            hin[b, k] = rand_dense(S_in)
+    polys = [[E.poly() for _ in range(4)] for _ in range(B)]
+
+    def upload_all():
+        for b in range(B):
+            for k in range(4):
+                polys[b][k].upload_ptr(host_in[b, k].data_ptr(), S_in)
+
+    def download_all():
+        for b in range(B):
+            for k in range(2):
+                polys[b][k].download_async_ptr(host_out[b, k].data_ptr(), S)
+
+    A0, A1, B0, B1 = ([polys[b][k] for b in range(B)] for k in range(4))
+
+    def step():
+        E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, 1, EA, EB)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    upload_all()
+    E.sync()
+    for _ in range(args.warmup):
+        step()
+    E.reset_stats()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    E.mark_begin()
+    for _ in range(args.steps):
+        step()
+    ms = E.mark_end()
+    barrier()
+    clocks = sampler.stop() if sampler else {}
+    st = E.stats()
+    launches = st["launches"]
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- e2e: host buffers -> H2D -> hot path -> D2H, every step
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            upload_all(); step(); download_all()
+        barrier()
+        E.mark_begin()
+        for _ in range(args.steps):
+            upload_all(); step(); download_all()
+        ems = E.mark_end()
+        barrier()
+        if world > 1:
+            t = torch.tensor([ems], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * B * args.steps / (ems / 1000.0), "unit": "mult/s",
+               "h2d_bytes_per_step": B * 4 * len(S_in) * ROW_BYTES, "d2h_bytes_per_step": B * 2 * len(S) * ROW_BYTES,
+               "ms_per_step": ems / args.steps}
+
+    # ---- per-kernel profile (one extra step bracketed by events per launch) -> roofline
+    peak, peak_kind = peaks()
+    E.profile(True)
+    step()
+    E.profile(False)
+    prof = sorted(E.profile_results(), key=lambda r: -r["ms"])
+    tot_ms = sum(r["ms"] for r in prof) or 1.0
+    roof = None
+    if prof:
+        top = prof[0]
+        ach = top["bytes"] / (top["ms"] / 1000.0) / 1e9
+        roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_kind": peak_kind, "traffic": None, "share_of_step": top["ms"] / tot_ms,
+                "launches_per_step": top["launches"], "avg_launch_ms": top["ms"] / top["launches"],
+                "alg_bytes_per_launch": top["bytes"] / top["launches"]}
+    kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot_ms, 4),
+                "alg_GBps": round(r["bytes"] / (r["ms"] / 1000.0) / 1e9, 1) if r["ms"] > 0 else None} for r in prof]
+
+    if rank != 0:
+        return
+    l_in, l, K, d = len(S_in), len(S), len(ch.special), nd
+    bmul = alg_bytes_per_mult(l_in, l, K, d)
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, dt = time_oracle(args.cpu_sample, 1, cores)
+        cpu = {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} multiplies of the same workload (batch 1), C++ oracle restating NTL-path HElib, {cores} threads, {dt:.1f}s"}
+    line = {
+        "metric": "ctxt_mults_per_s", "value": value, "unit": "mult/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (60-bit RNS limbs)", "data": "synthetic",
+        "config": {"workload": w["name"], "N": N, "l_in": l_in, "l": l, "K": K, "digits": d, "batch_per_gpu": B,
+                   "sharding": "independent ciphertexts per rank, no data-path collective",
+                   "l2": f"inputs larger than L2 ({B * 4 * l_in * ROW_BYTES / 2**20:.0f} MiB of operands per step)",
+                   "alg_bytes_per_mult": bmul},
+        "alg_roofline": {"achieved_GBps": value / world * bmul / 1e9, "peak_GBps": peak, "frac": value / world * bmul / 1e9 / peak, "peak_kind": peak_kind},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        "exact_crt_fallbacks": st["exact_fallbacks"],
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ binding used by the tests, bench.py and __graft_entry__.py.  There is no CPU fal
 works anywhere, but creating an Engine without a CUDA device (or without the built library)
 raises.
 """
-from .engine import Engine, Poly, HbError, load_library, library_path  # noqa: F401
+from .engine import Engine, Poly, Chain, HbError, load_library, library_path  # noqa: F401
 from .build import build_library  # noqa: F401
 
-__all__ = ["Engine", "Poly", "HbError", "load_library", "library_path", "build_library"]
+__all__ = ["Engine", "Poly", "Chain", "HbError", "load_library", "library_path", "build_library"]

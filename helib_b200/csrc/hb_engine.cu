@@ -69,6 +69,12 @@ struct hb_ctx {
   size_t bytes; u64 launches;
   cudaEvent_t ev0, ev1;
   size_t max_smem;
+  // optional per-launch profiling (bench.py): CUDA events around every kernel launch
+  bool profiling;
+  struct ProfRec { const char* name; cudaEvent_t a, b; u64 bytes; };
+  std::vector<ProfRec> prof_pending;
+  struct ProfAgg { std::string name; u64 launches; double ms; u64 bytes; };
+  std::vector<ProfAgg> prof;
 };
 struct hb_poly { hb_ctx* ctx; u64* d; };
 
@@ -85,10 +91,28 @@ static int ctx_scratch(hb_ctx* c) {
   HB_TRY(ctx_alloc(c, (void**)&c->tmpB, sz));
   return HB_OK;
 }
-static int post_launch(hb_ctx* c, const char* what) {
+static void pre_launch(hb_ctx* c) {
+#ifndef HB_SIM
+  if (c->profiling) {
+    hb_ctx::ProfRec r; r.name = nullptr; r.bytes = 0;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, c->stream);
+    c->prof_pending.push_back(r);
+  }
+#endif
+}
+// bytes = algorithmic HBM bytes of this launch (rows read once + rows written once)
+static int post_launch(hb_ctx* c, const char* what, u64 bytes = 0) {
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return hb_fail(HB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+#ifndef HB_SIM
+  if (c->profiling && !c->prof_pending.empty()) {
+    hb_ctx::ProfRec& r = c->prof_pending.back();
+    r.name = what; r.bytes = bytes;
+    cudaEventRecord(r.b, c->stream);
+  }
+#endif
   return HB_OK;
 }
 
@@ -119,7 +143,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->logN = 0; while (((size_t)1 << c->logN) < c->N) c->logN++;
   c->log_blk = c->logN >= 11 ? 8 : 0;
   c->tmpA = c->tmpB = nullptr; c->bytes = 0; c->launches = 0; c->ndigits = 0;
-  c->d_primes = nullptr; c->d_tw = nullptr; c->d_stats = nullptr;
+  c->d_primes = nullptr; c->d_tw = nullptr; c->d_stats = nullptr; c->profiling = false;
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
   const size_t N = c->N;
@@ -293,6 +317,50 @@ extern "C" int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t*
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return HB_OK;
 }
+extern "C" int hb_poly_download_async(hb_poly* p, const int32_t* idx, int n, uint64_t* host) {
+  if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_download_async: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_poly_download_async"));
+  for (int j = 0; j < n; j++) {
+    size_t off = (size_t)idx[j] * c->N;
+    HB_CUDA(cudaMemcpyAsync(host + off, p->d + off, c->N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return HB_OK;
+}
+static int prof_collect(hb_ctx* c) {
+#ifndef HB_SIM
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_pending) {
+    float ms = 0.f;
+    if (r.name) {
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      bool found = false;
+      for (auto& a : c->prof) if (a.name == r.name) { a.launches++; a.ms += ms; a.bytes += r.bytes; found = true; break; }
+      if (!found) c->prof.push_back({r.name, 1, (double)ms, r.bytes});
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  c->prof_pending.clear();
+#endif
+  return HB_OK;
+}
+extern "C" int hb_ctx_profile(hb_ctx* c, int enable) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_profile: null");
+  HB_TRY(prof_collect(c));
+  if (enable && !c->profiling) c->prof.clear();
+  c->profiling = enable != 0;
+  return HB_OK;
+}
+extern "C" int hb_ctx_profile_get(hb_ctx* c, int i, char* name, int namelen, uint64_t* launches, double* ms, uint64_t* bytes) {
+  if (!c || !name || namelen <= 0) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_profile_get: null");
+  HB_TRY(prof_collect(c));
+  if (i < 0 || i >= (int)c->prof.size()) return HB_ERR_BAD_ARG;
+  snprintf(name, namelen, "%s", c->prof[i].name.c_str());
+  if (launches) *launches = c->prof[i].launches;
+  if (ms) *ms = c->prof[i].ms;
+  if (bytes) *bytes = c->prof[i].bytes;
+  return HB_OK;
+}
 static int pool_get(hb_ctx* c, int n, std::vector<hb_poly*>& out) {
   while ((int)c->pool.size() < n) { hb_poly* p; HB_TRY(hb_poly_create(c, &p)); c->pool.push_back(p); }
   out.assign(c->pool.begin(), c->pool.begin() + n);
@@ -320,8 +388,9 @@ static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst
     J.nitems = nitems;
     for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
     dim3 grid(1u << (n1 - lwb), nr, nitems);
-    if (dir > 0) { HB_LAUNCH(k_fwd_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_fwd_blk")); }
-    else { HB_LAUNCH(k_inv_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_blk")); }
+    pre_launch(c);
+    if (dir > 0) { HB_LAUNCH(k_fwd_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k_fwd_blk_subscale" : "k_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
+    else { HB_LAUNCH(k_inv_blk, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
 }
@@ -337,8 +406,9 @@ static int launch_cols(hb_ctx* c, int dir, const u64* const* src, u64* const* ds
     J.nitems = nitems;
     for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
     dim3 grid(1u << (c->log_blk - lw), nr, nitems);
-    if (dir > 0) { HB_LAUNCH(k_fwd_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_fwd_cols")); }
-    else { HB_LAUNCH(k_inv_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_cols")); }
+    pre_launch(c);
+    if (dir > 0) { HB_LAUNCH(k_fwd_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_fwd_cols", (u64)2 * nr * nitems * c->N * 8)); }
+    else { HB_LAUNCH(k_inv_cols, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k_inv_cols", (u64)2 * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
 }
@@ -368,8 +438,11 @@ static int launch_pw(hb_ctx* c, const PwArgs& A, int nitems, const int32_t* idx,
     }
     unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
     dim3 grid(gx, nr, nitems);
+    static const int rw[] = {3, 3, 3, 2, 2, 3, 1, 2, 7, 2};  // rows moved per element, by op
+    static const char* nm[] = {"k_pw_add", "k_pw_sub", "k_pw_mul", "k_pw_neg", "k_pw_scale", "k_pw_subscale", "k_pw_zero", "k_pw_copy", "k_pw_tensor", "k_pw_automorph"};
+    pre_launch(c);
     HB_LAUNCH(k_pointwise, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
-    HB_TRY(post_launch(c, "k_pointwise"));
+    HB_TRY(post_launch(c, nm[A.op], (u64)rw[A.op] * nr * nitems * c->N * 8));
   }
   return HB_OK;
 }
@@ -484,8 +557,9 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   J.cv = E->d; J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw; J.nitems = nit; J.stats = c->d_stats;
   for (int i = 0; i < nit; i++) { J.src[i] = tA[i]; J.dst[i] = tB[i]; }
   dim3 grid(1u << (c->log_blk - lw), nit);
+  pre_launch(c);
   HB_LAUNCH(k_conv, grid, dim3(HB_THREADS), smem, c->stream, c->d_primes, J);
-  return post_launch(c, "k_conv");
+  return post_launch(c, "k_conv", (u64)(n + nt) * nit * c->N * 8);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -616,8 +690,9 @@ extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, u
   HbCrtJob J; J.cv = E->d; J.N = (int)c->N; J.Lout = Lout; J.positive = positive; J.src = c->tmpB; J.out = d_out;
   HbCrtTabs T; T.t = E->d_t; T.t_s = E->d_t_s;
   dim3 grid((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS));
+  pre_launch(c);
   HB_LAUNCH(k_crt, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J, T);
-  int r = post_launch(c, "k_crt");
+  int r = post_launch(c, "k_crt", (u64)(n + Lout) * c->N * 8);
   if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_to_poly: copy failed: %s", cudaGetErrorString(e)); }
   cudaFree(d_out);
   return r;
@@ -683,8 +758,10 @@ extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig,
         for (int i = 0; i < ndig; i++) J.dig[it][i] = digits[(i0 + it) * maxdig + i]->d;
       }
       unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
+      pre_launch(c);
       HB_LAUNCH(k_ks_inner, dim3(gx, nr, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
-      HB_TRY(post_launch(c, "k_ks_inner"));
+      // reads ndig digit rows + out0,out1 per item, 2*ndig evk rows once; writes out0,out1
+      HB_TRY(post_launch(c, "k_ks_inner", ((u64)(ndig + 4) * nit + 2 * ndig) * nr * c->N * 8));
     }
     return HB_OK;
   });

@@ -80,6 +80,15 @@ class Poly:
         self.eng._ck(self.eng.lib.hb_poly_upload(self.h, p, n, dense.ctypes.data_as(u64p)))
         return self
 
+    def upload_ptr(self, ptr, idx):
+        """Upload from a raw host pointer to a dense [nprimes][N] matrix (e.g. pinned memory)."""
+        a, p, n = _idx(idx)
+        self.eng._ck(self.eng.lib.hb_poly_upload(self.h, p, n, C.cast(ptr, u64p)))
+
+    def download_async_ptr(self, ptr, idx):
+        a, p, n = _idx(idx)
+        self.eng._ck(self.eng.lib.hb_poly_download_async(self.h, p, n, C.cast(ptr, u64p)))
+
     def download(self, idx, out=None):
         if out is None:
             out = np.zeros((self.eng.np, self.eng.N), dtype=np.uint64)
@@ -155,6 +164,20 @@ class Engine:
         ms = C.c_float()
         self._ck(self.lib.hb_ctx_mark_end(self.h, C.byref(ms)))
         return ms.value
+
+    def profile(self, enable: bool):
+        self._ck(self.lib.hb_ctx_profile(self.h, int(enable)))
+
+    def profile_results(self):
+        out, i = [], 0
+        while True:
+            name = C.create_string_buffer(64)
+            n, ms, by = C.c_uint64(), C.c_double(), C.c_uint64()
+            if self.lib.hb_ctx_profile_get(self.h, i, name, 64, C.byref(n), C.byref(ms), C.byref(by)) != 0:
+                break
+            out.append({"kernel": name.value.decode(), "launches": n.value, "ms": ms.value, "bytes": by.value})
+            i += 1
+        return out
 
     # ---- operations (lists of Poly = batch items)
     def ntt_fwd(self, polys, idx):
@@ -239,3 +262,53 @@ class Engine:
         y, ps, ns = _idx(S)
         self._ck(self.lib.hb_mul_relin_moddown(_arr(a0), _arr(a1), _arr(b0), _arr(b1), len(a0), pi, ni, ps, ns,
                                                C.c_uint64(int(ptxt_space)), _arr(evk_a), _arr(evk_b), len(evk_a)))
+
+
+class Chain:
+    """Host-side prime chain (hb_chain): helib::Context::buildModChain reproduced in C++."""
+
+    def __init__(self, m, p, r, bits, c, sk_hwt=0, resolution=3, bits_in_special=0, stdev=3.2, lib=None):
+        self.lib = lib if lib is not None else load_library()
+        self.lib.hb_chain_last_error.restype = C.c_char_p
+        self.lib.hb_chain_destroy.restype = None
+        self.lib.hb_chain_destroy.argtypes = [C.c_void_p]
+        self.h = C.c_void_p()
+        rc = self.lib.hb_chain_build(C.byref(self.h), C.c_uint64(m), C.c_int64(p), int(r), int(bits), int(c),
+                                     int(sk_hwt), int(resolution), int(bits_in_special), C.c_double(stdev))
+        if rc != 0:
+            raise HbError(rc, self.lib.hb_chain_last_error().decode())
+        n = [C.c_int() for _ in range(5)]
+        phim = C.c_int64()
+        self.lib.hb_chain_info(self.h, *[C.byref(x) for x in n], C.byref(phim))
+        self.m, self.p, self.r, self.phim = int(m), int(p), int(r), phim.value
+        npr = n[0].value
+        primes = np.zeros(npr, dtype=np.uint64)
+        kind = np.zeros(npr, dtype=np.int32)
+        dig = np.zeros(npr, dtype=np.int32)
+        self.lib.hb_chain_get(self.h, primes.ctypes.data_as(u64p), kind.ctypes.data_as(i32p), dig.ctypes.data_as(i32p))
+        self.primes = [int(q) for q in primes]
+        self.small = [i for i in range(npr) if kind[i] == 0]
+        self.ctxt = [i for i in range(npr) if kind[i] == 1]
+        self.special = [i for i in range(npr) if kind[i] == 2]
+        self.digits = [[i for i in range(npr) if dig[i] == d] for d in range(n[4].value)]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.hb_chain_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set4size(self, low, high, from1, from2=None, reverse=False):
+        a, p1, n1 = _idx(from1)
+        out = np.zeros(len(self.primes), dtype=np.int32)
+        nout = C.c_int()
+        if from2 is None:
+            rc = self.lib.hb_chain_set4size(self.h, C.c_double(low), C.c_double(high), p1, n1, None, 0, int(reverse), out.ctypes.data_as(i32p), C.byref(nout))
+        else:
+            b, p2, n2 = _idx(from2)
+            rc = self.lib.hb_chain_set4size(self.h, C.c_double(low), C.c_double(high), p1, n1, p2, n2, int(reverse), out.ctypes.data_as(i32p), C.byref(nout))
+        if rc != 0:
+            raise HbError(rc, "hb_chain_set4size")
+        return [int(x) for x in out[:nout.value]]

@@ -71,12 +71,18 @@ int hb_ctx_reset_stats(hb_ctx* ctx);
  * two marks (CUDA events on the launching stream). */
 int hb_ctx_mark_begin(hb_ctx* ctx);
 int hb_ctx_mark_end(hb_ctx* ctx, float* ms_out);
+/* Per-kernel profile for the roofline report: while enabled, every launch is bracketed by CUDA
+ * events on the launching stream.  hb_ctx_profile_get(i, ...) returns HB_ERR_BAD_ARG past the end.
+ * bytes = algorithmic HBM bytes (each row read once / written once) summed over the launches. */
+int hb_ctx_profile(hb_ctx* ctx, int enable);
+int hb_ctx_profile_get(hb_ctx* ctx, int i, char* name, int namelen, uint64_t* launches, double* ms, uint64_t* bytes);
 
 /* ---- device polynomials (helib::DoubleCRT storage, include/helib/DoubleCRT.h:87-94) ---- */
 int hb_poly_create(hb_ctx* ctx, hb_poly** out);          /* zero-filled [nprimes][N] */
 void hb_poly_destroy(hb_poly* p);
 int hb_poly_upload(hb_poly* p, const int32_t* idx, int n, const uint64_t* host_dense);
 int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t* host_dense);  /* synchronises */
+int hb_poly_download_async(hb_poly* p, const int32_t* idx, int n, uint64_t* host_dense); /* stream-ordered; hb_ctx_sync() before reading */
 
 /* ---- per-prime transforms: Cmodulus::FFT / iFFT (src/CModulus.cpp:362-429, 486-553) -----
  * In place on rows idx of each poly: coefficient rows (values in [0,q)) <-> evaluation rows. */

@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU session: smoke, gpu tests, bench, ncu launch list, ncu full capture of the top kernels.
+# Usage (through gpurun): bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+echo "== smoke" ; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke_$TAG.log
+echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu_$TAG.log
+echo "== bench" ; timeout 900 python bench.py --steps 10 --warmup 3 2> $OUT/bench_$TAG.err | tee $OUT/bench_$TAG.json | cut -c1-1500
+tail -5 $OUT/bench_$TAG.err
+echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tee $OUT/bench_ref_$TAG.json | cut -c1-300
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
+   python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu --no-e2e > $OUT/ncu_bench_$TAG.log 2>&1
+tail -2 $OUT/ncu_bench_$TAG.log | cut -c1-300
+echo "== ncu full: k_conv / k_fwd_blk / k_inv_blk"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_conv|k_fwd_blk|k_inv_blk|k_ks_inner' -s 30 -c 8 -f -o $OUT/prof_$TAG \
+   python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
+tail -2 $OUT/ncu_full_$TAG.log | cut -c1-300
+ls -la $OUT
+fi

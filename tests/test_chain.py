@@ -1,0 +1,127 @@
+"""Prime chain: product C++ (hb_chain_build) vs the Python restatement, plus known answers.
+
+Host-only code: runs against the real libhelib_b200.so (no device needed for the chain ABI).
+"""
+import ctypes
+import math
+
+import pytest
+
+import pyoracle as po
+from helib_b200 import Chain, HbError, load_library, library_path
+
+CONFIGS = {
+    "cfg1_bgv_m4096": (4096, 257, 1, 60, 2),
+    "cfg2_ckks_2^17_1190": (1 << 17, -1, 1, 1190, 2),
+    "cfg3_bgv_2^17_1500_c3": (1 << 17, 257, 1, 1500, 3),
+    "cfg4_ckks_2^17_1700": (1 << 17, -1, 1, 1700, 2),
+    "bgv_m64": (64, 257, 1, 120, 2),
+    "bgv_p17r2": (2048, 17, 2, 150, 3),
+    "ckks_8192": (8192, -1, 1, 119, 2),
+    "thinboot_m21845_chain_only": (21845, 2, 1, 580, 2),   # non power of two: chain logic only
+}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return load_library()
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_chain_matches_python_restatement(lib, name):
+    m, p, r, bits, c = CONFIGS[name]
+    ref = po.build_mod_chain(m, p, r, bits, c)
+    ch = Chain(m, p, r, bits, c, lib=lib)
+    assert ch.primes == ref.primes
+    assert (ch.small, ch.ctxt, ch.special) == (ref.small, ref.ctxt, ref.special)
+    assert ch.digits == ref.digits
+    assert ch.phim == ref.phim
+
+
+def test_survey_shapes():
+    """SURVEY.md section 8 header: the shapes the reference's chain logic yields."""
+    ch = po.build_mod_chain(1 << 17, -1, 1, 1190, 2)
+    assert (len(ch.small), len(ch.ctxt), len(ch.special)) == (6, 20, 10)
+    assert [len(d) for d in ch.digits] == [10, 10]
+    assert [q.bit_length() for q in ch.primes[:6]] == [40, 40, 48, 51, 54, 57]
+    ch = po.build_mod_chain(1 << 17, 257, 1, 1500, 3)
+    assert (len(ch.ctxt), len(ch.special), [len(d) for d in ch.digits]) == (26, 9, [9, 9, 8])
+    assert ch.primes[ch.ctxt[0]].bit_length() == 58 and ch.primes[ch.special[0]].bit_length() == 56
+    ch = po.build_mod_chain(1 << 17, -1, 1, 1700, 2)
+    assert (len(ch.ctxt), len(ch.special)) == (29, 15)
+    ch = po.build_mod_chain(4096, 257, 1, 60, 2)
+    assert (len(ch.small), len(ch.ctxt), len(ch.special)) == (6, 2, 1)
+
+
+def test_prime_generator_known_answers():
+    """SURVEY.md section 9.12 known answers (restated rule + independent primality test)."""
+    assert po.PrimeGenerator(60, 1 << 17).next() == 237 * 2**52 + 1 == 1067353111686807553
+    assert po.PrimeGenerator(40, 1 << 17).next() == 113 * 2**33 + 1 == 970662608897
+    assert po.PrimeGenerator(58, 1 << 17).next() == 280349076803813377
+    assert po.PrimeGenerator(54, 4096).next() == 16044073672507393
+    sympy = pytest.importorskip("sympy")
+    g = po.PrimeGenerator(60, 1 << 17)
+    for _ in range(5):
+        q = g.next()
+        assert sympy.isprime(q) and (q - 1) % (1 << 17) == 0
+        assert (1 << 60) - (1 << 57) <= q < (1 << 60)
+
+
+def test_ctxt_primes_bits_within_4_percent():
+    """reference: tests/TestContext.cpp:205-225 (buildModChain(1016, c=2): total ctxt bits within 4%)."""
+    ch = po.build_mod_chain(8192, 3, 1, 1016, 2)
+    total = sum(math.log2(ch.primes[i]) for i in ch.ctxt)
+    assert 1016 - 0.5 <= total <= 1016 * 1.04
+
+
+def test_digit_count_clipped(lib):
+    """reference: tests/TestContext.cpp:249-306 (number of digits clipped to #ctxt primes)."""
+    ch = Chain(64, 257, 1, 50, 5, lib=lib)
+    assert len(ch.digits) <= len(ch.ctxt)
+
+
+def test_bad_arguments(lib):
+    with pytest.raises(HbError):
+        Chain(4096, 2, 1, 60, 2, lib=lib)      # p divides m (src/PAlgebra.cpp:458)
+    with pytest.raises(HbError):
+        Chain(4096, 257, 1, 0, 2, lib=lib)     # nBits < 1 (src/Context.cpp:1044-1046)
+
+
+def test_set4size_prefers_fewest_dropped(lib):
+    m, p, r, bits, c = CONFIGS["cfg2_ckks_2^17_1190"]
+    ch = Chain(m, p, r, bits, c, lib=lib)
+    full = ch.ctxt
+    logq = sum(math.log(ch.primes[i]) for i in full)
+    lo = logq - 1.5 * math.log(ch.primes[full[-1]])
+    got = ch.set4size(lo, lo + 4 * math.log(2), full, full, reverse=True)
+    size = sum(math.log(ch.primes[i]) for i in got)
+    assert lo <= size <= lo + 4 * math.log(2)
+    assert set(i for i in got if i in ch.ctxt) == set(ch.ctxt[:len([i for i in got if i in ch.ctxt])])  # prefix of ctxt primes
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The C-ABI library loads here (no GPU) and exports every symbol include/*.h declares."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = ctypes.CDLL(library_path())
+    names = set()
+    for h in ("helib_b200.h", "helib_b200_chain.h"):
+        src = open(os.path.join(root, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", src))
+    assert len(names) > 30
+    for n in sorted(names):
+        assert hasattr(lib, n), f"missing export {n}"
+    assert lib.hb_device_count() == 0 or lib.hb_device_count() > 0
+
+
+def test_no_device_fails_loudly(lib):
+    """No CPU fallback: without a CUDA device the engine refuses to create a context."""
+    if lib.hb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from helib_b200 import Engine
+    ch = po.build_mod_chain(64, 257, 1, 120, 2)
+    with pytest.raises(HbError) as ei:
+        Engine(64, ch.primes, lib=lib)
+    assert ei.value.code == -3   # HB_ERR_NO_DEVICE

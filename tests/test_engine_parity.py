@@ -169,3 +169,58 @@ def test_mul_relin_moddown(lib, cfg):
     for it, o in enumerate(ops):
         r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, p, evk_a, evk_b)
         assert rows_equal(A0[it].download(S), r0, S) and rows_equal(A1[it].download(S), r1, S)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes (N = 2^16): direct bit-exact parity (the C++ oracle finishes these in
+# seconds) plus size-independent properties.  GPU only.
+
+@pytest.mark.gpu
+def test_full_size_config2_mul_relin_moddown(cuda_lib):
+    cfg = (1 << 17, -1, 1, 1190, 2)
+    ch, psis, O, E = make(cuda_lib, *cfg, nthreads=8)
+    assert (len(ch.ctxt), len(ch.special)) == (20, 10)
+    rng = np.random.default_rng(7)
+    full = ch.ctxt + ch.special
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    S_in, S = ch.ctxt, ch.ctxt[:-1]
+    ops = [[O.random(rng, S_in) for _ in range(4)] for _ in range(2)]
+    A0, A1, B0, B1 = ([E.poly(o[k], S_in) for o in ops] for k in range(4))
+    E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, 1, EA, EB)
+    for it, o in enumerate(ops):
+        r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, 1, evk_a, evk_b)
+        assert rows_equal(A0[it].download(S), r0, S) and rows_equal(A1[it].download(S), r1, S)
+    # round trip at full size
+    x = O.random(rng, full)
+    P = E.poly(x, full)
+    E.ntt_inv([P], full); E.ntt_fwd([P], full)
+    assert rows_equal(P.download(full), x, full)
+
+
+@pytest.mark.gpu
+def test_full_size_config3_relinearize_bgv(cuda_lib):
+    cfg = (1 << 17, 257, 1, 1500, 3)
+    ch, psis, O, E = make(cuda_lib, *cfg, nthreads=8)
+    assert (len(ch.ctxt), len(ch.special), [len(d) for d in ch.digits]) == (26, 9, [9, 9, 8])
+    rng = np.random.default_rng(8)
+    full = ch.ctxt + ch.special
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    S = ch.ctxt
+    Sp = sorted(S + ch.special)
+    c0, c1, c2 = (O.random(rng, S) for _ in range(3))
+    C0, C1, C2 = E.poly(c0, S), E.poly(c1, S), E.poly(c2, S)
+    E.relinearize([C0], [C1], [C2], S, EA, EB)
+    r0, r1 = O.relinearize(c0, c1, c2, S, evk_a, evk_b)
+    assert rows_equal(C0.download(Sp), r0, Sp) and rows_equal(C1.download(Sp), r1, Sp)
+    # mod-down with the BGV correction at full size
+    E.scale_down([C0, C1], Sp, S, 257)
+    O.scale_down(r0, Sp, S, 257); O.scale_down(r1, Sp, S, 257)
+    assert rows_equal(C0.download(S), r0, S) and rows_equal(C1.download(S), r1, S)
