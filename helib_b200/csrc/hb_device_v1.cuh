@@ -1,0 +1,412 @@
+// hb_device_v1.cuh -- register-blocked transform kernels (the fast path for N >= 2^12).
+//
+// A 256-point sub-transform (either phase of the N = N1 x 256 split) is done as radix-16 x
+// radix-16: each thread holds 16 residues in registers, runs 4 butterfly stages (Harvey lazy
+// butterflies, Shoup twiddles, values kept in [0,4q) forward / [0,2q) inverse), exchanges through
+// a padded shared-memory tile (row stride 17, block stride 273: conflict-free for 64-bit
+// accesses), and runs the other 4 stages.  Values crossing a kernel boundary are canonical.
+//
+//   k1_fwd_blk / k1_inv_blk : "blk" phases, 16 blocks (= 16 adjacent natural-order outputs,
+//                             128-byte segments) per CTA, twiddles kept in registers across the
+//                             batch-item loop.                       needs log_blk = 8, n1 >= 4
+//   k1_fwd_cols/k1_inv_cols : "cols" phases, 16 columns per CTA.     needs n1 = 8 (N = 2^16)
+//   k1_conv                 : fused iNTT-cols -> exact CRT -> NTT-cols with 64-thread groups
+//                             working on different rows concurrently.  needs n1 = 8
+#pragma once
+#include "hb_device.cuh"
+
+#define HB1_RS 17     // row stride inside a 256-element transform tile
+#define HB1_BS 273    // tile stride (16*17 + 1)
+
+__device__ __forceinline__ void hb_group_sync(int group, int nthreads) {
+#ifdef HB_SIM
+  cusim::bar_sync(1 + group, nthreads);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(nthreads) : "memory");
+#endif
+}
+
+// (hi,lo) += a*b with an explicit carry chain
+__device__ __forceinline__ void hb1_mac128(u64& hi, u64& lo, u64 a, u64 b) {
+#ifdef HB_SIM
+  hb_mac128(hi, lo, a, b);
+#else
+  asm("{\n\t.reg .u64 pl, ph;\n\t"
+      "mul.lo.u64 pl, %2, %3;\n\t"
+      "mul.hi.u64 ph, %2, %3;\n\t"
+      "add.cc.u64 %0, %0, pl;\n\t"
+      "addc.u64 %1, %1, ph;\n\t}"
+      : "+l"(lo), "+l"(hi)
+      : "l"(a), "l"(b));
+#endif
+}
+
+// Cooley-Tukey butterfly, x,y in [0,4q) -> [0,4q)
+__device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, u64 q, u64 q2) {
+  u64 xr = x >= q2 ? x - q2 : x;
+  u64 t = hb_mul_shoup_lazy(y, w, ws, q);
+  x = xr + t;
+  y = xr - t + q2;
+}
+// Gentleman-Sande butterfly, x,y in [0,2q) -> [0,2q)
+__device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, u64 q, u64 q2) {
+  u64 s = x + y;
+  u64 d = x - y + q2;
+  x = s >= q2 ? s - q2 : s;
+  y = hb_mul_shoup_lazy(d, w, ws, q);
+}
+__device__ __forceinline__ u64 hb1_canon4(u64 x, u64 q, u64 q2) {  // [0,4q) -> [0,q)
+  if (x >= q2) x -= q2;
+  if (x >= q) x -= q;
+  return x;
+}
+__device__ __forceinline__ u64 hb1_canon2(u64 x, u64 q) { return x >= q ? x - q : x; }
+
+// 4 forward stages on 16 registers; twiddle of stage k (distance 8>>k), group g is tw[(1<<k)-1+g]
+struct Hb1TwReg {
+  ulonglong2 t[15];
+  __device__ __forceinline__ ulonglong2 get(int k, int g) const { return t[(1 << k) - 1 + g]; }
+};
+// twiddles read through a pointer per stage (uniform/broadcast loads or shared memory)
+struct Hb1TwPtr {
+  const ulonglong2* p[4];
+  __device__ __forceinline__ ulonglong2 get(int k, int g) const { return p[k][g]; }
+};
+template <class TW>
+__device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 q, u64 q2) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int d = 8 >> k;
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++) {
+      const ulonglong2 w = tw.get(k, g);
+#pragma unroll
+      for (int o = 0; o < d; o++) hb1_ct(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, q, q2);
+    }
+  }
+}
+template <class TW>
+__device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 q, u64 q2) {
+#pragma unroll
+  for (int k = 3; k >= 0; k--) {
+    const int d = 8 >> k;
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++) {
+      const ulonglong2 w = tw.get(k, g);
+#pragma unroll
+      for (int o = 0; o < d; o++) hb1_gs(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, q, q2);
+    }
+  }
+}
+__device__ __forceinline__ unsigned hb1_brev4(unsigned x) {
+  return ((x & 1u) << 3) | ((x & 2u) << 1) | ((x & 4u) >> 1) | ((x & 8u) >> 3);
+}
+
+struct Hb1BlkJob {
+  int logN, epi;
+  HbRows rows;
+  u64 scal[HB_MAXROWS], scal_s[HB_MAXROWS];
+  int nitems;
+  const u64* src[HB_MAXB];
+  u64* dst[HB_MAXB];
+};
+
+// Forward "blk" phase, 16 blocks per CTA.  grid = (N1/16, nrows, item-groups), 256 threads.
+// smem: 16 tiles (HB1_BS u64 each) + 16x16 pass-1 twiddles.
+__global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
+  HB_SMEM_DECL
+  u64* T = HB_SMEM;
+  ulonglong2* TW1 = (ulonglong2*)(T + 16 * HB1_BS + 8);
+  const int tid = threadIdx.x;
+  const int n1 = J.logN - 8;
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const u64 q = P.q, q2 = P.q + P.q;
+  const size_t rowoff = (size_t)pi << J.logN;
+  const unsigned u0 = blockIdx.x << 4;
+  // pass-1 mapping: (blk1, lo) ; pass-2 mapping: (hi, blk2)
+  const int blk1 = tid >> 4, lo = tid & 15;
+  const int hi = tid >> 4, blk2 = tid & 15;
+  const unsigned b1 = hb_brev(u0 + blk1, n1), b2 = hb_brev(u0 + blk2, n1);
+  if (lo < 15) {  // entry e = (1<<k)-1+g of block blk1
+    int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
+    int g = e - ((1 << k) - 1);
+    TW1[blk1 * 16 + e] = P.fw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
+  }
+  Hb1TwReg tw2;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++)
+      tw2.t[(1 << k) - 1 + g] = P.fw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
+  const u64 sc = J.scal[blockIdx.y], sc_s = J.scal_s[blockIdx.y];
+  const unsigned hrev = hb1_brev4(hi);
+  __syncthreads();
+  Hb1TwPtr tw1;
+  tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
+  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
+    const u64* src = J.src[it] + rowoff + ((size_t)b1 << 8) + lo;
+    u64* dst = J.dst[it] + rowoff + u0 + blk2;
+    u64 a[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = src[16 * r];
+    hb1_r16_fwd(a, tw1, q, q2);
+#pragma unroll
+    for (int r = 0; r < 16; r++) T[blk1 * HB1_BS + HB1_RS * r + lo] = a[r];
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = T[blk2 * HB1_BS + HB1_RS * hi + l];
+    hb1_r16_fwd(a, tw2, q, q2);
+#pragma unroll
+    for (int l = 0; l < 16; l++) {
+      u64 v = hb1_canon4(a[l], q, q2);
+      const size_t o = (size_t)((hb1_brev4(l) << 4) | hrev) << n1;   // brev8(16*hi + l) * N1
+      if (J.epi == 1) v = hb_mul_shoup(hb_submod(dst[o], v, q), sc, sc_s, q);
+      dst[o] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Inverse "blk" phase (bit-reversal + first 8 GS stages), 16 blocks per CTA.
+__global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
+  HB_SMEM_DECL
+  u64* T = HB_SMEM;
+  ulonglong2* TW1 = (ulonglong2*)(T + 16 * HB1_BS + 8);
+  const int tid = threadIdx.x;
+  const int n1 = J.logN - 8;
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const u64 q = P.q, q2 = P.q + P.q;
+  const size_t rowoff = (size_t)pi << J.logN;
+  const unsigned u0 = blockIdx.x << 4;
+  const int blk1 = tid >> 4, lo = tid & 15;   // second pass (on r)
+  const int hi = tid >> 4, blk2 = tid & 15;   // first pass (on lo)
+  const unsigned b1 = hb_brev(u0 + blk1, n1), b2 = hb_brev(u0 + blk2, n1);
+  if (lo < 15) {
+    int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
+    int g = e - ((1 << k) - 1);
+    TW1[blk1 * 16 + e] = P.iw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
+  }
+  Hb1TwReg tw2;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++)
+      tw2.t[(1 << k) - 1 + g] = P.iw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
+  const unsigned hrev = hb1_brev4(hi);
+  __syncthreads();
+  Hb1TwPtr tw1;
+  tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
+  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
+    const u64* src = J.src[it] + rowoff + u0 + blk2;
+    u64* dst = J.dst[it] + rowoff + ((size_t)b1 << 8) + lo;
+    u64 a[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = src[(size_t)((hb1_brev4(l) << 4) | hrev) << n1];
+    hb1_r16_inv(a, tw2, q, q2);
+#pragma unroll
+    for (int l = 0; l < 16; l++) T[blk2 * HB1_BS + HB1_RS * hi + l] = a[l];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = T[blk1 * HB1_BS + HB1_RS * r + lo];
+    hb1_r16_inv(a, tw1, q, q2);
+#pragma unroll
+    for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon2(a[r], q);
+    __syncthreads();
+  }
+}
+
+struct Hb1ColsJob {
+  int logN;
+  HbRows rows;
+  int nitems;
+  const u64* src[HB_MAXB];
+  u64* dst[HB_MAXB];
+};
+
+// "cols" phases for n1 = 8 (N = 2^16): tile [256][16 columns].  grid = (16, nrows, item-groups).
+__global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restrict__ primes, Hb1ColsJob J) {
+  HB_SMEM_DECL
+  u64* T = HB_SMEM;
+  const int tid = threadIdx.x;
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const u64 q = P.q, q2 = P.q + P.q;
+  const size_t rowoff = (size_t)pi << J.logN;
+  const unsigned c0 = blockIdx.x << 4;
+  const int c = tid & 15, x = tid >> 4;  // x = lo in pass 1 (on r), hi in pass 2 (on lo)
+  Hb1TwPtr tw1;
+  tw1.p[0] = P.fw + 1; tw1.p[1] = P.fw + 2; tw1.p[2] = P.fw + 4; tw1.p[3] = P.fw + 8;
+  Hb1TwReg tw2;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++) tw2.t[(1 << k) - 1 + g] = P.fw[(16 << k) + (x << k) + g];
+  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
+    const u64* src = J.src[it] + rowoff + c0 + c;
+    u64* dst = J.dst[it] + rowoff + c0 + c;
+    u64 a[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = src[(size_t)(16 * r + x) << 8];
+    hb1_r16_fwd(a, tw1, q, q2);
+#pragma unroll
+    for (int r = 0; r < 16; r++) T[c * HB1_BS + HB1_RS * r + x] = a[r];
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = T[c * HB1_BS + HB1_RS * x + l];
+    hb1_r16_fwd(a, tw2, q, q2);
+#pragma unroll
+    for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = hb1_canon4(a[l], q, q2);
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restrict__ primes, Hb1ColsJob J) {
+  HB_SMEM_DECL
+  u64* T = HB_SMEM;
+  const int tid = threadIdx.x;
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const u64 q = P.q, q2 = P.q + P.q;
+  const size_t rowoff = (size_t)pi << J.logN;
+  const unsigned c0 = blockIdx.x << 4;
+  const int c = tid & 15, x = tid >> 4;  // x = hi in pass 1 (on lo), lo in pass 2 (on r)
+  Hb1TwPtr tw1;
+  tw1.p[0] = P.iw + 1; tw1.p[1] = P.iw + 2; tw1.p[2] = P.iw + 4; tw1.p[3] = P.iw + 8;
+  Hb1TwReg tw2;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++) tw2.t[(1 << k) - 1 + g] = P.iw[(16 << k) + (x << k) + g];
+  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
+    const u64* src = J.src[it] + rowoff + c0 + c;
+    u64* dst = J.dst[it] + rowoff + c0 + c;
+    u64 a[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = src[(size_t)(16 * x + l) << 8];
+    hb1_r16_inv(a, tw2, q, q2);
+#pragma unroll
+    for (int l = 0; l < 16; l++) T[c * HB1_BS + HB1_RS * x + l] = a[l];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = T[c * HB1_BS + HB1_RS * r + x];
+    hb1_r16_inv(a, tw1, q, q2);
+#pragma unroll
+    for (int r = 0; r < 16; r++) dst[(size_t)(16 * r + x) << 8] = hb_mul_shoup(a[r], P.ninv, P.ninv_s, q);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused exact base conversion, n1 = 8, 4 columns per CTA, NG groups of 64 threads.
+// Row tile layout: Y[c*HB1C_BS + 17*(i1>>4) + (i1&15)], c in [0,4), i1 in [0,256).
+#define HB1C_BS 276           // column stride in k1_conv (2*276 mod 32 = 8: 4 cols x 4 rows conflict-free)
+#define HB1_TS (4 * HB1C_BS)  // u64 per row tile (1104)
+
+struct Hb1ConvJob {
+  const HbConvDev* cv;
+  int logN, ngroups;
+  int nitems;
+  const u64* src[HB_MAXB];
+  u64* dst[HB_MAXB];
+  u64* stats;
+};
+
+__global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
+  HB_SMEM_DECL
+  const HbConvDev* cv = J.cv;
+  const int n = cv->n, nt = cv->nt, NG = J.ngroups;
+  u64* Y = HB_SMEM;                               // [n][HB1_TS]
+  i64* Vb = (i64*)(Y + (size_t)n * HB1_TS);       // [1024]  index c*256 + i1
+  u64* W = (u64*)(Vb + 1024);                     // [NG][HB1_TS]
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6, gt = tid & 63;
+  const int c = gt & 3, x = gt >> 2;              // x in [0,16)
+  const unsigned c0 = blockIdx.x << 2;
+  const u64* src = J.src[blockIdx.y];
+  u64* dst = J.dst[blockIdx.y];
+
+  // ---- sources: inverse cols phase, * (Q/q_j)^-1 * N^-1, canonical y_j into Y[j]
+  for (int j = grp; j < n; j += NG) {
+    const int pi = cv->src_prime[j];
+    const HbPrimeDev P = primes[pi];
+    const u64 q = P.q, q2 = P.q + P.q;
+    const u64* s = src + ((size_t)pi << J.logN) + c0 + c;
+    u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS;
+    u64 a[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = s[(size_t)(16 * x + l) << 8];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.iw + 16 + x; tw.p[1] = P.iw + 32 + 2 * x; tw.p[2] = P.iw + 64 + 4 * x; tw.p[3] = P.iw + 128 + 8 * x;
+      hb1_r16_inv(a, tw, q, q2);
+    }
+#pragma unroll
+    for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
+    hb_group_sync(grp, 64);
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = Yj[HB1_RS * r + x];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.iw + 1; tw.p[1] = P.iw + 2; tw.p[2] = P.iw + 4; tw.p[3] = P.iw + 8;
+      hb1_r16_inv(a, tw, q, q2);
+    }
+    const u64 t = cv->tn[j], ts = cv->tn_s[j];
+#pragma unroll
+    for (int r = 0; r < 16; r++) Yj[HB1_RS * r + x] = hb_mul_shoup(a[r], t, ts, q);
+  }
+  __syncthreads();
+  // ---- v (multiple of Q to subtract, incl. the BGV correction) per coefficient
+  for (int e = tid; e < 1024; e += blockDim.x) {
+    const int cc = e >> 8, i1 = e & 255;
+    Vb[e] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats);
+  }
+  __syncthreads();
+  // ---- targets: x mod q_t in registers, forward cols phase, store
+  u64* Wg = W + (size_t)grp * HB1_TS + c * HB1C_BS;
+  for (int t = grp; t < nt; t += NG) {
+    const int pi = cv->tgt_prime[t];
+    const HbPrimeDev P = primes[pi];
+    const u64 q = P.q, q2 = P.q + P.q;
+    const u64* ct = cv->c + (size_t)t * n;
+    u64 ahi[16], alo[16];
+    {
+      const u64 nq = cv->negQ[t], pq = cv->Qmod[t];
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const i64 v = Vb[c * 256 + 16 * r + x];
+        const u64 m = v >= 0 ? (u64)v : (u64)(-v);
+        const u64 f = v >= 0 ? nq : pq;
+        alo[r] = m * f; ahi[r] = __umul64hi(m, f);
+      }
+    }
+    for (int j = 0; j < n; j++) {
+      const u64 cj = ct[j];
+      const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x;
+#pragma unroll
+      for (int r = 0; r < 16; r++) hb1_mac128(ahi[r], alo[r], Yj[HB1_RS * r], cj);
+    }
+    u64 a[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = hb_reduce128(ahi[r], alo[r], P);
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;
+      hb1_r16_fwd(a, tw, q, q2);
+    }
+    hb_group_sync(grp, 64);   // previous target's pass-2 reads of Wg are complete
+#pragma unroll
+    for (int r = 0; r < 16; r++) Wg[HB1_RS * r + x] = a[r];
+    hb_group_sync(grp, 64);
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = Wg[HB1_RS * x + l];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.fw + 16 + x; tw.p[1] = P.fw + 32 + 2 * x; tw.p[2] = P.fw + 64 + 4 * x; tw.p[3] = P.fw + 128 + 8 * x;
+      hb1_r16_fwd(a, tw, q, q2);
+    }
+    u64* d = dst + ((size_t)pi << J.logN) + c0 + c;
+#pragma unroll
+    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = hb1_canon4(a[l], q, q2);
+  }
+}

@@ -4,10 +4,12 @@
 // tables and the exact-CRT conversion tables, and issues stream-ordered launches of the kernels
 // in hb_device.cuh.  There is no CPU compute path: without a CUDA device hb_ctx_create fails.
 #include "hb_device.cuh"
+#include "hb_device_v1.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -69,6 +71,8 @@ struct hb_ctx {
   size_t bytes; u64 launches;
   cudaEvent_t ev0, ev1;
   size_t max_smem;
+  bool force_v0;     // HB_FORCE_V0=1: generic radix-2 kernels only (A/B testing)
+  int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
   // optional per-launch profiling (bench.py): CUDA events around every kernel launch
   bool profiling;
   struct ProfRec { const char* name; cudaEvent_t a, b; u64 bytes; };
@@ -104,6 +108,8 @@ static void pre_launch(hb_ctx* c) {
 // bytes = algorithmic HBM bytes of this launch (rows read once + rows written once)
 static int post_launch(hb_ctx* c, const char* what, u64 bytes = 0) {
   c->launches++;
+  static const bool trace = getenv("HB_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[hb] launch %s alg_bytes=%llu\n", what, (unsigned long long)bytes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return hb_fail(HB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
 #ifndef HB_SIM
@@ -146,6 +152,11 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->d_primes = nullptr; c->d_tw = nullptr; c->d_stats = nullptr; c->profiling = false;
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
+  { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
+  c->resident_ctas = 296;
+#ifndef HB_SIM
+  { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->resident_ctas = 2 * prop.multiProcessorCount; }
+#endif
   const size_t N = c->N;
   for (int i = 0; i < nprimes; i++) {
     u64 qi = q[i];
@@ -191,6 +202,9 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem + 1024));
   HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 #endif
   *out = c;
   return HB_OK;
@@ -373,9 +387,62 @@ static void fill_rows(HbRows& r, const int32_t* idx, int n) { r.n = n; for (int 
 static int logwb_of(hb_ctx* c) { int n1 = c->logN - c->log_blk; return std::min(n1, 10 - c->log_blk); }
 static int logw_cols(hb_ctx* c) { int n1 = c->logN - c->log_blk; int lw = 10 - n1; if (lw < 0) lw = 0; return std::min(lw, c->log_blk); }
 
+static bool v1_blk_ok(hb_ctx* c) { return !c->force_v0 && c->log_blk == 8 && c->logN - 8 >= 4; }
+static bool v1_cols_ok(hb_ctx* c) { return !c->force_v0 && c->log_blk == 8 && c->logN - 8 == 8; }
+// number of item groups (gridDim.z): each CTA loops over ceil(nitems/z) items re-using its twiddles;
+// pick z so the grid fills whole waves of resident CTAs with the fewest CTAs
+static int pick_item_groups(hb_ctx* c, long ctas_per_item_group, int nitems) {
+  int best = 1; double best_eff = -1;
+  for (int z = 1; z <= nitems; z++) {
+    long ctas = ctas_per_item_group * z;
+    long waves = (ctas + c->resident_ctas - 1) / c->resident_ctas;
+    int per = (nitems + z - 1) / z;
+    double eff = (double)ctas / (double)(waves * c->resident_ctas) * ((double)nitems / (double)(per * z));
+    if (eff > best_eff + 0.02) { best_eff = eff; best = z; }
+  }
+  return best;
+}
+static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
+                         int epi, const u64* scal) {
+  const int n1 = c->logN - 8;
+  const size_t smem = (16 * HB1_BS + 8) * sizeof(u64) + 256 * sizeof(ulonglong2);
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    Hb1BlkJob J; memset(&J, 0, sizeof(J));
+    J.logN = c->logN; J.epi = epi;
+    fill_rows(J.rows, idx + r0, nr);
+    for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    unsigned gx = 1u << (n1 - 4);
+    dim3 grid(gx, nr, pick_item_groups(c, (long)gx * nr, nitems));
+    pre_launch(c);
+    if (dir > 0) { HB_LAUNCH(k1_fwd_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k1_fwd_blk_subscale" : "k1_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
+    else { HB_LAUNCH(k1_inv_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
+  }
+  return HB_OK;
+}
+static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n) {
+  const size_t smem = (16 * HB1_BS + 8) * sizeof(u64);
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    Hb1ColsJob J; memset(&J, 0, sizeof(J));
+    J.logN = c->logN;
+    fill_rows(J.rows, idx + r0, nr);
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    dim3 grid(16, nr, pick_item_groups(c, 16L * nr, nitems));
+    pre_launch(c);
+    if (dir > 0) { HB_LAUNCH(k1_fwd_cols, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_fwd_cols", (u64)2 * nr * nitems * c->N * 8)); }
+    else { HB_LAUNCH(k1_inv_cols, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_cols", (u64)2 * nr * nitems * c->N * 8)); }
+  }
+  return HB_OK;
+}
+
 // direction: +1 forward blk (src -> dst, optional epilogue), -1 inverse blk
 static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
                       int epi, const u64* scal) {
+  if (v1_blk_ok(c)) return launch_blk_v1(c, dir, src, dst, nitems, idx, n, epi, scal);
   const int lwb = logwb_of(c);
   const int n1 = c->logN - c->log_blk;
   const size_t smem = ((size_t)1 << lwb) * (((size_t)1 << c->log_blk) + 1) * sizeof(u64);
@@ -395,6 +462,7 @@ static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst
   return HB_OK;
 }
 static int launch_cols(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n) {
+  if (v1_cols_ok(c)) return launch_cols_v1(c, dir, src, dst, nitems, idx, n);
   const int lw = logw_cols(c);
   const int n1 = c->logN - c->log_blk;
   const size_t smem = ((size_t)1 << (n1 + lw)) * sizeof(u64);
@@ -548,6 +616,19 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   u64* tA[HB_MAXB]; u64* tB[HB_MAXB];
   tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
   HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
+  if (v1_cols_ok(c)) {
+    int ng = 8;
+    size_t smem1 = ((size_t)(n + ng) * HB1_TS + 1024) * sizeof(u64);
+    if (smem1 > 220 * 1024) { ng = 4; smem1 = ((size_t)(n + ng) * HB1_TS + 1024) * sizeof(u64); }
+    if (smem1 <= 220 * 1024) {
+      Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
+      J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats;
+      for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
+      pre_launch(c);
+      HB_LAUNCH(k1_conv, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+      return post_launch(c, "k1_conv", (u64)(n + nt) * nit * c->N * 8);
+    }
+  }
   const int n1 = c->logN - c->log_blk;
   int lw = logw_cols(c);
   while (lw > 0 && ((size_t)(n + 2) << (n1 + lw)) * sizeof(u64) > c->max_smem) lw--;

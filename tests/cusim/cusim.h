@@ -27,6 +27,7 @@ extern dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 extern char* smem_;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void syncthreads();
+void bar_sync(int id, int count);  // named barrier (PTX bar.sync id, count)
 }  // namespace cusim
 
 #define threadIdx cusim::threadIdx_
@@ -114,10 +115,17 @@ static void fiber_entry() {
   swapcontext(&fibers[cur_fiber].ctx, &sched_ctx);
 }
 
-void syncthreads() {
+static int bar_arrived[16], bar_gen[16];
+static unsigned cur_nthr = 0;
+
+// counter/generation barriers: a fiber arrives, then yields until the generation advances
+void bar_sync(int id, int count) {
   int me = cur_fiber;
-  swapcontext(&fibers[me].ctx, &sched_ctx);
+  int gen = bar_gen[id];
+  if (++bar_arrived[id] == count) { bar_arrived[id] = 0; bar_gen[id]++; return; }
+  while (bar_gen[id] == gen) swapcontext(&fibers[me].ctx, &sched_ctx);
 }
+void syncthreads() { bar_sync(0, (int)cur_nthr); }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   unsigned nthr = block.x * block.y * block.z;
@@ -133,6 +141,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
         smem_ = shared.data();
+        cur_nthr = nthr;
+        for (int b = 0; b < 16; b++) { bar_arrived[b] = 0; bar_gen[b] = 0; }
         for (unsigned t = 0; t < nthr; t++) {
           getcontext(&fibers[t].ctx);
           fibers[t].ctx.uc_stack.ss_sp = fibers[t].stack;

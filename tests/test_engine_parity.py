@@ -224,3 +224,31 @@ def test_full_size_config3_relinearize_bgv(cuda_lib):
     E.scale_down([C0, C1], Sp, S, 257)
     O.scale_down(r0, Sp, S, 257); O.scale_down(r1, Sp, S, 257)
     assert rows_equal(C0.download(S), r0, S) and rows_equal(C1.download(S), r1, S)
+
+
+def test_sim_full_ring_dimension_small_chain(sim_lib):
+    """N = 2^16 with a short chain on the simulator: exercises the register-blocked (v1) cols and
+    fused-conversion kernels, which only exist for N = 2^16, without a GPU."""
+    cfg = (1 << 17, 257, 1, 230, 2)
+    ch, psis, O, E = make(sim_lib, *cfg, nthreads=8)
+    rng = np.random.default_rng(9)
+    full = ch.ctxt + ch.special
+    x = O.random(rng, full)
+    P = E.poly(x, full)
+    E.ntt_inv([P], full)
+    ref = x.copy(); O.ntt_inv_rows(ref, full)
+    assert rows_equal(P.download(full), ref, full)
+    E.ntt_fwd([P], full)
+    assert rows_equal(P.download(full), x, full)
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    S_in = ch.ctxt
+    S = ch.ctxt[:-1] if len(ch.ctxt) > 1 else ch.ctxt
+    o = [O.random(rng, S_in) for _ in range(4)]
+    A0, A1, B0, B1 = ([E.poly(o[k], S_in)] for k in range(4))
+    E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, 257, EA, EB)
+    r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, 257, evk_a, evk_b)
+    assert rows_equal(A0[0].download(S), r0, S) and rows_equal(A1[0].download(S), r1, S)
