@@ -42,6 +42,7 @@ struct HbPrimeDev {
   u64 ninv, ninv_s;        // N^-1 mod q (+ Shoup companion floor(w*2^64/q))
   u64 c64, c64_s;          // 2^64 mod q (+ Shoup)
   u64 one_s;               // floor(2^64 / q)
+  u64 nq, q3;              // 2^64 - q and 3q, kept as opaque table values so ptxas does not re-derive them from q
   const ulonglong2* fw;    // fw[k] = (psi^brev(k), shoup), k = 1..N-1   (Cooley-Tukey, merged twist)
   const ulonglong2* iw;    // iw[k] = (psi^-brev(k), shoup)              (Gentleman-Sande)
 };

@@ -2,7 +2,7 @@
 //
 // A 256-point sub-transform (either phase of the N = N1 x 256 split) is done as radix-16 x
 // radix-16: each thread holds 16 residues in registers, runs 4 butterfly stages (Harvey lazy
-// butterflies, Shoup twiddles, values kept in [0,4q) forward / [0,2q) inverse), exchanges through
+// butterflies, Shoup twiddles, values kept in [0,6q) forward / [0,3q) inverse), exchanges through
 // a padded shared-memory tile (row stride 17, block stride 273: conflict-free for 64-bit
 // accesses), and runs the other 4 stages.  Values crossing a kernel boundary are canonical.
 //
@@ -41,26 +41,47 @@ __device__ __forceinline__ void hb1_mac128(u64& hi, u64& lo, u64 a, u64 b) {
 #endif
 }
 
-// Cooley-Tukey butterfly, x,y in [0,4q) -> [0,4q)
-__device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, u64 q, u64 q2) {
-  u64 xr = x >= q2 ? x - q2 : x;
-  u64 t = hb_mul_shoup_lazy(y, w, ws, q);
+// ---- lazy arithmetic of the register kernels (requires q < 2^60, so 6q < 2^63) -------------
+// Approximate high word of a 64x64 product: drops the lo*lo partial product, so the result is
+// floor(a*b/2^64) or one less.  3 IMAD.WIDE instead of 4 and a shorter carry chain.
+__device__ __forceinline__ u64 hb1_mulhi_approx(u64 a, u64 b) {
+  const unsigned alo = (unsigned)a, ahi = (unsigned)(a >> 32), blo = (unsigned)b, bhi = (unsigned)(b >> 32);
+  const u64 p1 = (u64)alo * bhi;
+  const u64 p2 = (u64)ahi * blo + (unsigned)p1;
+  const u64 p3 = (u64)ahi * bhi + (p1 >> 32);
+  return p3 + (p2 >> 32);
+}
+// y*w mod q up to a multiple of q: result in [0,3q) for ANY 64-bit y (Shoup quotient off by <= 2).
+// nq = 2^64 - q, so the subtraction is folded into the multiply-add chain.
+__device__ __forceinline__ u64 hb1_shoup3(u64 y, u64 w, u64 ws, u64 nq) {
+  return y * w + hb1_mulhi_approx(y, ws) * nq;
+}
+// x in [0,2m) -> [0,m) by one conditional subtraction decided on the sign of x-m (both < 2^63)
+__device__ __forceinline__ u64 hb1_csub(u64 x, u64 m) {
+  const u64 d = x - m;
+  return (i64)d < 0 ? x : d;
+}
+// Cooley-Tukey butterfly, x,y in [0,6q) -> [0,6q)
+__device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, u64 nq, u64 q3) {
+  const u64 xr = hb1_csub(x, q3);
+  const u64 t = hb1_shoup3(y, w, ws, nq);
   x = xr + t;
-  y = xr - t + q2;
+  y = xr - t + q3;
 }
-// Gentleman-Sande butterfly, x,y in [0,2q) -> [0,2q)
-__device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, u64 q, u64 q2) {
-  u64 s = x + y;
-  u64 d = x - y + q2;
-  x = s >= q2 ? s - q2 : s;
-  y = hb_mul_shoup_lazy(d, w, ws, q);
+// Gentleman-Sande butterfly, x,y in [0,3q) -> [0,3q)
+__device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, u64 nq, u64 q3) {
+  const u64 s = x + y;
+  const u64 d = x - y + q3;
+  x = hb1_csub(s, q3);
+  y = hb1_shoup3(d, w, ws, nq);
 }
-__device__ __forceinline__ u64 hb1_canon4(u64 x, u64 q, u64 q2) {  // [0,4q) -> [0,q)
-  if (x >= q2) x -= q2;
-  if (x >= q) x -= q;
-  return x;
+__device__ __forceinline__ u64 hb1_canon3(u64 x, u64 q) {  // [0,3q) -> [0,q)
+  x = hb1_csub(x, q + q);
+  return hb1_csub(x, q);
 }
-__device__ __forceinline__ u64 hb1_canon2(u64 x, u64 q) { return x >= q ? x - q : x; }
+__device__ __forceinline__ u64 hb1_canon6(u64 x, u64 q) {  // [0,6q) -> [0,q)
+  return hb1_canon3(hb1_csub(x, 3 * q), q);
+}
 
 // 4 forward stages on 16 registers; twiddle of stage k (distance 8>>k), group g is tw[(1<<k)-1+g]
 struct Hb1TwReg {
@@ -73,7 +94,7 @@ struct Hb1TwPtr {
   __device__ __forceinline__ ulonglong2 get(int k, int g) const { return p[k][g]; }
 };
 template <class TW>
-__device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 q, u64 q2) {
+__device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 nq, u64 q3) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int d = 8 >> k;
@@ -81,12 +102,12 @@ __device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 q, u
     for (int g = 0; g < (1 << k); g++) {
       const ulonglong2 w = tw.get(k, g);
 #pragma unroll
-      for (int o = 0; o < d; o++) hb1_ct(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, q, q2);
+      for (int o = 0; o < d; o++) hb1_ct(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, nq, q3);
     }
   }
 }
 template <class TW>
-__device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 q, u64 q2) {
+__device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 nq, u64 q3) {
 #pragma unroll
   for (int k = 3; k >= 0; k--) {
     const int d = 8 >> k;
@@ -94,7 +115,7 @@ __device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 q, u
     for (int g = 0; g < (1 << k); g++) {
       const ulonglong2 w = tw.get(k, g);
 #pragma unroll
-      for (int o = 0; o < d; o++) hb1_gs(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, q, q2);
+      for (int o = 0; o < d; o++) hb1_gs(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, nq, q3);
     }
   }
 }
@@ -111,17 +132,43 @@ struct Hb1BlkJob {
   u64* dst[HB_MAXB];
 };
 
+// 8-byte asynchronous global->shared copy (LDGSTS) and its group fences
+__device__ __forceinline__ void hb1_cp8(u64* dst_smem, const u64* src) {
+#ifdef HB_SIM
+  *dst_smem = *src;
+#else
+  unsigned sa = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void hb1_cp_commit() {
+#ifndef HB_SIM
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> __device__ __forceinline__ void hb1_cp_wait() {
+#ifndef HB_SIM
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+#define HB1_STAGE (16 * HB1_BS + 8)   // u64 per staging/exchange buffer
+
 // Forward "blk" phase, 16 blocks per CTA.  grid = (N1/16, nrows, item-groups), 256 threads.
-// smem: 16 tiles (HB1_BS u64 each) + 16x16 pass-1 twiddles.
+// Software pipelined over the batch items: each thread prefetches its own 16 inputs of the NEXT
+// item (and, for the mod-down epilogue, the 16 old destination values of the CURRENT item) into
+// shared memory with cp.async while it computes; the staging tile doubles as the exchange tile.
+// smem: S[2][HB1_STAGE] | O[16][256] | TW1[256]
 __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
-  u64* T = HB_SMEM;
-  ulonglong2* TW1 = (ulonglong2*)(T + 16 * HB1_BS + 8);
+  u64* S = HB_SMEM;
+  u64* O = S + 2 * HB1_STAGE;
+  ulonglong2* TW1 = (ulonglong2*)(O + 16 * 256);
   const int tid = threadIdx.x;
   const int n1 = J.logN - 8;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, q2 = P.q + P.q;
+  const u64 q = P.q, nq = P.nq, q3 = P.q3;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned u0 = blockIdx.x << 4;
   // pass-1 mapping: (blk1, lo) ; pass-2 mapping: (hi, blk2)
@@ -141,43 +188,71 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
       tw2.t[(1 << k) - 1 + g] = P.fw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
   const u64 sc = J.scal[blockIdx.y], sc_s = J.scal_s[blockIdx.y];
   const unsigned hrev = hb1_brev4(hi);
-  __syncthreads();
+  const bool epi = J.epi == 1;
   Hb1TwPtr tw1;
   tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
-  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
-    const u64* src = J.src[it] + rowoff + ((size_t)b1 << 8) + lo;
-    u64* dst = J.dst[it] + rowoff + u0 + blk2;
+  const int own = blk1 * HB1_BS + lo;   // + HB1_RS * r
+  const size_t srcoff = rowoff + ((size_t)b1 << 8) + lo;
+  const size_t dstoff = rowoff + u0 + blk2;
+  int it = blockIdx.z, buf = 0;
+  if (it < J.nitems) {
+    const u64* src = J.src[it] + srcoff;
+#pragma unroll
+    for (int r = 0; r < 16; r++) hb1_cp8(S + own + HB1_RS * r, src + 16 * r);
+  }
+  hb1_cp_commit();
+  __syncthreads();  // TW1 visible
+  for (; it < J.nitems; it += gridDim.z, buf ^= 1) {
+    u64* Sb = S + buf * HB1_STAGE;
+    u64* dst = J.dst[it] + dstoff;
+    if (epi) {
+#pragma unroll
+      for (int l = 0; l < 16; l++) hb1_cp8(O + l * 256 + tid, dst + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
+    }
+    hb1_cp_commit();
+    const int nxt = it + gridDim.z;
+    if (nxt < J.nitems) {
+      const u64* src = J.src[nxt] + srcoff;
+      u64* Sn = S + (buf ^ 1) * HB1_STAGE;
+#pragma unroll
+      for (int r = 0; r < 16; r++) hb1_cp8(Sn + own + HB1_RS * r, src + 16 * r);
+    }
+    hb1_cp_commit();
+    hb1_cp_wait<2>();   // this item's inputs have landed (issued one iteration ago)
     u64 a[16];
 #pragma unroll
-    for (int r = 0; r < 16; r++) a[r] = src[16 * r];
-    hb1_r16_fwd(a, tw1, q, q2);
+    for (int r = 0; r < 16; r++) a[r] = Sb[own + HB1_RS * r];
+    hb1_r16_fwd(a, tw1, nq, q3);
 #pragma unroll
-    for (int r = 0; r < 16; r++) T[blk1 * HB1_BS + HB1_RS * r + lo] = a[r];
+    for (int r = 0; r < 16; r++) Sb[own + HB1_RS * r] = a[r];
     __syncthreads();
 #pragma unroll
-    for (int l = 0; l < 16; l++) a[l] = T[blk2 * HB1_BS + HB1_RS * hi + l];
-    hb1_r16_fwd(a, tw2, q, q2);
+    for (int l = 0; l < 16; l++) a[l] = Sb[blk2 * HB1_BS + HB1_RS * hi + l];
+    hb1_r16_fwd(a, tw2, nq, q3);
+    hb1_cp_wait<1>();   // old destination values (epilogue) have landed
 #pragma unroll
     for (int l = 0; l < 16; l++) {
-      u64 v = hb1_canon4(a[l], q, q2);
+      u64 v = hb1_canon6(a[l], q);
       const size_t o = (size_t)((hb1_brev4(l) << 4) | hrev) << n1;   // brev8(16*hi + l) * N1
-      if (J.epi == 1) v = hb_mul_shoup(hb_submod(dst[o], v, q), sc, sc_s, q);
+      if (epi) v = hb_mul_shoup(hb_submod(O[l * 256 + tid], v, q), sc, sc_s, q);
       dst[o] = v;
     }
-    __syncthreads();
+    __syncthreads();   // all exchange reads of Sb done before it is refilled two iterations later
   }
+  hb1_cp_wait<0>();
 }
 
-// Inverse "blk" phase (bit-reversal + first 8 GS stages), 16 blocks per CTA.
+// Inverse "blk" phase (bit-reversal + first 8 GS stages), 16 blocks per CTA, same pipelining.
+// smem: S[2][HB1_STAGE] | TW1[256]
 __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
-  u64* T = HB_SMEM;
-  ulonglong2* TW1 = (ulonglong2*)(T + 16 * HB1_BS + 8);
+  u64* S = HB_SMEM;
+  ulonglong2* TW1 = (ulonglong2*)(S + 2 * HB1_STAGE);
   const int tid = threadIdx.x;
   const int n1 = J.logN - 8;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, q2 = P.q + P.q;
+  const u64 q = P.q, nq = P.nq, q3 = P.q3;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned u0 = blockIdx.x << 4;
   const int blk1 = tid >> 4, lo = tid & 15;   // second pass (on r)
@@ -195,26 +270,46 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
     for (int g = 0; g < (1 << k); g++)
       tw2.t[(1 << k) - 1 + g] = P.iw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
   const unsigned hrev = hb1_brev4(hi);
-  __syncthreads();
   Hb1TwPtr tw1;
   tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
-  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
-    const u64* src = J.src[it] + rowoff + u0 + blk2;
-    u64* dst = J.dst[it] + rowoff + ((size_t)b1 << 8) + lo;
+  const int own = blk2 * HB1_BS + HB1_RS * hi;   // + l
+  const size_t srcoff = rowoff + u0 + blk2;
+  const size_t dstoff = rowoff + ((size_t)b1 << 8) + lo;
+  int it = blockIdx.z, buf = 0;
+  if (it < J.nitems) {
+    const u64* src = J.src[it] + srcoff;
+#pragma unroll
+    for (int l = 0; l < 16; l++) hb1_cp8(S + own + l, src + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
+  }
+  hb1_cp_commit();
+  __syncthreads();
+  for (; it < J.nitems; it += gridDim.z, buf ^= 1) {
+    u64* Sb = S + buf * HB1_STAGE;
+    const int nxt = it + gridDim.z;
+    if (nxt < J.nitems) {
+      const u64* src = J.src[nxt] + srcoff;
+      u64* Sn = S + (buf ^ 1) * HB1_STAGE;
+#pragma unroll
+      for (int l = 0; l < 16; l++) hb1_cp8(Sn + own + l, src + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
+    }
+    hb1_cp_commit();
+    hb1_cp_wait<1>();
     u64 a[16];
 #pragma unroll
-    for (int l = 0; l < 16; l++) a[l] = src[(size_t)((hb1_brev4(l) << 4) | hrev) << n1];
-    hb1_r16_inv(a, tw2, q, q2);
+    for (int l = 0; l < 16; l++) a[l] = Sb[own + l];
+    hb1_r16_inv(a, tw2, nq, q3);
 #pragma unroll
-    for (int l = 0; l < 16; l++) T[blk2 * HB1_BS + HB1_RS * hi + l] = a[l];
+    for (int l = 0; l < 16; l++) Sb[own + l] = a[l];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) a[r] = T[blk1 * HB1_BS + HB1_RS * r + lo];
-    hb1_r16_inv(a, tw1, q, q2);
+    for (int r = 0; r < 16; r++) a[r] = Sb[blk1 * HB1_BS + HB1_RS * r + lo];
+    hb1_r16_inv(a, tw1, nq, q3);
+    u64* dst = J.dst[it] + dstoff;
 #pragma unroll
-    for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon2(a[r], q);
+    for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon3(a[r], q);
     __syncthreads();
   }
+  hb1_cp_wait<0>();
 }
 
 struct Hb1ColsJob {
@@ -232,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, q2 = P.q + P.q;
+  const u64 q = P.q, nq = P.nq, q3 = P.q3;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = lo in pass 1 (on r), hi in pass 2 (on lo)
@@ -249,15 +344,15 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
     u64 a[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = src[(size_t)(16 * r + x) << 8];
-    hb1_r16_fwd(a, tw1, q, q2);
+    hb1_r16_fwd(a, tw1, nq, q3);
 #pragma unroll
     for (int r = 0; r < 16; r++) T[c * HB1_BS + HB1_RS * r + x] = a[r];
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = T[c * HB1_BS + HB1_RS * x + l];
-    hb1_r16_fwd(a, tw2, q, q2);
+    hb1_r16_fwd(a, tw2, nq, q3);
 #pragma unroll
-    for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = hb1_canon4(a[l], q, q2);
+    for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = hb1_canon6(a[l], q);
     __syncthreads();
   }
 }
@@ -267,7 +362,7 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, q2 = P.q + P.q;
+  const u64 q = P.q, nq = P.nq, q3 = P.q3;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = hi in pass 1 (on lo), lo in pass 2 (on r)
@@ -284,13 +379,13 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
     u64 a[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = src[(size_t)(16 * x + l) << 8];
-    hb1_r16_inv(a, tw2, q, q2);
+    hb1_r16_inv(a, tw2, nq, q3);
 #pragma unroll
     for (int l = 0; l < 16; l++) T[c * HB1_BS + HB1_RS * x + l] = a[l];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = T[c * HB1_BS + HB1_RS * r + x];
-    hb1_r16_inv(a, tw1, q, q2);
+    hb1_r16_inv(a, tw1, nq, q3);
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[(size_t)(16 * r + x) << 8] = hb_mul_shoup(a[r], P.ninv, P.ninv_s, q);
     __syncthreads();
@@ -330,7 +425,7 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int j = grp; j < n; j += NG) {
     const int pi = cv->src_prime[j];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q, q2 = P.q + P.q;
+    const u64 q = P.q, nq = P.nq, q3 = P.q3;
     const u64* s = src + ((size_t)pi << J.logN) + c0 + c;
     u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS;
     u64 a[16];
@@ -339,7 +434,7 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.iw + 16 + x; tw.p[1] = P.iw + 32 + 2 * x; tw.p[2] = P.iw + 64 + 4 * x; tw.p[3] = P.iw + 128 + 8 * x;
-      hb1_r16_inv(a, tw, q, q2);
+      hb1_r16_inv(a, tw, nq, q3);
     }
 #pragma unroll
     for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
@@ -349,7 +444,7 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.iw + 1; tw.p[1] = P.iw + 2; tw.p[2] = P.iw + 4; tw.p[3] = P.iw + 8;
-      hb1_r16_inv(a, tw, q, q2);
+      hb1_r16_inv(a, tw, nq, q3);
     }
     const u64 t = cv->tn[j], ts = cv->tn_s[j];
 #pragma unroll
@@ -367,7 +462,7 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int t = grp; t < nt; t += NG) {
     const int pi = cv->tgt_prime[t];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q, q2 = P.q + P.q;
+    const u64 q = P.q, nq = P.nq, q3 = P.q3;
     const u64* ct = cv->c + (size_t)t * n;
     u64 ahi[16], alo[16];
     {
@@ -392,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;
-      hb1_r16_fwd(a, tw, q, q2);
+      hb1_r16_fwd(a, tw, nq, q3);
     }
     hb_group_sync(grp, 64);   // previous target's pass-2 reads of Wg are complete
 #pragma unroll
@@ -403,10 +498,10 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.fw + 16 + x; tw.p[1] = P.fw + 32 + 2 * x; tw.p[2] = P.fw + 64 + 4 * x; tw.p[3] = P.fw + 128 + 8 * x;
-      hb1_r16_fwd(a, tw, q, q2);
+      hb1_r16_fwd(a, tw, nq, q3);
     }
     u64* d = dst + ((size_t)pi << J.logN) + c0 + c;
 #pragma unroll
-    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = hb1_canon4(a[l], q, q2);
+    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = hb1_canon6(a[l], q);
   }
 }

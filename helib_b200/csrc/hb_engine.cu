@@ -160,7 +160,8 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   const size_t N = c->N;
   for (int i = 0; i < nprimes; i++) {
     u64 qi = q[i];
-    if (qi < 3 || qi >= (1ULL << 62) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^62 with m | q-1", i, (unsigned long long)qi); }
+    // HElib primes are < 2^HELIB_SP_NBITS = 2^60 (src/macro.h:16-23); the lazy butterflies need 6q < 2^63
+    if (qi < 3 || qi >= (1ULL << 60) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^60 with m | q-1", i, (unsigned long long)qi); }
     u64 ps = psi ? psi[i] : find_psi(qi, m);
     if (h_powmod(ps, N, qi) != qi - 1) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
     c->q.push_back(qi); c->psi.push_back(ps);
@@ -190,6 +191,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     P.ninv = h_powmod((u64)N % qi, qi - 2, qi); P.ninv_s = h_shoup(P.ninv, qi);
     P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi);
     P.one_s = (u64)(((u128)1 << 64) / qi);
+    P.nq = 0 - qi; P.q3 = 3 * qi;
     P.fw = c->d_tw + ((size_t)i * 2 + 0) * N;
     P.iw = c->d_tw + ((size_t)i * 2 + 1) * N;
   }
@@ -203,8 +205,8 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 #endif
   *out = c;
   return HB_OK;
@@ -405,7 +407,7 @@ static int pick_item_groups(hb_ctx* c, long ctas_per_item_group, int nitems) {
 static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
                          int epi, const u64* scal) {
   const int n1 = c->logN - 8;
-  const size_t smem = (16 * HB1_BS + 8) * sizeof(u64) + 256 * sizeof(ulonglong2);
+  const size_t smem = (2 * HB1_STAGE + (dir > 0 ? 16 * 256 : 0)) * sizeof(u64) + 256 * sizeof(ulonglong2);
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
     int nr = std::min(HB_MAXROWS, n - r0);
     Hb1BlkJob J; memset(&J, 0, sizeof(J));
@@ -617,10 +619,16 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
   HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
   if (v1_cols_ok(c)) {
-    int ng = 8;
-    size_t smem1 = ((size_t)(n + ng) * HB1_TS + 1024) * sizeof(u64);
-    if (smem1 > 220 * 1024) { ng = 4; smem1 = ((size_t)(n + ng) * HB1_TS + 1024) * sizeof(u64); }
-    if (smem1 <= 220 * 1024) {
+    // number of 64-thread row groups: best balance of the n source rows and nt target rows
+    int ng = 0; double best = -1; size_t smem1 = 0;
+    for (int g = 8; g >= 4; g--) {
+      size_t sm = ((size_t)(n + g) * HB1_TS + 1024) * sizeof(u64);
+      if (sm > 220 * 1024) continue;
+      double work = n + 1.4 * nt, slots = (double)((n + g - 1) / g) + 1.4 * ((nt + g - 1) / g);
+      double util = work / (slots * g) * (0.75 + 0.25 * g / 8.0);   // mild preference for more warps
+      if (util > best) { best = util; ng = g; smem1 = sm; }
+    }
+    if (ng > 0) {
       Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
       J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats;
       for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
