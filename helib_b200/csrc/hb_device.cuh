@@ -78,6 +78,10 @@ __device__ __forceinline__ u64 hb_reduce128(u64 hi, u64 lo, u64 q, u64 c64, u64 
   if (r >= q) r -= q;
   return r;
 }
+// same, but only reduced to [0,4q) (input of a lazy butterfly network)
+__device__ __forceinline__ u64 hb_reduce128_lazy(u64 hi, u64 lo, const HbPrimeDev& P) {
+  return hb_mul_shoup_lazy(hi, P.c64, P.c64_s, P.q) + (lo - __umul64hi(lo, P.one_s) * P.q);
+}
 __device__ __forceinline__ u64 hb_reduce128(u64 hi, u64 lo, const HbPrimeDev& P) {
   return hb_reduce128(hi, lo, P.q, P.c64, P.c64_s, P.one_s);
 }

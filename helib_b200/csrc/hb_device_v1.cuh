@@ -154,10 +154,24 @@ template <int N> __device__ __forceinline__ void hb1_cp_wait() {
 
 #define HB1_STAGE (16 * HB1_BS + 8)   // u64 per staging/exchange buffer
 
-// Forward "blk" phase, 16 blocks per CTA.  grid = (N1/16, nrows, item-groups), 256 threads.
-// Software pipelined over the batch items: each thread prefetches its own 16 inputs of the NEXT
-// item (and, for the mod-down epilogue, the 16 old destination values of the CURRENT item) into
-// shared memory with cp.async while it computes; the staging tile doubles as the exchange tile.
+// Work decomposition of the "blk" kernels: unit = (row, group of 16 blocks, batch item), numbered
+// row-major with the item fastest.  A persistent grid of CTAs takes contiguous, balanced chunks of
+// units, so consecutive units of a CTA mostly share (row, block group) and re-use its twiddles.
+struct Hb1Unit { int rowi, ug, it; };
+__device__ __forceinline__ Hb1Unit hb1_unit(long u, int G, int nitems) {
+  Hb1Unit x;
+  const int per_row = G * nitems;
+  x.rowi = (int)(u / per_row);
+  const int rem = (int)(u - (long)x.rowi * per_row);
+  x.ug = rem / nitems;
+  x.it = rem - x.ug * nitems;
+  return x;
+}
+
+// Forward "blk" phase, 16 blocks per unit, persistent CTAs (grid.x CTAs, 256 threads).
+// Software pipelined: each thread prefetches its own 16 inputs of the NEXT unit (and, for the
+// mod-down epilogue, the 16 old destination values of the CURRENT unit) into shared memory with
+// cp.async while it computes; the staging tile doubles as the exchange tile.
 // smem: S[2][HB1_STAGE] | O[16][256] | TW1[256]
 __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
@@ -166,59 +180,69 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
   ulonglong2* TW1 = (ulonglong2*)(O + 16 * 256);
   const int tid = threadIdx.x;
   const int n1 = J.logN - 8;
-  const int pi = J.rows.prime[blockIdx.y];
-  const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, nq = P.nq, q3 = P.q3;
-  const size_t rowoff = (size_t)pi << J.logN;
-  const unsigned u0 = blockIdx.x << 4;
+  const int G = 1 << (n1 - 4);
+  const long U = (long)J.rows.n * G * J.nitems;
+  const long ubeg = U * blockIdx.x / gridDim.x, uend = U * (blockIdx.x + 1) / gridDim.x;
+  if (ubeg >= uend) return;
   // pass-1 mapping: (blk1, lo) ; pass-2 mapping: (hi, blk2)
   const int blk1 = tid >> 4, lo = tid & 15;
   const int hi = tid >> 4, blk2 = tid & 15;
-  const unsigned b1 = hb_brev(u0 + blk1, n1), b2 = hb_brev(u0 + blk2, n1);
-  if (lo < 15) {  // entry e = (1<<k)-1+g of block blk1
-    int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
-    int g = e - ((1 << k) - 1);
-    TW1[blk1 * 16 + e] = P.fw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
-  }
-  Hb1TwReg tw2;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-#pragma unroll
-    for (int g = 0; g < (1 << k); g++)
-      tw2.t[(1 << k) - 1 + g] = P.fw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
-  const u64 sc = J.scal[blockIdx.y], sc_s = J.scal_s[blockIdx.y];
   const unsigned hrev = hb1_brev4(hi);
   const bool epi = J.epi == 1;
+  const int own = blk1 * HB1_BS + lo;   // + HB1_RS * r
   Hb1TwPtr tw1;
   tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
-  const int own = blk1 * HB1_BS + lo;   // + HB1_RS * r
-  const size_t srcoff = rowoff + ((size_t)b1 << 8) + lo;
-  const size_t dstoff = rowoff + u0 + blk2;
-  int it = blockIdx.z, buf = 0;
-  if (it < J.nitems) {
-    const u64* src = J.src[it] + srcoff;
+
+  auto src_ptr = [&](const Hb1Unit& x) {
+    const unsigned b = hb_brev((x.ug << 4) + blk1, n1);
+    return J.src[x.it] + ((size_t)J.rows.prime[x.rowi] << J.logN) + ((size_t)b << 8) + lo;
+  };
+  Hb1Unit cur = hb1_unit(ubeg, G, J.nitems);
+  {
+    const u64* src = src_ptr(cur);
 #pragma unroll
     for (int r = 0; r < 16; r++) hb1_cp8(S + own + HB1_RS * r, src + 16 * r);
   }
   hb1_cp_commit();
-  __syncthreads();  // TW1 visible
-  for (; it < J.nitems; it += gridDim.z, buf ^= 1) {
+  int key = -1, buf = 0;
+  u64 q = 0, nq = 0, q3 = 0, sc = 0, sc_s = 0;
+  Hb1TwReg tw2;
+  for (long u = ubeg; u < uend; u++, buf ^= 1) {
+    if (cur.rowi * G + cur.ug != key) {   // new (row, block group): reload modulus and twiddles
+      key = cur.rowi * G + cur.ug;
+      const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
+      q = P.q; nq = P.nq; q3 = P.q3;
+      sc = J.scal[cur.rowi]; sc_s = J.scal_s[cur.rowi];
+      const unsigned b1 = hb_brev((cur.ug << 4) + blk1, n1), b2 = hb_brev((cur.ug << 4) + blk2, n1);
+      if (lo < 15) {  // entry e = (1<<k)-1+g of block blk1
+        int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
+        int g = e - ((1 << k) - 1);
+        TW1[blk1 * 16 + e] = P.fw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int g = 0; g < (1 << k); g++)
+          tw2.t[(1 << k) - 1 + g] = P.fw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
+      __syncthreads();  // TW1 visible (the previous unit's trailing barrier ordered its last use)
+    }
     u64* Sb = S + buf * HB1_STAGE;
-    u64* dst = J.dst[it] + dstoff;
+    u64* dst = J.dst[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN) + (cur.ug << 4) + blk2;
     if (epi) {
 #pragma unroll
       for (int l = 0; l < 16; l++) hb1_cp8(O + l * 256 + tid, dst + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
     }
     hb1_cp_commit();
-    const int nxt = it + gridDim.z;
-    if (nxt < J.nitems) {
-      const u64* src = J.src[nxt] + srcoff;
+    Hb1Unit nxt = cur;
+    if (u + 1 < uend) {
+      nxt = hb1_unit(u + 1, G, J.nitems);
+      const u64* src = src_ptr(nxt);
       u64* Sn = S + (buf ^ 1) * HB1_STAGE;
 #pragma unroll
       for (int r = 0; r < 16; r++) hb1_cp8(Sn + own + HB1_RS * r, src + 16 * r);
     }
     hb1_cp_commit();
-    hb1_cp_wait<2>();   // this item's inputs have landed (issued one iteration ago)
+    hb1_cp_wait<2>();   // this unit's inputs have landed (issued one iteration ago)
     u64 a[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = Sb[own + HB1_RS * r];
@@ -237,12 +261,13 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
       if (epi) v = hb_mul_shoup(hb_submod(O[l * 256 + tid], v, q), sc, sc_s, q);
       dst[o] = v;
     }
-    __syncthreads();   // all exchange reads of Sb done before it is refilled two iterations later
+    __syncthreads();   // exchange reads of Sb / TW1 done before they are overwritten
+    cur = nxt;
   }
   hb1_cp_wait<0>();
 }
 
-// Inverse "blk" phase (bit-reversal + first 8 GS stages), 16 blocks per CTA, same pipelining.
+// Inverse "blk" phase (bit-reversal + first 8 GS stages), same decomposition and pipelining.
 // smem: S[2][HB1_STAGE] | TW1[256]
 __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
@@ -250,44 +275,54 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
   ulonglong2* TW1 = (ulonglong2*)(S + 2 * HB1_STAGE);
   const int tid = threadIdx.x;
   const int n1 = J.logN - 8;
-  const int pi = J.rows.prime[blockIdx.y];
-  const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, nq = P.nq, q3 = P.q3;
-  const size_t rowoff = (size_t)pi << J.logN;
-  const unsigned u0 = blockIdx.x << 4;
+  const int G = 1 << (n1 - 4);
+  const long U = (long)J.rows.n * G * J.nitems;
+  const long ubeg = U * blockIdx.x / gridDim.x, uend = U * (blockIdx.x + 1) / gridDim.x;
+  if (ubeg >= uend) return;
   const int blk1 = tid >> 4, lo = tid & 15;   // second pass (on r)
   const int hi = tid >> 4, blk2 = tid & 15;   // first pass (on lo)
-  const unsigned b1 = hb_brev(u0 + blk1, n1), b2 = hb_brev(u0 + blk2, n1);
-  if (lo < 15) {
-    int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
-    int g = e - ((1 << k) - 1);
-    TW1[blk1 * 16 + e] = P.iw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
-  }
-  Hb1TwReg tw2;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-#pragma unroll
-    for (int g = 0; g < (1 << k); g++)
-      tw2.t[(1 << k) - 1 + g] = P.iw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
   const unsigned hrev = hb1_brev4(hi);
   Hb1TwPtr tw1;
   tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
   const int own = blk2 * HB1_BS + HB1_RS * hi;   // + l
-  const size_t srcoff = rowoff + u0 + blk2;
-  const size_t dstoff = rowoff + ((size_t)b1 << 8) + lo;
-  int it = blockIdx.z, buf = 0;
-  if (it < J.nitems) {
-    const u64* src = J.src[it] + srcoff;
+  auto src_ptr = [&](const Hb1Unit& x) {
+    return J.src[x.it] + ((size_t)J.rows.prime[x.rowi] << J.logN) + (x.ug << 4) + blk2;
+  };
+  Hb1Unit cur = hb1_unit(ubeg, G, J.nitems);
+  {
+    const u64* src = src_ptr(cur);
 #pragma unroll
     for (int l = 0; l < 16; l++) hb1_cp8(S + own + l, src + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
   }
   hb1_cp_commit();
-  __syncthreads();
-  for (; it < J.nitems; it += gridDim.z, buf ^= 1) {
+  int key = -1, buf = 0;
+  u64 q = 0, nq = 0, q3 = 0;
+  unsigned b1 = 0;
+  Hb1TwReg tw2;
+  for (long u = ubeg; u < uend; u++, buf ^= 1) {
+    if (cur.rowi * G + cur.ug != key) {
+      key = cur.rowi * G + cur.ug;
+      const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
+      q = P.q; nq = P.nq; q3 = P.q3;
+      b1 = hb_brev((cur.ug << 4) + blk1, n1);
+      const unsigned b2 = hb_brev((cur.ug << 4) + blk2, n1);
+      if (lo < 15) {
+        int e = lo, k = e >= 7 ? 3 : (e >= 3 ? 2 : (e >= 1 ? 1 : 0));
+        int g = e - ((1 << k) - 1);
+        TW1[blk1 * 16 + e] = P.iw[((size_t)1 << (n1 + k)) + ((size_t)b1 << k) + g];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int g = 0; g < (1 << k); g++)
+          tw2.t[(1 << k) - 1 + g] = P.iw[((size_t)1 << (n1 + 4 + k)) + ((size_t)b2 << (4 + k)) + ((size_t)hi << k) + g];
+      __syncthreads();
+    }
     u64* Sb = S + buf * HB1_STAGE;
-    const int nxt = it + gridDim.z;
-    if (nxt < J.nitems) {
-      const u64* src = J.src[nxt] + srcoff;
+    Hb1Unit nxt = cur;
+    if (u + 1 < uend) {
+      nxt = hb1_unit(u + 1, G, J.nitems);
+      const u64* src = src_ptr(nxt);
       u64* Sn = S + (buf ^ 1) * HB1_STAGE;
 #pragma unroll
       for (int l = 0; l < 16; l++) hb1_cp8(Sn + own + l, src + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
@@ -304,10 +339,11 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = Sb[blk1 * HB1_BS + HB1_RS * r + lo];
     hb1_r16_inv(a, tw1, nq, q3);
-    u64* dst = J.dst[it] + dstoff;
+    u64* dst = J.dst[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN) + ((size_t)b1 << 8) + lo;
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon3(a[r], q);
     __syncthreads();
+    cur = nxt;
   }
   hb1_cp_wait<0>();
 }
@@ -407,7 +443,7 @@ struct Hb1ConvJob {
   u64* stats;
 };
 
-__global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
+__global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
   HB_SMEM_DECL
   const HbConvDev* cv = J.cv;
   const int n = cv->n, nt = cv->nt, NG = J.ngroups;
@@ -464,26 +500,29 @@ __global__ void __launch_bounds__(512, 1) k1_conv(const HbPrimeDev* __restrict__
     const HbPrimeDev P = primes[pi];
     const u64 q = P.q, nq = P.nq, q3 = P.q3;
     const u64* ct = cv->c + (size_t)t * n;
-    u64 ahi[16], alo[16];
+    u64 a[16];
     {
-      const u64 nq = cv->negQ[t], pq = cv->Qmod[t];
+      const u64 negq = cv->negQ[t], posq = cv->Qmod[t];
 #pragma unroll
-      for (int r = 0; r < 16; r++) {
-        const i64 v = Vb[c * 256 + 16 * r + x];
-        const u64 m = v >= 0 ? (u64)v : (u64)(-v);
-        const u64 f = v >= 0 ? nq : pq;
-        alo[r] = m * f; ahi[r] = __umul64hi(m, f);
+      for (int h = 0; h < 2; h++) {   // two halves of 8 coefficients: 32 accumulator registers live
+        u64 ahi[8], alo[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const i64 v = Vb[c * 256 + 16 * (8 * h + r) + x];
+          const u64 m = v >= 0 ? (u64)v : (u64)(-v);
+          const u64 f = v >= 0 ? negq : posq;
+          alo[r] = m * f; ahi[r] = __umul64hi(m, f);
+        }
+        for (int j = 0; j < n; j++) {
+          const u64 cj = ct[j];
+          const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x + HB1_RS * 8 * h;
+#pragma unroll
+          for (int r = 0; r < 8; r++) hb1_mac128(ahi[r], alo[r], Yj[HB1_RS * r], cj);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) a[8 * h + r] = hb_reduce128_lazy(ahi[r], alo[r], P);   // [0,4q): fine for the CT network
       }
     }
-    for (int j = 0; j < n; j++) {
-      const u64 cj = ct[j];
-      const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x;
-#pragma unroll
-      for (int r = 0; r < 16; r++) hb1_mac128(ahi[r], alo[r], Yj[HB1_RS * r], cj);
-    }
-    u64 a[16];
-#pragma unroll
-    for (int r = 0; r < 16; r++) a[r] = hb_reduce128(ahi[r], alo[r], P);
     {
       Hb1TwPtr tw;
       tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;

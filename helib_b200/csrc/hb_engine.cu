@@ -154,6 +154,9 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->max_smem = 200 * 1024;
   { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
   c->resident_ctas = 296;
+#ifdef HB_SIM
+  c->resident_ctas = 7;   // few, odd: every simulated CTA walks several units and crosses (row, block-group) boundaries
+#endif
 #ifndef HB_SIM
   { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->resident_ctas = 2 * prop.multiProcessorCount; }
 #endif
@@ -416,8 +419,8 @@ static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* 
     for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
     J.nitems = nitems;
     for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
-    unsigned gx = 1u << (n1 - 4);
-    dim3 grid(gx, nr, pick_item_groups(c, (long)gx * nr, nitems));
+    long units = (long)nr * nitems << (n1 - 4);
+    dim3 grid((unsigned)std::min<long>(units, c->resident_ctas));   // persistent CTAs, balanced contiguous chunks
     pre_launch(c);
     if (dir > 0) { HB_LAUNCH(k1_fwd_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k1_fwd_blk_subscale" : "k1_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
     else { HB_LAUNCH(k1_inv_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
@@ -621,11 +624,11 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   if (v1_cols_ok(c)) {
     // number of 64-thread row groups: best balance of the n source rows and nt target rows
     int ng = 0; double best = -1; size_t smem1 = 0;
-    for (int g = 8; g >= 4; g--) {
+    for (int g = 10; g >= 4; g--) {
       size_t sm = ((size_t)(n + g) * HB1_TS + 1024) * sizeof(u64);
-      if (sm > 220 * 1024) continue;
+      if (sm > 224 * 1024) continue;
       double work = n + 1.4 * nt, slots = (double)((n + g - 1) / g) + 1.4 * ((nt + g - 1) / g);
-      double util = work / (slots * g) * (0.75 + 0.25 * g / 8.0);   // mild preference for more warps
+      double util = work / slots;   // rows finished per row-time: rewards both balance and more groups
       if (util > best) { best = util; ng = g; smem1 = sm; }
     }
     if (ng > 0) {
