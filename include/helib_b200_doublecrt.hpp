@@ -1,0 +1,268 @@
+// helib_b200_doublecrt.hpp -- header-only C++17 mirror of helib::DoubleCRT over the C ABI.
+//
+// Same method names, argument meaning and error behaviour as the reference class
+// (include/helib/DoubleCRT.h:120-463), so that a maintainer can alias `helib::DoubleCRT` to
+// `hb::DoubleCRT` inside an NTL-equipped HElib build.  NTL types are replaced by
+// plain C++ ones here (ZZX -> vector of two's-complement limbs, IndexSet -> hb::IndexSet) because
+// this repository cannot link NTL; the shim in INTEGRATION.md shows the two conversions.
+//
+// Value semantics like the reference: copying a DoubleCRT copies its rows (device-to-device).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "helib_b200.h"
+#include "helib_b200_chain.h"
+
+namespace hb {
+
+// helib's exception taxonomy (include/helib/exceptions.h:52-139)
+struct RuntimeError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct LogicError : std::logic_error { using std::logic_error::logic_error; };
+struct InvalidArgument : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+
+inline void check(int rc) {
+  if (rc == HB_OK) return;
+  std::string msg = hb_last_error();
+  if (rc == HB_ERR_INDEX_SET) throw RuntimeError(msg);
+  if (rc == HB_ERR_BAD_ARG) throw InvalidArgument(msg);
+  if (rc == HB_ERR_UNSUPPORTED) throw LogicError(msg);
+  throw RuntimeError(msg);
+}
+
+// helib::IndexSet (include/helib/IndexSet.h) restricted to what the hot path uses
+class IndexSet {
+  std::set<long> s_;
+ public:
+  IndexSet() = default;
+  IndexSet(long lo, long hi) { for (long i = lo; i <= hi; i++) s_.insert(i); }
+  explicit IndexSet(long i) { s_.insert(i); }
+  IndexSet(std::initializer_list<long> l) : s_(l) {}
+  template <class It> IndexSet(It a, It b) : s_(a, b) {}
+  static IndexSet emptySet() { return IndexSet(); }
+  long card() const { return (long)s_.size(); }
+  bool contains(long i) const { return s_.count(i) != 0; }
+  bool contains(const IndexSet& o) const { return std::includes(s_.begin(), s_.end(), o.s_.begin(), o.s_.end()); }
+  bool disjointFrom(const IndexSet& o) const { for (long i : o.s_) if (s_.count(i)) return false; return true; }
+  void insert(long i) { s_.insert(i); }
+  void insert(const IndexSet& o) { s_.insert(o.s_.begin(), o.s_.end()); }
+  void remove(long i) { s_.erase(i); }
+  void remove(const IndexSet& o) { for (long i : o.s_) s_.erase(i); }
+  void retain(const IndexSet& o) { for (auto it = s_.begin(); it != s_.end();) it = o.s_.count(*it) ? std::next(it) : s_.erase(it); }
+  long first() const { return s_.empty() ? 0 : *s_.begin(); }
+  long last() const { return s_.empty() ? -1 : *s_.rbegin(); }
+  bool isInterval() const { return s_.empty() || last() - first() + 1 == card(); }
+  auto begin() const { return s_.begin(); }
+  auto end() const { return s_.end(); }
+  bool operator==(const IndexSet& o) const { return s_ == o.s_; }
+  bool operator!=(const IndexSet& o) const { return s_ != o.s_; }
+  bool operator<=(const IndexSet& o) const { return o.contains(*this); }
+  bool operator>=(const IndexSet& o) const { return contains(o); }
+  IndexSet operator|(const IndexSet& o) const { IndexSet r = *this; r.insert(o); return r; }
+  IndexSet operator&(const IndexSet& o) const { IndexSet r = *this; r.retain(o); return r; }
+  IndexSet operator/(const IndexSet& o) const { IndexSet r = *this; r.remove(o); return r; }  // set minus
+  std::vector<int32_t> vec() const { return std::vector<int32_t>(s_.begin(), s_.end()); }
+};
+inline bool empty(const IndexSet& s) { return s.card() == 0; }
+inline bool disjoint(const IndexSet& a, const IndexSet& b) { return a.disjointFrom(b); }
+
+// helib::Context reduced to the chain + its device image (include/helib/Context.h)
+class Context {
+  hb_chain* chain_ = nullptr;
+  hb_ctx* ctx_ = nullptr;
+  std::vector<uint64_t> primes_;
+  IndexSet small_, ctxt_, special_;
+  std::vector<IndexSet> digits_;
+  long m_, phim_;
+ public:
+  Context(long m, long p, long r, long bits, long c, int device = 0) : m_(m) {
+    if (hb_chain_build(&chain_, (uint64_t)m, p, (int)r, (int)bits, (int)c, 0, 3, 0, 3.2) != HB_OK)
+      throw InvalidArgument(hb_chain_last_error());
+    int np, ns, nc, nsp, nd; int64_t phim;
+    hb_chain_info(chain_, &np, &ns, &nc, &nsp, &nd, &phim);
+    phim_ = (long)phim;
+    primes_.resize(np);
+    std::vector<int32_t> kind(np), dig(np);
+    hb_chain_get(chain_, primes_.data(), kind.data(), dig.data());
+    digits_.resize(nd);
+    std::vector<int32_t> sp;
+    for (int i = 0; i < np; i++) {
+      if (kind[i] == 0) small_.insert(i);
+      else if (kind[i] == 1) { ctxt_.insert(i); if (dig[i] >= 0) digits_[dig[i]].insert(i); }
+      else { special_.insert(i); sp.push_back(i); }
+    }
+    check(hb_ctx_create(&ctx_, device, (uint64_t)m, np, primes_.data(), nullptr));
+    check(hb_ctx_set_chain(ctx_, dig.data(), nd, sp.data(), (int)sp.size()));
+  }
+  ~Context() { if (ctx_) hb_ctx_destroy(ctx_); if (chain_) hb_chain_destroy(chain_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  long getM() const { return m_; }
+  long getPhiM() const { return phim_; }
+  long numPrimes() const { return (long)primes_.size(); }
+  long ithPrime(long i) const { return (long)primes_.at(i); }
+  const IndexSet& getSmallPrimes() const { return small_; }
+  const IndexSet& getCtxtPrimes() const { return ctxt_; }
+  const IndexSet& getSpecialPrimes() const { return special_; }
+  const std::vector<IndexSet>& getDigits() const { return digits_; }
+  const IndexSet& getDigit(long i) const { return digits_.at(i); }
+  hb_ctx* handle() const { return ctx_; }
+  hb_chain* chain() const { return chain_; }
+  void sync() const { check(hb_ctx_sync(ctx_)); }
+};
+
+class DoubleCRT {
+  const Context* context_;
+  IndexSet set_;
+  hb_poly* p_ = nullptr;
+  void alloc() { check(hb_poly_create(context_->handle(), &p_)); }
+ public:
+  // DoubleCRT(context, indexSet): zero object on the given primes (DoubleCRT.h:153-158)
+  DoubleCRT(const Context& ctx, const IndexSet& s) : context_(&ctx), set_(s) { alloc(); }
+  // DoubleCRT(zzX poly, context, indexSet): small-coefficient polynomial (DoubleCRT.h:140-151)
+  DoubleCRT(const std::vector<long>& poly, const Context& ctx, const IndexSet& s) : context_(&ctx), set_(s) {
+    alloc();
+    const long N = ctx.getPhiM(), np = ctx.numPrimes();
+    if ((long)poly.size() > N) throw InvalidArgument("polynomial degree >= phi(m)");
+    std::vector<uint64_t> dense((size_t)np * N, 0);
+    for (long i : s) {
+      const long q = ctx.ithPrime(i);
+      for (size_t k = 0; k < poly.size(); k++) { long v = poly[k] % q; dense[(size_t)i * N + k] = (uint64_t)(v < 0 ? v + q : v); }
+    }
+    auto idx = s.vec();
+    if (!idx.empty()) { check(hb_poly_upload(p_, idx.data(), (int)idx.size(), dense.data())); hb_poly* arr[1] = {p_}; check(hb_ntt_fwd(arr, 1, idx.data(), (int)idx.size())); }
+  }
+  DoubleCRT(const DoubleCRT& o) : context_(o.context_), set_(o.set_) {
+    alloc();
+    auto idx = set_.vec();
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; hb_poly* s[1] = {o.p_}; check(hb_pointwise(HB_OP_COPY, d, s, 1, idx.data(), (int)idx.size())); }
+  }
+  DoubleCRT& operator=(const DoubleCRT& o) {
+    if (this == &o) return *this;
+    if (context_ != o.context_) throw RuntimeError("DoubleCRT assignment: incompatible contexts");
+    set_ = o.set_;
+    auto idx = set_.vec();
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; hb_poly* s[1] = {o.p_}; check(hb_pointwise(HB_OP_COPY, d, s, 1, idx.data(), (int)idx.size())); }
+    return *this;
+  }
+  ~DoubleCRT() { if (p_) hb_poly_destroy(p_); }
+
+  const Context& getContext() const { return *context_; }
+  const IndexSet& getIndexSet() const { return set_; }
+  hb_poly* handle() const { return p_; }
+
+  // Op<Add/Sub/Mul> (src/DoubleCRT.cpp:216-337): other must cover this's primes
+  DoubleCRT& Op(const DoubleCRT& other, int op, bool matchIndexSets) {
+    if (context_ != other.context_) throw RuntimeError("DoubleCRT::Op: incompatible objects");
+    if (matchIndexSets && !(set_ >= other.set_)) throw RuntimeError("DoubleCRT::Op: matchIndexSets not honored");
+    if (!(set_ <= other.set_)) throw RuntimeError("DoubleCRT::Op: !(map.getIndexSet() <= other.map.getIndexSet())");
+    auto idx = set_.vec();
+    if (idx.empty()) return *this;
+    hb_poly* d[1] = {p_}; hb_poly* s[1] = {other.p_};
+    check(hb_pointwise(op, d, s, 1, idx.data(), (int)idx.size()));
+    return *this;
+  }
+  DoubleCRT& Add(const DoubleCRT& o, bool matchIndexSets = true) { return Op(o, HB_OP_ADD, matchIndexSets); }
+  DoubleCRT& Sub(const DoubleCRT& o, bool matchIndexSets = true) { return Op(o, HB_OP_SUB, matchIndexSets); }
+  DoubleCRT& Mul(const DoubleCRT& o, bool matchIndexSets = true) { return Op(o, HB_OP_MUL, matchIndexSets); }
+  DoubleCRT& operator+=(const DoubleCRT& o) { return Add(o); }
+  DoubleCRT& operator-=(const DoubleCRT& o) { return Sub(o); }
+  DoubleCRT& operator*=(const DoubleCRT& o) { return Mul(o); }
+  DoubleCRT& Negate() {
+    auto idx = set_.vec();
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; check(hb_pointwise(HB_OP_NEG, d, d, 1, idx.data(), (int)idx.size())); }
+    return *this;
+  }
+  // Op(ZZ, MulFun) for a word-sized scalar (src/DoubleCRT.cpp:339-361)
+  DoubleCRT& operator*=(long num) {
+    auto idx = set_.vec();
+    std::vector<uint64_t> sc;
+    for (int i : idx) { long q = context_->ithPrime(i); long v = num % q; sc.push_back((uint64_t)(v < 0 ? v + q : v)); }
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; check(hb_scale_rows(d, 1, idx.data(), (int)idx.size(), sc.data())); }
+    return *this;
+  }
+  // operator/= by the product of a set of chain primes (what the hot path divides by; src/DoubleCRT.cpp:1122-1139)
+  DoubleCRT& divideByPrimes(const IndexSet& f) {
+    auto idx = set_.vec(), fi = f.vec();
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; check(hb_scale_by_primes(d, 1, idx.data(), (int)idx.size(), fi.data(), (int)fi.size(), 1)); }
+    return *this;
+  }
+  // automorph / complexConj (src/DoubleCRT.cpp:1160-1255)
+  void automorph(long k) {
+    DoubleCRT tmp(*this);
+    auto idx = set_.vec();
+    if (idx.empty()) return;
+    hb_poly* d[1] = {p_}; hb_poly* s[1] = {tmp.p_};
+    check(hb_automorph(d, s, 1, idx.data(), (int)idx.size(), (uint64_t)k));
+  }
+  void complexConj() { automorph(context_->getM() - 1); }
+  // removePrimes / addPrimes / addPrimesAndScale (src/DoubleCRT.cpp:565-647)
+  void removePrimes(const IndexSet& s) { set_.remove(s); }
+  void addPrimes(const IndexSet& s1) {
+    if (empty(s1)) return;
+    auto cur = set_.vec(), add = s1.vec();
+    hb_poly* d[1] = {p_};
+    check(hb_add_primes(d, 1, cur.data(), (int)cur.size(), add.data(), (int)add.size()));
+    set_.insert(s1);
+  }
+  double addPrimesAndScale(const IndexSet& s1) {
+    if (empty(s1)) return 0.0;
+    auto cur = set_.vec(), add = s1.vec();
+    hb_poly* d[1] = {p_};
+    check(hb_add_primes_and_scale(d, 1, cur.data(), (int)cur.size(), add.data(), (int)add.size()));
+    bool was_empty = empty(set_);
+    set_.insert(s1);
+    if (was_empty) return 0.0;
+    double lf = 0; for (long i : s1) lf += std::log((double)context_->ithPrime(i));
+    return lf;
+  }
+  // scaleDownToSet (src/DoubleCRT.cpp:1464-1516)
+  void scaleDownToSet(const IndexSet& s, long ptxtSpace) {
+    IndexSet diff = set_ / s;
+    if (empty(diff)) return;
+    if (ptxtSpace < 1) throw InvalidArgument("ptxtSpace must be at least 1");
+    auto cur = set_.vec(), keep = (set_ & s).vec();
+    hb_poly* d[1] = {p_};
+    check(hb_scale_down(d, 1, cur.data(), (int)cur.size(), keep.data(), (int)keep.size(), (uint64_t)ptxtSpace));
+    set_.remove(diff);
+  }
+  // breakIntoDigits (src/DoubleCRT.cpp:479-561); the FP64 noise norm it returns is host metadata (not computed)
+  void breakIntoDigits(std::vector<DoubleCRT>& digits) const {
+    const long maxdig = (long)context_->getDigits().size();
+    digits.clear();
+    IndexSet all = set_ | context_->getSpecialPrimes();
+    for (long i = 0; i < maxdig; i++) digits.emplace_back(*context_, all);
+    std::vector<hb_poly*> dp;
+    for (auto& d : digits) dp.push_back(d.p_);
+    auto cur = set_.vec();
+    hb_poly* s[1] = {p_};
+    int nd = 0;
+    check(hb_break_into_digits(s, 1, cur.data(), (int)cur.size(), dp.data(), (int)maxdig, &nd));
+    digits.erase(digits.begin() + nd, digits.end());
+  }
+  // toPoly (src/DoubleCRT.cpp:925-1113): N x L little-endian two's-complement limbs
+  std::vector<uint64_t> toPoly(const IndexSet& s, bool positive, int& L) const {
+    auto idx = (set_ & s).vec();
+    L = (int)idx.size() + 1;
+    std::vector<uint64_t> out((size_t)context_->getPhiM() * L);
+    check(hb_to_poly(p_, idx.data(), (int)idx.size(), positive ? 1 : 0, out.data(), L));
+    return out;
+  }
+  // getOneRow (DoubleCRT.h:332-336)
+  std::vector<long> getOneRow(long i) const {
+    if (!set_.contains(i)) throw RuntimeError("getOneRow: prime not in index set");
+    const long N = context_->getPhiM();
+    std::vector<uint64_t> dense((size_t)context_->numPrimes() * N);
+    int32_t idx[1] = {(int32_t)i};
+    check(hb_poly_download(p_, idx, 1, dense.data()));
+    return std::vector<long>(dense.begin() + (size_t)i * N, dense.begin() + (size_t)(i + 1) * N);
+  }
+};
+
+}  // namespace hb

@@ -1,0 +1,70 @@
+// C++ test of the helib::DoubleCRT mirror (include/helib_b200_doublecrt.hpp) over the C ABI.
+// Exercises the reference's own unit-level properties for this path:
+//   FFT o iFFT = identity on polynomials          (tests/TestHEXL.cpp:189-218)
+//   addPrimes / removePrimes round trip            
+//   index-set precondition failures raise          (src/DoubleCRT.cpp:227-253)
+//   (a*b) computed in evaluation form == schoolbook negacyclic product (toPoly)
+// Exit codes: 0 ok, 3 no CUDA device (expected on the CPU box), 1 failure.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "helib_b200_doublecrt.hpp"
+
+static long coeff_of(const std::vector<uint64_t>& limbs, int L, long k) {  // small values only
+  return (long)limbs[(size_t)k * L];
+}
+
+int main() {
+  if (hb_device_count() <= 0) { std::printf("no CUDA device: %s\n", "engine has no CPU path"); return 3; }
+  try {
+    hb::Context ctx(/*m=*/4096, /*p=*/257, /*r=*/1, /*bits=*/120, /*c=*/2);
+    const long N = ctx.getPhiM();
+    const hb::IndexSet S = ctx.getCtxtPrimes();
+    std::vector<long> f(N), g(N);
+    unsigned long long st = 12345;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (long)((st >> 33) % 21) - 10; };
+    for (long i = 0; i < N; i++) { f[i] = rnd(); g[i] = rnd(); }
+    hb::DoubleCRT F(f, ctx, S), G(g, ctx, S);
+    // product in evaluation form vs schoolbook
+    hb::DoubleCRT H(F);
+    H *= G;
+    int L = 0;
+    std::vector<uint64_t> hp = H.toPoly(S, false, L);
+    for (long k : {0L, 1L, N / 2, N - 1}) {
+      long acc = 0;
+      for (long i = 0; i < N; i++) { long j = k - i; if (j >= 0) acc += f[i] * g[j]; else acc -= f[i] * g[j + N]; }
+      if (coeff_of(hp, L, k) != acc) { std::printf("product mismatch at %ld\n", k); return 1; }
+    }
+    // addPrimes to the special primes and back
+    hb::DoubleCRT E(F);
+    E.addPrimes(ctx.getSpecialPrimes());
+    std::vector<long> row_new = E.getOneRow(ctx.getSpecialPrimes().first());
+    hb::DoubleCRT F2(f, ctx, S | ctx.getSpecialPrimes());
+    if (row_new != F2.getOneRow(ctx.getSpecialPrimes().first())) { std::printf("addPrimes row mismatch\n"); return 1; }
+    E.removePrimes(ctx.getSpecialPrimes());
+    if (E.getOneRow(S.first()) != F.getOneRow(S.first())) { std::printf("removePrimes changed a row\n"); return 1; }
+    // scaleDownToSet keeps the value / P up to the small rounding term: (P*x) scaled down by P == x
+    hb::DoubleCRT X(F);
+    X.addPrimesAndScale(ctx.getSpecialPrimes());
+    X.scaleDownToSet(S, 1);
+    if (X.getOneRow(S.first()) != F.getOneRow(S.first())) { std::printf("scale up/down is not the identity\n"); return 1; }
+    // digits: two digits, each over S | special
+    std::vector<hb::DoubleCRT> digits;
+    F.breakIntoDigits(digits);
+    if (digits.size() != ctx.getDigits().size()) { std::printf("digit count\n"); return 1; }
+    // error behaviour
+    bool threw = false;
+    try { hb::DoubleCRT A(ctx, S), B(ctx, hb::IndexSet(S.first())); A += B; } catch (const hb::RuntimeError&) { threw = true; }
+    if (!threw) { std::printf("missing RuntimeError for index-set violation\n"); return 1; }
+    threw = false;
+    try { hb::DoubleCRT A(F); A.addPrimes(hb::IndexSet(S.first())); } catch (const hb::RuntimeError&) { threw = true; }
+    if (!threw) { std::printf("missing RuntimeError for non-disjoint addPrimes\n"); return 1; }
+    ctx.sync();
+    std::printf("shim OK: N=%ld primes=%ld digits=%zu\n", N, ctx.numPrimes(), digits.size());
+    return 0;
+  } catch (const std::exception& e) {
+    std::printf("exception: %s\n", e.what());
+    return 1;
+  }
+}

@@ -1,0 +1,35 @@
+"""The header-only C++ mirror of helib::DoubleCRT (include/helib_b200_doublecrt.hpp) compiles against
+the C ABI and links the product library; on a GPU it runs the reference's unit-level properties."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
+
+
+def build_exe():
+    src = os.path.join(ROOT, "tests", "cpp", "test_shim.cpp")
+    deps = [src, os.path.join(ROOT, "include", "helib_b200_doublecrt.hpp"), os.path.join(ROOT, "helib_b200", "libhelib_b200.so")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
+                               "-L" + os.path.join(ROOT, "helib_b200"), "-lhelib_b200", "-Wl,-rpath," + os.path.join(ROOT, "helib_b200")])
+    return EXE
+
+
+def test_shim_compiles_links_and_refuses_without_gpu():
+    from helib_b200 import load_library
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if load_library().hb_device_count() <= 0:
+        assert r.returncode == 3, r.stdout + r.stderr      # no device: loud refusal, no CPU fallback
+    else:
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_runs_on_gpu():
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "shim OK" in r.stdout, r.stdout + r.stderr

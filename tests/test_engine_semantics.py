@@ -1,0 +1,201 @@
+"""Engine through the C ABI: golden fixtures, exact-CRT fallback, reference error behaviour and
+an end-to-end BGV semantic check (encrypt -> multiply -> relinearise -> mod-down -> decrypt).
+Each test runs on the CPU kernel-logic simulator (not gpu) and on the real CUDA library (-m gpu)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import orc
+import pyoracle as po
+from common import chain, make, rows_equal
+from helib_b200 import HbError
+
+
+def backends():
+    return [pytest.param("sim", id="sim"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=backends())
+def lib(request):
+    return request.getfixturevalue("sim_lib" if request.param == "sim" else "cuda_lib")
+
+
+def test_golden_vectors_through_engine(lib):
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for fn in sorted(f for f in os.listdir(gdir) if f.endswith(".json")):
+        G = json.load(open(os.path.join(gdir, fn)))
+        ch, psis, O, E = make(lib, *G["params"])
+        S = ch.ctxt
+        Sp = sorted(S + ch.special)
+        x = O.zeros()
+        for i in S:
+            x[i] = np.array(G["x"][str(i)], dtype=np.uint64)
+        P = E.poly(x, S)
+        assert orc.limbs_to_ints(E.to_poly(P, S)) == G["to_poly"]
+        digs = E.break_into_digits([P], S)[0]
+        for d, ref in enumerate(G["digits_rows"]):
+            got = digs[d].download(Sp)
+            for i, row in ref.items():
+                assert list(got[int(i)]) == row
+        y = O.zeros()
+        for i in Sp:
+            y[i] = np.array(G["y"][str(i)], dtype=np.uint64)
+        Y = E.poly(y, Sp)
+        E.scale_down([Y], Sp, S, G["ptxt_space"])
+        got = Y.download(S)
+        for i in S:
+            assert list(got[i]) == G["scale_down_rows"][str(i)]
+
+
+@pytest.mark.parametrize("cfg", [(64, 257, 1, 120, 2), (4096, 3, 1, 110, 2), (1 << 17, 257, 1, 230, 2)])
+def test_exact_crt_fallback_on_boundary_values(lib, cfg):
+    """Coefficients whose CRT value sits on the rounding boundary (+-(Q-1)/2, 0, +-1) force the
+    exact multi-limb path; results must still equal the oracle bit for bit."""
+    ch, psis, O, E = make(lib, *cfg)
+    n = ch.phim
+    cur = ch.ctxt + ch.special
+    keep = ch.ctxt[:1]
+    drop = [i for i in cur if i not in keep]
+    Pd = ch.product(drop)
+    assert Pd.bit_length() > 70
+    half = (Pd - 1) // 2
+    rnd = random.Random(7)
+    Qall = ch.product(cur)
+    specials = [half, -half, 0, 1, -1, half - 1, -(half - 1), half + Pd, -half + 5 * Pd]
+    coeffs = [specials[k % len(specials)] + Pd * rnd.randrange(1 << 40) * (k % 3 == 2) if k < 64 else rnd.randrange(Qall) for k in range(n)]
+    limbs = orc.ints_to_limbs(coeffs, len(cur) + 1)
+    x = O.zeros()
+    O.fft_bigpoly(limbs, cur, x)
+    for p in (1, 2, ch.p ** ch.r):
+        P = E.poly(x, cur)
+        E.reset_stats()
+        E.scale_down([P], cur, keep, p)
+        ref = x.copy(); O.scale_down(ref, cur, keep, p)
+        assert rows_equal(P.download(keep), ref, keep), p
+        assert E.stats()["exact_fallbacks"] > 0
+    # toPoly of the special rows reproduces the planted boundary values exactly
+    P = E.poly(x, cur)
+    got = orc.limbs_to_ints(E.to_poly(P, drop))
+    assert got[:9] == [po.bal(s, Pd) for s in specials]
+
+
+def test_reference_error_behaviour(lib):
+    """Index-set preconditions raise like the reference (RuntimeError -> HB_ERR_INDEX_SET = -2;
+    InvalidArgument/LogicError -> HB_ERR_BAD_ARG = -1)."""
+    ch, psis, O, E = make(lib, 64, 257, 1, 120, 2)
+    S = ch.ctxt
+    P, Q = E.poly(), E.poly()
+    with pytest.raises(HbError) as ei:          # src/DoubleCRT.cpp:574-575
+        E.add_primes([P], S, [S[0]])
+    assert ei.value.code == -2
+    with pytest.raises(HbError) as ei:          # src/DoubleCRT.cpp:497-498
+        E.break_into_digits([P], S + ch.special)
+    assert ei.value.code == -2
+    with pytest.raises(HbError) as ei:          # src/DoubleCRT.cpp:1165-1167
+        E.automorph([Q], [P], S, 2)
+    assert ei.value.code == -2
+    with pytest.raises(HbError) as ei:          # src/DoubleCRT.cpp:1474-1476
+        E.scale_down([P], S, [ch.special[0]], 1)
+    assert ei.value.code == -2
+    with pytest.raises(HbError) as ei:
+        E.ntt_fwd([P], [len(ch.primes)])
+    assert ei.value.code == -1
+    with pytest.raises(HbError) as ei:          # ptxtSpace >= 1 (src/DoubleCRT.cpp:1472)
+        E.scale_down([P], S + ch.special, S, 0)
+    assert ei.value.code == -1
+    # nothing-to-do cases return quietly (src/DoubleCRT.cpp:569-572, 1468-1470)
+    E.add_primes([P], S, [])
+    E.scale_down([P], S, S, 1)
+    # two contexts do not mix (src/DoubleCRT.cpp:222-223)
+    ch2, _, _, E2 = make(lib, 64, 257, 1, 120, 2)
+    with pytest.raises(HbError) as ei:
+        E.pointwise("add", [P], [E2.poly()], S)
+    assert ei.value.code == -2
+
+
+def sample_small(rng, n, kind):
+    if kind == "ternary":
+        return [int(x) for x in rng.integers(-1, 2, n)]
+    return [int(round(x)) for x in rng.normal(0, 3.2, n)]   # include/helib/Context.h:1080 (stdev 3.2)
+
+
+def dcrt_of(O, ch, coeffs, idx):
+    """Small signed polynomial -> evaluation rows on idx (DoubleCRT(poly, context, s), src/DoubleCRT.cpp:68-85)."""
+    d = O.zeros()
+    for i in idx:
+        d[i] = np.array([c % ch.primes[i] for c in coeffs], dtype=np.uint64)
+    O.ntt_fwd_rows(d, idx)
+    return d
+
+
+@pytest.mark.parametrize("cfg", [(128, 257, 1, 150, 2), (4096, 17, 1, 160, 3)])
+def test_bgv_multiply_decrypts_to_product(lib, cfg):
+    """decrypt(mul + relin + mod-down (E(a), E(b))) == a*b (BGV, exact).
+    Key material restated from RLWE1 / GenKeySWmatrix (src/keys.cpp:40-72,1159-1256):
+    b_i = p*e_i - a_i*s + P*(prod_{j<i} Q_j)*s^2."""
+    ch, psis, O, E = make(lib, *cfg)
+    p, n = ch.p, ch.phim
+    rng = np.random.default_rng(11)
+    full = ch.ctxt + ch.special
+    s = sample_small(rng, n, "ternary")
+    S_dcrt = dcrt_of(O, ch, s, full)
+    s2 = S_dcrt.copy(); O.pointwise("mul", s2, S_dcrt, full)
+
+    def encrypt(msg, idx):
+        a = O.random(rng, idx)
+        c0 = dcrt_of(O, ch, [p * e + m_ for e, m_ in zip(sample_small(rng, n, "gauss"), msg)], idx)
+        t = a.copy(); O.pointwise("mul", t, S_dcrt, idx)
+        O.pointwise("sub", c0, t, idx)          # c0 = p*e + m - a*s
+        return c0, a
+
+    # key-switching matrix s^2 -> s
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = []
+    from_key = s2.copy()
+    O.scale_by_primes(from_key, full, ch.special)            # P * s^2
+    for i in range(nd):
+        b = dcrt_of(O, ch, [p * e for e in sample_small(rng, n, "gauss")], full)
+        t = evk_a[i].copy(); O.pointwise("mul", t, S_dcrt, full)
+        O.pointwise("sub", b, t, full)
+        O.pointwise("add", b, from_key, full)
+        evk_b.append(b)
+        O.scale_by_primes(from_key, full, ch.digits[i])       # *= prod(digit i)
+    evk_b = np.stack(evk_b)
+
+    ma = [int(x) for x in rng.integers(0, p, n)]
+    mb = [int(x) for x in rng.integers(0, p, n)]
+    S_in = ch.ctxt
+    S = ch.ctxt[:-1]
+    a0, a1 = encrypt(ma, S_in)
+    b0, b1 = encrypt(mb, S_in)
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    A0, A1, B0, B1 = E.poly(a0, S_in), E.poly(a1, S_in), E.poly(b0, S_in), E.poly(b1, S_in)
+    E.mul_relin_moddown([A0], [A1], [B0], [B1], S_in, S, p, EA, EB)
+    # decrypt: (c0 + c1*s) over S, balanced, mod p  (src/keys.cpp:1327-1400)
+    E.pointwise("mul", [A1], [E.poly(S_dcrt, S)], S)
+    E.pointwise("add", [A0], [A1], S)
+    dec = orc.limbs_to_ints(E.to_poly(A0, S))
+    Q = ch.product(S)
+    assert max(abs(v) for v in dec) < Q // 4, "noise overflow: parameters too tight for the test"
+    # each operand's mod-down by the dropped prime multiplies its plaintext by q_drop^-1 mod p
+    qd = ch.primes[S_in[-1]]
+    f = pow(pow(qd, -1, p), 2, p)
+    expect = [v * f % p for v in po.negacyclic_mul_schoolbook(ma, mb, p)] if n <= 256 else None
+    got = [v % p for v in dec]
+    if expect is not None:
+        assert got == expect
+    # and bit-exact agreement with the oracle's own run of the same circuit
+    parts = [x.copy() for x in (a0, a1, b0, b1)]
+    for x in parts:
+        O.scale_down(x, S_in, S, p)
+    t0, t1, t2 = O.tensor(*parts, S)
+    r0, r1 = O.relinearize(t0, t1, t2, S, evk_a, evk_b)
+    Sp = sorted(S + ch.special)
+    O.scale_down(r0, Sp, S, p); O.scale_down(r1, Sp, S, p)
+    O.pointwise("mul", r1, S_dcrt, S); O.pointwise("add", r0, r1, S)
+    assert orc.limbs_to_ints(O.to_poly(r0, S)) == dec
