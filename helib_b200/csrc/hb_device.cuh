@@ -198,6 +198,7 @@ struct HbConvJob {
   const u64* src[HB_MAXB];   // "blk"-phase output of the inverse transform (rows src_prime)
   u64* dst[HB_MAXB];         // "cols"-phase output of the forward transform (rows tgt_prime)
   u64* stats;                // [0] += number of exact-fallback evaluations
+  int src_is_y;              // 1: src rows already hold y_j = coeff * (Q/q_j)^-1 mod q_j in coefficient order
 };
 
 struct HbCrtJob {            // DoubleCRT::toPoly: exact balanced integer per coefficient
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(HB_THREADS) k_conv(const HbPrimeDev* __restric
     u64* T = Y + (size_t)j * TILE;
     hb_cols_load(T, src + ((size_t)pi << J.logN), n1, lb, logw, c0);
     __syncthreads();
+    if (J.src_is_y) continue;   // prime-sharded path: y_j rows were produced (and all-gathered) beforehand
     hb_tile_inv_cols(T, n1, logw, P.iw, P.q);
     const u64 t = cv->tn[j], ts = cv->tn_s[j];
     for (int e = tid; e < TILE; e += nthr) T[e] = hb_mul_shoup(T[e], t, ts, P.q);

@@ -441,6 +441,7 @@ struct Hb1ConvJob {
   const u64* src[HB_MAXB];
   u64* dst[HB_MAXB];
   u64* stats;
+  int src_is_y;   // 1: sources are y_j coefficient rows already (prime-sharded path)
 };
 
 __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
@@ -467,6 +468,11 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     u64 a[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = s[(size_t)(16 * x + l) << 8];
+    if (J.src_is_y) {   // uniform per launch: no transform, just stage the tile
+#pragma unroll
+      for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
+      continue;
+    }
     {
       Hb1TwPtr tw;
       tw.p[0] = P.iw + 16 + x; tw.p[1] = P.iw + 32 + 2 * x; tw.p[2] = P.iw + 64 + 4 * x; tw.p[3] = P.iw + 128 + 8 * x;

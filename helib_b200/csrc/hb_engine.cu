@@ -62,7 +62,7 @@ struct hb_ctx {
   std::vector<HbPrimeDev> h_primes;
   HbPrimeDev* d_primes;
   ulonglong2* d_tw;
-  cudaStream_t stream;
+  cudaStream_t stream; cudaStream_t own_stream; bool stream_external = false;
   std::vector<int> digit_of; int ndigits; std::vector<int> special;
   u64* tmpA; u64* tmpB;
   u64* d_stats;
@@ -80,7 +80,7 @@ struct hb_ctx {
   struct ProfAgg { std::string name; u64 launches; double ms; u64 bytes; };
   std::vector<ProfAgg> prof;
 };
-struct hb_poly { hb_ctx* ctx; u64* d; };
+struct hb_poly { hb_ctx* ctx; u64* d; bool owned = true; };
 
 static int ctx_alloc(hb_ctx* c, void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
@@ -170,6 +170,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     c->q.push_back(qi); c->psi.push_back(ps);
   }
   HB_CUDA(cudaStreamCreate(&c->stream));
+  c->own_stream = c->stream;
 #ifndef HB_SIM
   HB_CUDA(cudaEventCreate(&c->ev0)); HB_CUDA(cudaEventCreate(&c->ev1));
 #endif
@@ -221,7 +222,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->own_stream);
   delete c;
 }
 
@@ -294,8 +295,7 @@ extern "C" int hb_poly_create(hb_ctx* c, hb_poly** out) {
 extern "C" void hb_poly_destroy(hb_poly* p) {
   if (!p) return;
   cudaStreamSynchronize(p->ctx->stream);
-  p->ctx->bytes -= (size_t)p->ctx->nprimes * p->ctx->N * sizeof(u64);
-  cudaFree(p->d);
+  if (p->owned) { p->ctx->bytes -= (size_t)p->ctx->nprimes * p->ctx->N * sizeof(u64); cudaFree(p->d); }
   delete p;
 }
 static int check_idx(hb_ctx* c, const int32_t* idx, int n, const char* who, bool allow_empty = false) {
@@ -614,13 +614,15 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
   return HB_OK;
 }
 
-// inverse-blk (polys -> tmpA), fused conversion (tmpA -> tmpB), for one chunk of items
-static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p) {
+// inverse-blk (polys -> tmpA), fused conversion (tmpA -> tmpB), for one chunk of items.
+// src_is_y: polys already hold the y_j coefficient rows (prime-sharded path): no inverse phase at all.
+static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p, int src_is_y = 0) {
   HB_TRY(ctx_scratch(c));
   ConvEntry* E; HB_TRY(get_conv(c, src, n, tgt, nt, p, &E));
   u64* tA[HB_MAXB]; u64* tB[HB_MAXB];
   tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
-  HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
+  if (src_is_y) { for (int i = 0; i < nit; i++) tA[i] = polys[i]; }
+  else HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
   if (v1_cols_ok(c)) {
     // number of 64-thread row groups: best balance of the n source rows and nt target rows
     int ng = 0; double best = -1; size_t smem1 = 0;
@@ -633,7 +635,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
     }
     if (ng > 0) {
       Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
-      J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats;
+      J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats; J1.src_is_y = src_is_y;
       for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
       pre_launch(c);
       HB_LAUNCH(k1_conv, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
@@ -646,7 +648,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   size_t smem = ((size_t)(n + 2) << (n1 + lw)) * sizeof(u64);
   if (smem > c->max_smem) return hb_fail(HB_ERR_UNSUPPORTED, "base conversion tile needs %zu bytes of shared memory", smem);
   HbConvJob J; memset(&J, 0, sizeof(J));
-  J.cv = E->d; J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw; J.nitems = nit; J.stats = c->d_stats;
+  J.cv = E->d; J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw; J.nitems = nit; J.stats = c->d_stats; J.src_is_y = src_is_y;
   for (int i = 0; i < nit; i++) { J.src[i] = tA[i]; J.dst[i] = tB[i]; }
   dim3 grid(1u << (c->log_blk - lw), nit);
   pre_launch(c);
@@ -788,6 +790,63 @@ extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, u
   if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_to_poly: copy failed: %s", cudaGetErrorString(e)); }
   cudaFree(d_out);
   return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// prime-sharded base conversion: split of hb_add_primes / hb_scale_down at the point
+// where residues must cross shards.  make_y is local to the owner of each source row; after an
+// all-gather of the y rows every rank converts to the target rows it owns.
+extern "C" int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned, hb_poly* const* ypolys) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_conv_make_y")); HB_TRY(check_polys(ypolys, nitems, &c, "hb_conv_make_y"));
+  HB_TRY(check_idx(c, D, nD, "hb_conv_make_y")); HB_TRY(check_idx(c, owned, nOwned, "hb_conv_make_y(owned)", true));
+  if (nOwned == 0) return HB_OK;
+  std::vector<u64> sc(nOwned);
+  for (int k = 0; k < nOwned; k++) {
+    if (std::find(D, D + nD, owned[k]) == D + nD) return hb_fail(HB_ERR_INDEX_SET, "hb_conv_make_y: owned prime %d is not in the source set", owned[k]);
+    u64 q = c->q[owned[k]], r = 1 % q;
+    for (int j = 0; j < nD; j++) if (D[j] != owned[k]) r = h_mulmod(r, c->q[D[j]] % q, q);
+    sc[k] = h_powmod(r, q - 2, q);   // (Q_D / q_j)^-1 mod q_j   (src/DoubleCRT.cpp:1033-1041)
+  }
+  HB_TRY(ctx_scratch(c));
+  HB_TRY(for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
+    return launch_cols(c, -1, (const u64* const*)tA, Y, nit, owned, nOwned);
+  }));
+  return pw_simple(HB_PW_SCALE, ypolys, nullptr, nitems, owned, nOwned, sc.data(), c);
+}
+// mode 0: dst rows tgt = x mod q_t (addPrimes);  mode 1: dst rows tgt = (dst - x)/Q_D (scaleDownToSet)
+extern "C" int hb_conv_from_y(hb_poly* const* ypolys, int nitems, const int32_t* D, int nD, const int32_t* tgt, int nT,
+                              uint64_t ptxt_space, hb_poly* const* dst, int mode) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(ypolys, nitems, &c, "hb_conv_from_y")); HB_TRY(check_polys(dst, nitems, &c, "hb_conv_from_y"));
+  HB_TRY(check_idx(c, D, nD, "hb_conv_from_y")); HB_TRY(check_idx(c, tgt, nT, "hb_conv_from_y(targets)", true));
+  if (nT == 0) return HB_OK;
+  HB_TRY(check_disjoint(D, nD, tgt, nT, "hb_conv_from_y"));
+  if (ptxt_space < 1 || mode < 0 || mode > 1) return hb_fail(HB_ERR_BAD_ARG, "hb_conv_from_y: bad ptxt_space or mode");
+  std::vector<u64> sc;
+  if (mode == 1) HB_TRY(scalars_by_primes(c, tgt, nT, D, nD, 1, sc));
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* Y[HB_MAXB]; u64* Dp[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(ypolys, i0, nit, Y); ptrs_of(dst, i0, nit, Dp); tmp_ptrs(c, c->tmpB, nit, tB);
+    HB_TRY(conv_chunk(c, Y, nit, D, nD, tgt, nT, ptxt_space, 1));
+    return launch_blk(c, +1, (const u64* const*)tB, Dp, nit, tgt, nT, mode, mode == 1 ? sc.data() : nullptr);
+  });
+}
+// Alias caller-owned device memory ([nprimes][N] u64) as a polynomial (not freed by hb_poly_destroy).
+extern "C" int hb_poly_wrap(hb_ctx* c, void* device_ptr, hb_poly** out) {
+  if (!c || !device_ptr || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_wrap: null");
+  hb_poly* p = new hb_poly(); p->ctx = c; p->d = (u64*)device_ptr; p->owned = false;
+  *out = p;
+  return HB_OK;
+}
+// Run the context's launches on a caller-provided CUDA stream (e.g. torch's current stream, so that
+// NCCL collectives issued through torch.distributed are ordered with the kernels).  0 = default stream.
+extern "C" int hb_ctx_set_stream(hb_ctx* c, void* cuda_stream) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_stream: null");
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  c->stream = (cudaStream_t)cuda_stream;
+  c->stream_external = true;
+  return HB_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -77,7 +77,8 @@ class Poly:
     def upload(self, dense, idx):
         assert dense.dtype == np.uint64 and dense.flags["C_CONTIGUOUS"] and dense.shape == (self.eng.np, self.eng.N)
         a, p, n = _idx(idx)
-        self.eng._ck(self.eng.lib.hb_poly_upload(self.h, p, n, dense.ctypes.data_as(u64p)))
+        if n:
+            self.eng._ck(self.eng.lib.hb_poly_upload(self.h, p, n, dense.ctypes.data_as(u64p)))
         return self
 
     def upload_ptr(self, ptr, idx):
@@ -93,7 +94,8 @@ class Poly:
         if out is None:
             out = np.zeros((self.eng.np, self.eng.N), dtype=np.uint64)
         a, p, n = _idx(idx)
-        self.eng._ck(self.eng.lib.hb_poly_download(self.h, p, n, out.ctypes.data_as(u64p)))
+        if n:
+            self.eng._ck(self.eng.lib.hb_poly_download(self.h, p, n, out.ctypes.data_as(u64p)))
         return out
 
 
@@ -312,3 +314,32 @@ class Chain:
         if rc != 0:
             raise HbError(rc, "hb_chain_set4size")
         return [int(x) for x in out[:nout.value]]
+
+
+def _engine_extra(cls):
+    def wrap(self, ptr):
+        """Alias caller-owned device memory (uint64[nprimes][N]) as a Poly (hb_poly_wrap)."""
+        p = Poly.__new__(Poly)
+        p.eng = self
+        p.h = C.c_void_p()
+        self._ck(self.lib.hb_poly_wrap(self.h, C.c_void_p(ptr), C.byref(p.h)))
+        return p
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.hb_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def conv_make_y(self, polys, D, owned, ypolys):
+        a, pd, nd = _idx(D)
+        b, po_, no = _idx(owned)
+        self._ck(self.lib.hb_conv_make_y(_arr(polys), len(polys), pd, nd, po_, no, _arr(ypolys)))
+
+    def conv_from_y(self, ypolys, D, tgt, ptxt_space, dst, mode):
+        a, pd, nd = _idx(D)
+        b, pt, nt = _idx(tgt)
+        self._ck(self.lib.hb_conv_from_y(_arr(ypolys), len(ypolys), pd, nd, pt, nt, C.c_uint64(int(ptxt_space)), _arr(dst), int(mode)))
+
+    cls.wrap, cls.set_stream, cls.conv_make_y, cls.conv_from_y = wrap, set_stream, conv_make_y, conv_from_y
+    return cls
+
+
+_engine_extra(Engine)

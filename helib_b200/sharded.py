@@ -1,0 +1,134 @@
+"""Prime-sharded key switching across GPUs (BASELINE config 4).
+
+One process per GPU.  Rows are sharded by RNS prime index (round-robin inside the ctxt primes and
+inside the special primes, so every rank owns an equal share of every digit); the evaluation-key rows
+are sharded identically and never move.  Residues cross shards at exactly two points, each one
+all-gather over torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests):
+
+  1. breakIntoDigits: the y_j = iNTT(row_j)*(Q_D/q_j)^-1 rows of each digit (l rows in total),
+  2. mod-down: the y rows of the K special primes of both parts.
+
+Everything else (transforms, exact CRT to the owned target rows, mixed-radix updates, evk inner
+product) is local.  torch is plumbing here: tensors own the exchange buffers, torch.distributed
+carries them; all arithmetic is in the engine's kernels (hb_conv_make_y / hb_conv_from_y).
+
+Reference semantics: Ctxt::reLinearize / keySwitchPart / keySwitchDigits (src/Ctxt.cpp:191-230,720-842),
+DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:479-561), Ctxt::modDownToSet (src/Ctxt.cpp:393-562).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def owner_map(ctxt, special, world):
+    """prime index -> owning rank: round-robin within each class."""
+    own = {}
+    for cls in (ctxt, special):
+        for k, i in enumerate(cls):
+            own[i] = k % world
+    return own
+
+
+class ShardedKeySwitch:
+    def __init__(self, eng, ctxt, special, digits, rank=None, world=None, device="cuda"):
+        self.E = eng
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.ctxt, self.special, self.digits = list(ctxt), list(special), [list(d) for d in digits]
+        self.owner = owner_map(self.ctxt, self.special, self.world)
+        self.device = device
+        self._bufs = {}
+
+    def owned(self, idx):
+        return [i for i in idx if self.owner[i] == self.rank]
+
+    # ---- exchange buffers: torch owns the memory, the engine aliases it
+    def _ybuf(self, key):
+        if key not in self._bufs:
+            t = torch.zeros((self.E.np, self.E.N), dtype=torch.int64, device=self.device)
+            self._bufs[key] = (t, self.E.wrap(t.data_ptr()))
+        return self._bufs[key]
+
+    def _all_gather_rows(self, tensors, D):
+        """After this call every rank holds rows D of every tensor in `tensors` (each rank contributed the
+        rows it owns).  One all_gather of a packed [n_items, max_owned, N] buffer."""
+        if self.world == 1:
+            return
+        per = [[i for i in D if self.owner[i] == r] for r in range(self.world)]
+        mx = max(len(p) for p in per)
+        mine = per[self.rank]
+        send = torch.zeros((len(tensors), mx, self.E.N), dtype=torch.int64, device=self.device)
+        if mine:
+            rows = torch.tensor(mine, device=self.device)
+            for k, t in enumerate(tensors):
+                send[k, :len(mine)] = t.index_select(0, rows)
+        flat = torch.empty(self.world * send.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(flat, send.view(-1))
+        recv = flat.view((self.world,) + tuple(send.shape))
+        for r in range(self.world):
+            if r == self.rank or not per[r]:
+                continue
+            rows = torch.tensor(per[r], device=self.device)
+            for k, t in enumerate(tensors):
+                t.index_copy_(0, rows, recv[r, k, :len(per[r])])
+
+    def _sync_engine_to_torch(self):
+        # engine and torch share the stream on GPUs (Engine.set_stream); on the CPU simulator calls are synchronous
+        pass
+
+    def relinearize(self, c0, c1, c2, S, evk_a, evk_b, dig_polys=None):
+        """3-part (1, s, s^2) ciphertexts over ctxt primes S -> 2-part over S | special (rows owned by this
+        rank only).  c0,c1,c2: lists of Poly (batch items) holding at least the owned rows."""
+        E = self.E
+        Sp = sorted(set(S) | set(self.special))
+        oS, oSp, oSpec = self.owned(S), self.owned(Sp), self.owned(self.special)
+        nit = len(c0)
+        # parts with handle 1 / base s: addPrimesAndScale(special) on the owned rows (src/Ctxt.cpp:764-768)
+        if oS:
+            E.scale_by_primes(c0, oS, self.special)
+            E.scale_by_primes(c1, oS, self.special)
+        if oSpec:
+            E.zero_rows(c0, oSpec)
+            E.zero_rows(c1, oSpec)
+        # digits (src/DoubleCRT.cpp:479-561)
+        remaining, nd = set(S), 0
+        while remaining:
+            remaining -= set(self.digits[nd])
+            nd += 1
+        dsets = [[i for i in S if i in self.digits[d]] for d in range(nd)]
+        if dig_polys is None:
+            dig_polys = [[E.poly() for _ in range(nd)] for _ in range(nit)]
+        for d in range(nd):
+            od = self.owned(dsets[d])
+            if od:
+                E.pointwise("copy", [dp[d] for dp in dig_polys], c2, od)
+        for d in range(nd):
+            col = [dp[d] for dp in dig_polys]
+            ys = [self._ybuf(("dig", it)) for it in range(nit)]
+            E.conv_make_y(col, dsets[d], self.owned(dsets[d]), [y[1] for y in ys])
+            self._all_gather_rows([y[0] for y in ys], dsets[d])
+            tgt = self.owned([i for i in Sp if i not in dsets[d]])
+            E.conv_from_y([y[1] for y in ys], dsets[d], tgt, 1, col, 0)
+            for j in range(d + 1, nd):   # digits[j] -= digits[d]; digits[j] /= prod(full digit d)
+                oj = self.owned(dsets[j])
+                if oj:
+                    colj = [dp[j] for dp in dig_polys]
+                    E.pointwise("sub", colj, col, oj)
+                    E.scale_by_primes(colj, oj, self.digits[d], inv=True)
+        # evk inner product on the owned rows (src/Ctxt.cpp:191-230)
+        if oSp:
+            E.keyswitch_digits([dp[:nd] for dp in dig_polys], oSp, evk_a[:nd], evk_b[:nd], c0, c1)
+        return Sp
+
+    def mod_down(self, parts, cur, keep, ptxt_space=1):
+        """Ctxt::modDownToSet on row-sharded parts: drop cur\\keep (e.g. the special primes)."""
+        E = self.E
+        drop = [i for i in cur if i not in keep]
+        if not drop:
+            return
+        ys = [self._ybuf(("md", k)) for k in range(len(parts))]
+        E.conv_make_y(parts, drop, self.owned(drop), [y[1] for y in ys])
+        self._all_gather_rows([y[0] for y in ys], drop)
+        E.conv_from_y([y[1] for y in ys], drop, self.owned(keep), ptxt_space, parts, 1)

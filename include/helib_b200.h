@@ -122,6 +122,23 @@ int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_pol
 /* DoubleCRT::automorph (src/DoubleCRT.cpp:1160-1202): dst[j] = src[idx(rep(j)*k mod m)], dst != src */
 int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, uint64_t k);
 
+/* ---- prime-sharded base conversion (one rank per GPU, rows sharded by prime index).
+ * The exact conversion of hb_add_primes / hb_scale_down split where residues must cross shards:
+ *   hb_conv_make_y : for the owned rows of the source set D: y_j = iNTT(row_j) * (Q_D/q_j)^-1 mod q_j,
+ *                    written to ypolys rows `owned` in coefficient order (local work, no communication);
+ *   [caller: all-gather of the y rows over NCCL/NVLink so that every rank holds all rows of D]
+ *   hb_conv_from_y : exact CRT of the gathered y rows, reduction mod the target primes this rank owns,
+ *                    forward transform into dst rows tgt.  mode 0: dst = x (addPrimes, src/DoubleCRT.cpp:565-599);
+ *                    mode 1: dst = (dst - x) / Q_D with the BGV correction (scaleDownToSet, :1464-1516). */
+int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned, hb_poly* const* ypolys);
+int hb_conv_from_y(hb_poly* const* ypolys, int nitems, const int32_t* D, int nD, const int32_t* tgt, int nT,
+                   uint64_t ptxt_space, hb_poly* const* dst, int mode);
+/* Alias caller-owned device memory (uint64[nprimes][N]) as a polynomial; hb_poly_destroy does not free it. */
+int hb_poly_wrap(hb_ctx* ctx, void* device_ptr, hb_poly** out);
+/* Issue the context's work on a caller-provided CUDA stream (cudaStream_t), e.g. the stream the caller's
+ * NCCL collectives are ordered on. */
+int hb_ctx_set_stream(hb_ctx* ctx, void* cuda_stream);
+
 /* ---- fused ciphertext-level paths (host orchestration of Ctxt::reLinearize / keySwitchPart,
  * src/Ctxt.cpp:720-842, and Ctxt::multLowLvl + reLinearize + modDownToSet, src/Ctxt.cpp:393-562,
  * 1681-1774) with explicit prime sets (the noise-driven choice stays in the host Ctxt layer).

@@ -1,0 +1,44 @@
+"""Prime-sharded key switching: world_size-2/3 over gloo with the CPU kernel simulator,
+and over NCCL on real GPUs (-m gpu, needs >= 2 devices)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "mp", "sharded_worker.py")
+
+
+def run(backend, world, cfg, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, backend, cfg]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    for k in range(world):
+        assert f"RANK {k} OK" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("world,cfg,port", [(2, "64,257,1,120,2", 29611), (3, "4096,17,1,160,3", 29612)])
+def test_sharded_keyswitch_gloo_sim(sim_lib, world, cfg, port):
+    run("sim", world, cfg, port)
+
+
+def test_owner_map_balances_digits():
+    import pyoracle as po
+    from helib_b200.sharded import owner_map
+    ch = po.build_mod_chain(1 << 17, -1, 1, 1700, 2)
+    for world in (2, 4, 8):
+        own = owner_map(ch.ctxt, ch.special, world)
+        for cls in (ch.ctxt, ch.special) + tuple(ch.digits):
+            counts = [sum(1 for i in cls if own[i] == r) for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+
+
+@pytest.mark.gpu
+def test_sharded_keyswitch_nccl(cuda_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    run("cuda", 2, "8192,257,1,160,2", 29613)
