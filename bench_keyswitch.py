@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"])
     ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -48,7 +49,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ch = Chain(wl["m"], wl["p"], wl["r"], wl["bits"], wl["c"])
     E = Engine(wl["m"], ch.primes, None, ch.digits, ch.special, device=local)
-    E.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()            # the engine, torch index ops and NCCL all run ordered on this stream
+    torch.cuda.set_stream(side)
+    E.set_stream(side.cuda_stream)
     p = 1 if ch.p == -1 else ch.p ** ch.r
     N, npr, B = E.N, E.np, args.batch
     S = ch.ctxt
@@ -84,15 +87,35 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     E.reset_stats()
+    step()
+    launches_per_step = E.stats()["launches"]
+    barrier()
+    # The sharded step is ~100 small launches + 3 collectives: capture it once into a CUDA graph
+    # (engine kernels and torch's NCCL all-gathers are all ordered on torch's current stream).
+    graphed = False
+    run = step
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                step()
+            run = g.replay
+            graphed = True
+            for _ in range(2):
+                run()
+        except Exception as ex:   # fall back to eager launches
+            if rank == 0:
+                print(f"[bench_keyswitch] CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+            run = step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        run()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = E.stats()["launches"]
+    launches = launches_per_step * args.steps
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -115,7 +138,7 @@ def main():
                        "collectives_per_keyswitch": (d + 1) if (sharded and world > 1) else 0,
                        "all_gather_bytes_per_keyswitch": (l + 2 * K) * ROW if (sharded and world > 1) else 0, "alg_bytes_per_keyswitch": bks},
             "alg_roofline": {"achieved_GBps": v * bks / 1e9, "peak_GBps": peak * world, "frac": v * bks / 1e9 / (peak * world)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "cuda_graph": graphed,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -56,23 +56,28 @@ class ShardedKeySwitch:
         rows it owns).  One all_gather of a packed [n_items, max_owned, N] buffer."""
         if self.world == 1:
             return
-        per = [[i for i in D if self.owner[i] == r] for r in range(self.world)]
+        key = ("rows", tuple(D))
+        if key not in self._bufs:   # index tensors are built once (host->device copies are not graph-capturable)
+            per = [[i for i in D if self.owner[i] == r] for r in range(self.world)]
+            self._bufs[key] = (per, [torch.tensor(p, dtype=torch.int64, device=self.device) if p else None for p in per])
+        per, rowt = self._bufs[key]
         mx = max(len(p) for p in per)
         mine = per[self.rank]
-        send = torch.zeros((len(tensors), mx, self.E.N), dtype=torch.int64, device=self.device)
+        skey = ("send", len(tensors), mx)
+        if skey not in self._bufs:
+            self._bufs[skey] = (torch.zeros((len(tensors), mx, self.E.N), dtype=torch.int64, device=self.device),
+                                torch.empty(self.world * len(tensors) * mx * self.E.N, dtype=torch.int64, device=self.device))
+        send, flat = self._bufs[skey]
         if mine:
-            rows = torch.tensor(mine, device=self.device)
             for k, t in enumerate(tensors):
-                send[k, :len(mine)] = t.index_select(0, rows)
-        flat = torch.empty(self.world * send.numel(), dtype=torch.int64, device=self.device)
+                send[k, :len(mine)] = t.index_select(0, rowt[self.rank])
         dist.all_gather_into_tensor(flat, send.view(-1))
         recv = flat.view((self.world,) + tuple(send.shape))
         for r in range(self.world):
             if r == self.rank or not per[r]:
                 continue
-            rows = torch.tensor(per[r], device=self.device)
             for k, t in enumerate(tensors):
-                t.index_copy_(0, rows, recv[r, k, :len(per[r])])
+                t.index_copy_(0, rowt[r], recv[r, k, :len(per[r])])
 
     def _sync_engine_to_torch(self):
         # engine and torch share the stream on GPUs (Engine.set_stream); on the CPU simulator calls are synchronous
