@@ -199,6 +199,7 @@ struct HbConvJob {
   u64* dst[HB_MAXB];         // "cols"-phase output of the forward transform (rows tgt_prime)
   u64* stats;                // [0] += number of exact-fallback evaluations
   int src_is_y;              // 1: src rows already hold y_j = coeff * (Q/q_j)^-1 mod q_j in coefficient order
+  double* frac[HB_MAXB];     // optional: x/Q per coefficient (natural coefficient order) for the embedding norm
 };
 
 struct HbCrtJob {            // DoubleCRT::toPoly: exact balanced integer per coefficient
@@ -450,7 +451,7 @@ __device__ HB_NOINLINE int hb_crt_exact(const HbConvDev* cv, const u64* y, int y
 // v = round(sum_j y_j/q_j) via 0.64 fixed point; exact fallback when within the error margin of
 // the rounding boundary.  With has_p: also the BGV correction of DoubleCRT::scaleDownToSet
 // (src/DoubleCRT.cpp:1485-1511) folded into the returned multiple of Q.
-__device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int ystride, u64* stats) {
+__device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int ystride, u64* stats, double* frac = nullptr) {
   const int n = cv->n;
   u64 shi = 0, slo = 0;
   for (int j = 0; j < n; j++) {
@@ -488,9 +489,14 @@ __device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int 
         }
         minus = sign < 0;
       }
-      v += minus ? (i64)u - (i64)p : (i64)u;
+      const i64 v2 = minus ? (i64)u - (i64)p : (i64)u;
+      v += v2;
+      if (frac) *frac = (double)(i64)(F ^ 0x8000000000000000ULL) * 5.421010862427522e-20 - (double)v2;  // delta'/P
+      return v;
     }
   }
+  // x / Q in (-1/2, 1/2): the 0.64 fixed-point fraction re-centred (FP64 noise metadata, src/norms.cpp:443-485)
+  if (frac) *frac = (double)(i64)(F ^ 0x8000000000000000ULL) * 5.421010862427522e-20;
   return v;
 }
 
@@ -525,7 +531,12 @@ __global__ void __launch_bounds__(HB_THREADS) k_conv(const HbPrimeDev* __restric
     for (int e = tid; e < TILE; e += nthr) T[e] = hb_mul_shoup(T[e], t, ts, P.q);
   }
   __syncthreads();
-  for (int e = tid; e < TILE; e += nthr) Vb[e] = hb_conv_v(cv, Y + e, TILE, J.stats);
+  double* fr = J.frac[blockIdx.y];
+  for (int e = tid; e < TILE; e += nthr) {
+    double f;
+    Vb[e] = hb_conv_v(cv, Y + e, TILE, J.stats, fr ? &f : nullptr);
+    if (fr) fr[((size_t)(e >> logw) << lb) + c0 + (e & ((1 << logw) - 1))] = f;
+  }
   __syncthreads();
   for (int t = 0; t < nt; t++) {
     const int pi = cv->tgt_prime[t];
@@ -624,5 +635,53 @@ __global__ void __launch_bounds__(HB_THREADS) k_ks_inner(const HbPrimeDev* __res
     }
     J.out0[it][o] = hb_reduce128(h0, l0, P);
     J.out1[it][o] = hb_reduce128(h1, l1, P);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Canonical-embedding norm (noise metadata): max_j |f(zeta^(2j+1))|, zeta = e^(i*pi/N), in FP64.
+// Replaces embeddingLargestCoeff (src/norms.cpp:204-261,443-485) for power-of-two m.
+// frac[k] -> z[k] = frac[k] * e^(i*pi*k/N); length-N complex DIF FFT, radix-16 per pass; max |z|.
+#ifdef HB_SIM
+#include <cmath>
+struct double2 { double x, y; };
+static inline void sincospi(double a, double* s, double* c) { *s = sin(a * 3.14159265358979323846); *c = cos(a * 3.14159265358979323846); }
+#endif
+struct HbNormJob { int logN; int npoly; const double* frac; double2* z; unsigned long long* maxbits; };
+__global__ void __launch_bounds__(HB_THREADS) k_norm_twist(HbNormJob J) {
+  const size_t N = (size_t)1 << J.logN;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+    double s, c;
+    sincospi((double)k / (double)N, &s, &c);
+    const double f = J.frac[(size_t)blockIdx.y * N + k];
+    double2 o; o.x = f * c; o.y = f * s;
+    J.z[(size_t)blockIdx.y * N + k] = o;
+  }
+}
+// one radix-2 DIF stage at distance d = 2^logd (in place); the last stage also reduces max |z|^2
+__global__ void __launch_bounds__(HB_THREADS) k_norm_stage(HbNormJob J, int logd, int last) {
+  const size_t N = (size_t)1 << J.logN, half = N >> 1, d = (size_t)1 << logd;
+  double2* z = J.z + (size_t)blockIdx.y * N;
+  double m = 0.0;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = b & (d - 1), p = ((b >> logd) << (logd + 1)) + o;
+    const double2 u = z[p], v = z[p + d];
+    double s, c;
+    sincospi(-(double)o / (double)d, &s, &c);   // W_{2d}^o
+    double2 a, t, w;
+    a.x = u.x + v.x; a.y = u.y + v.y;
+    t.x = u.x - v.x; t.y = u.y - v.y;
+    w.x = t.x * c - t.y * s; w.y = t.x * s + t.y * c;
+    z[p] = a; z[p + d] = w;
+    if (last) { const double ma = a.x * a.x + a.y * a.y, mw = w.x * w.x + w.y * w.y; m = ma > m ? ma : m; m = mw > m ? mw : m; }
+  }
+  if (last) {
+#ifdef HB_SIM
+    unsigned long long bits; memcpy(&bits, &m, 8);
+    if (bits > J.maxbits[blockIdx.y]) J.maxbits[blockIdx.y] = bits;
+#else
+    atomicMax(J.maxbits + blockIdx.y, (unsigned long long)__double_as_longlong(m));  // non-negative doubles order like integers
+#endif
   }
 }

@@ -442,6 +442,7 @@ struct Hb1ConvJob {
   u64* dst[HB_MAXB];
   u64* stats;
   int src_is_y;   // 1: sources are y_j coefficient rows already (prime-sharded path)
+  double* frac[HB_MAXB];   // optional x/Q per coefficient for the embedding norm
 };
 
 __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
@@ -496,7 +497,10 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   // ---- v (multiple of Q to subtract, incl. the BGV correction) per coefficient
   for (int e = tid; e < 1024; e += blockDim.x) {
     const int cc = e >> 8, i1 = e & 255;
-    Vb[e] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats);
+    double* fr = J.frac[blockIdx.y];
+    double f;
+    Vb[e] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
+    if (fr) fr[((size_t)i1 << 8) + c0 + cc] = f;
   }
   __syncthreads();
   // ---- targets: x mod q_t in registers, forward cols phase, store

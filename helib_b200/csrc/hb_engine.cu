@@ -7,6 +7,7 @@
 #include "hb_device_v1.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -65,6 +66,7 @@ struct hb_ctx {
   cudaStream_t stream; cudaStream_t own_stream; bool stream_external = false;
   std::vector<int> digit_of; int ndigits; std::vector<int> special;
   u64* tmpA; u64* tmpB;
+  double* d_frac; void* d_z; unsigned long long* d_max;   // embedding-norm scratch (allocated on first use)
   u64* d_stats;
   std::map<std::string, ConvEntry> convs;
   std::vector<hb_poly*> pool;
@@ -148,7 +150,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->device = device; c->m = m; c->N = m / 2; c->nprimes = nprimes;
   c->logN = 0; while (((size_t)1 << c->logN) < c->N) c->logN++;
   c->log_blk = c->logN >= 11 ? 8 : 0;
-  c->tmpA = c->tmpB = nullptr; c->bytes = 0; c->launches = 0; c->ndigits = 0;
+  c->tmpA = c->tmpB = nullptr; c->d_frac = nullptr; c->d_z = nullptr; c->d_max = nullptr; c->bytes = 0; c->launches = 0; c->ndigits = 0;
   c->d_primes = nullptr; c->d_tw = nullptr; c->d_stats = nullptr; c->profiling = false;
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
@@ -221,6 +223,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
+  cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -616,8 +619,35 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
 
 // inverse-blk (polys -> tmpA), fused conversion (tmpA -> tmpB), for one chunk of items.
 // src_is_y: polys already hold the y_j coefficient rows (prime-sharded path): no inverse phase at all.
-static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p, int src_is_y = 0) {
+static int norm_scratch(hb_ctx* c) {
+  if (c->d_frac) return HB_OK;
+  HB_TRY(ctx_alloc(c, (void**)&c->d_frac, (size_t)HB_MAXB * c->N * sizeof(double)));
+  HB_TRY(ctx_alloc(c, (void**)&c->d_z, (size_t)HB_MAXB * c->N * 2 * sizeof(double)));
+  HB_TRY(ctx_alloc(c, (void**)&c->d_max, HB_MAXB * sizeof(unsigned long long)));
+  return HB_OK;
+}
+// max_j |f(zeta^(2j+1))| of the nit fraction polynomials in c->d_frac -> out[0..nit)   (synchronises)
+static int norm_chunk(hb_ctx* c, int nit, double* out) {
+  HbNormJob J; J.logN = c->logN; J.npoly = nit; J.frac = c->d_frac; J.z = (double2*)c->d_z; J.maxbits = c->d_max;
+  HB_CUDA(cudaMemsetAsync(c->d_max, 0, nit * sizeof(unsigned long long), c->stream));
+  unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
+  pre_launch(c);
+  HB_LAUNCH(k_norm_twist, dim3(gx, nit), dim3(HB_THREADS), 0, c->stream, J);
+  HB_TRY(post_launch(c, "k_norm_twist", (u64)nit * c->N * 24));
+  for (int logd = c->logN - 1; logd >= 0; logd--) {
+    pre_launch(c);
+    HB_LAUNCH(k_norm_stage, dim3(gx, nit), dim3(HB_THREADS), 0, c->stream, J, logd, logd == 0 ? 1 : 0);
+    HB_TRY(post_launch(c, "k_norm_stage", (u64)nit * c->N * 32));
+  }
+  unsigned long long bits[HB_MAXB];
+  HB_CUDA(cudaMemcpyAsync(bits, c->d_max, nit * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nit; i++) { double m2; memcpy(&m2, &bits[i], 8); out[i] = std::sqrt(m2); }
+  return HB_OK;
+}
+static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p, int src_is_y = 0, bool want_frac = false) {
   HB_TRY(ctx_scratch(c));
+  if (want_frac) HB_TRY(norm_scratch(c));
   ConvEntry* E; HB_TRY(get_conv(c, src, n, tgt, nt, p, &E));
   u64* tA[HB_MAXB]; u64* tB[HB_MAXB];
   tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
@@ -636,6 +666,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
     if (ng > 0) {
       Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
       J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats; J1.src_is_y = src_is_y;
+      if (want_frac) for (int i = 0; i < nit; i++) J1.frac[i] = c->d_frac + (size_t)i * c->N;
       for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
       pre_launch(c);
       HB_LAUNCH(k1_conv, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
@@ -649,6 +680,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   if (smem > c->max_smem) return hb_fail(HB_ERR_UNSUPPORTED, "base conversion tile needs %zu bytes of shared memory", smem);
   HbConvJob J; memset(&J, 0, sizeof(J));
   J.cv = E->d; J.logN = c->logN; J.log_blk = c->log_blk; J.logw = lw; J.nitems = nit; J.stats = c->d_stats; J.src_is_y = src_is_y;
+  if (want_frac) for (int i = 0; i < nit; i++) J.frac[i] = c->d_frac + (size_t)i * c->N;
   for (int i = 0; i < nit; i++) { J.src[i] = tA[i]; J.dst[i] = tB[i]; }
   dim3 grid(1u << (c->log_blk - lw), nit);
   pre_launch(c);
@@ -736,20 +768,35 @@ extern "C" int hb_add_primes_and_scale(hb_poly* const* polys, int nitems, const 
   if (ncur > 0) HB_TRY(hb_scale_by_primes(polys, nitems, cur, ncur, add, nadd, 0));
   return hb_zero_rows(polys, nitems, add, nadd);
 }
-extern "C" int hb_add_primes(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd) {
+// log_norms (optional, [nitems]): ln of the canonical-embedding norm of the balanced polynomial (toPoly of rows cur)
+static int add_primes_impl(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd, double* log_norms) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_add_primes"));
   HB_TRY(check_idx(c, cur, ncur, "hb_add_primes", true)); HB_TRY(check_idx(c, add, nadd, "hb_add_primes", true));
   if (nadd == 0) return HB_OK;  // src/DoubleCRT.cpp:569-572
   HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimes"));
   if (ncur == 0) return hb_zero_rows(polys, nitems, add, nadd);  // src/DoubleCRT.cpp:577-583
   HB_TRY(ctx_scratch(c));
+  double logQ = 0; for (int j = 0; j < ncur; j++) logQ += std::log((double)c->q[cur[j]]);
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
-    HB_TRY(conv_chunk(c, P, nit, cur, ncur, add, nadd, 1));
-    return launch_blk(c, +1, (const u64* const*)tB, P, nit, add, nadd, 0, nullptr);
+    HB_TRY(conv_chunk(c, P, nit, cur, ncur, add, nadd, 1, 0, log_norms != nullptr));
+    HB_TRY(launch_blk(c, +1, (const u64* const*)tB, P, nit, add, nadd, 0, nullptr));
+    if (log_norms) {
+      double m[HB_MAXB]; HB_TRY(norm_chunk(c, nit, m));
+      for (int i = 0; i < nit; i++) log_norms[i0 + i] = (m[i] > 0 ? std::log(m[i]) : -INFINITY) + logQ;
+    }
+    return HB_OK;
   });
 }
-extern "C" int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space) {
+extern "C" int hb_add_primes(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd) {
+  return add_primes_impl(polys, nitems, cur, ncur, add, nadd, nullptr);
+}
+extern "C" int hb_add_primes_norm(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd, double* log_norms) {
+  if (!log_norms) return hb_fail(HB_ERR_BAD_ARG, "hb_add_primes_norm: null output");
+  return add_primes_impl(polys, nitems, cur, ncur, add, nadd, log_norms);
+}
+// norms (optional, [nitems]): canonical-embedding norm of delta/P (the "fdelta" of Ctxt::modDownToSet, src/Ctxt.cpp:476-505)
+static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space, double* norms) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_scale_down"));
   HB_TRY(check_idx(c, cur, ncur, "hb_scale_down")); HB_TRY(check_idx(c, keep, nkeep, "hb_scale_down(keep)", true));
   if (ptxt_space < 1) return hb_fail(HB_ERR_BAD_ARG, "ptxtSpace must be at least 1");  // src/DoubleCRT.cpp:1472
@@ -764,9 +811,18 @@ extern "C" int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* c
   HB_TRY(ctx_scratch(c));
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
-    HB_TRY(conv_chunk(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space));
-    return launch_blk(c, +1, (const u64* const*)tB, P, nit, kept.data(), (int)kept.size(), 1, sc.data());
+    HB_TRY(conv_chunk(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space, 0, norms != nullptr));
+    HB_TRY(launch_blk(c, +1, (const u64* const*)tB, P, nit, kept.data(), (int)kept.size(), 1, sc.data()));
+    if (norms) HB_TRY(norm_chunk(c, nit, norms + i0));
+    return HB_OK;
   });
+}
+extern "C" int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space) {
+  return scale_down_impl(polys, nitems, cur, ncur, keep, nkeep, ptxt_space, nullptr);
+}
+extern "C" int hb_scale_down_norm(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space, double* norms) {
+  if (!norms) return hb_fail(HB_ERR_BAD_ARG, "hb_scale_down_norm: null output");
+  return scale_down_impl(polys, nitems, cur, ncur, keep, nkeep, ptxt_space, norms);
 }
 extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, uint64_t* out, int Lout) {
   if (!p || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly: null");
@@ -851,7 +907,16 @@ extern "C" int hb_ctx_set_stream(hb_ctx* c, void* cuda_stream) {
 
 // ------------------------------------------------------------------------------------------
 // digits and key switching
+static int break_into_digits_impl(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out, double* log_norms);
 extern "C" int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out) {
+  return break_into_digits_impl(src, nitems, cur, ncur, digits, maxdig, ndig_out, nullptr);
+}
+// log_norms[item*maxdig + i] = ln ||E_i||_canon; the reference returns their sum (src/DoubleCRT.cpp:542-545)
+extern "C" int hb_break_into_digits_norm(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out, double* log_norms) {
+  if (!log_norms) return hb_fail(HB_ERR_BAD_ARG, "hb_break_into_digits_norm: null output");
+  return break_into_digits_impl(src, nitems, cur, ncur, digits, maxdig, ndig_out, log_norms);
+}
+static int break_into_digits_impl(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out, double* log_norms) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(src, nitems, &c, "hb_break_into_digits")); HB_TRY(check_idx(c, cur, ncur, "hb_break_into_digits"));
   if (!digits || !ndig_out) return hb_fail(HB_ERR_BAD_ARG, "hb_break_into_digits: null");
   // index set must be a subset of ctxt primes (src/DoubleCRT.cpp:497-498)
@@ -878,7 +943,9 @@ extern "C" int hb_break_into_digits(hb_poly* const* src, int nitems, const int32
   }
   for (int i = 0; i < nd; i++) {
     for (int it = 0; it < nitems; it++) col[it] = digits[it * maxdig + i];
-    HB_TRY(hb_add_primes(col.data(), nitems, dset[i].data(), (int)dset[i].size(), notin[i].data(), (int)notin[i].size()));
+    std::vector<double> ln(nitems);
+    HB_TRY(add_primes_impl(col.data(), nitems, dset[i].data(), (int)dset[i].size(), notin[i].data(), (int)notin[i].size(), log_norms ? ln.data() : nullptr));
+    if (log_norms) for (int it = 0; it < nitems; it++) log_norms[it * maxdig + i] = ln[it];
     for (int j = i + 1; j < nd; j++) {  // digits[j] -= digits[i]; digits[j] /= pi  (src/DoubleCRT.cpp:551-556)
       for (int it = 0; it < nitems; it++) col2[it] = digits[it * maxdig + j];
       std::vector<u64> sc; HB_TRY(scalars_by_primes(c, dset[j].data(), (int)dset[j].size(), full[i].data(), (int)full[i].size(), 1, sc));

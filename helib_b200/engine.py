@@ -343,3 +343,36 @@ def _engine_extra(cls):
 
 
 _engine_extra(Engine)
+
+
+def _engine_norms(cls):
+    def add_primes_norm(self, polys, cur, add):
+        a, pc, nc = _idx(cur)
+        b, pa, na = _idx(add)
+        out = np.zeros(len(polys), dtype=np.float64)
+        self._ck(self.lib.hb_add_primes_norm(_arr(polys), len(polys), pc, nc, pa, na, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def scale_down_norm(self, polys, cur, keep, ptxt_space=1):
+        a, pc, nc = _idx(cur)
+        b, pk, nk = _idx(keep)
+        out = np.zeros(len(polys), dtype=np.float64)
+        self._ck(self.lib.hb_scale_down_norm(_arr(polys), len(polys), pc, nc, pk, nk, C.c_uint64(int(ptxt_space)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def break_into_digits_norm(self, src, cur, digits=None):
+        a, pc, nc = _idx(cur)
+        maxdig = len(self.digits)
+        if digits is None:
+            digits = [[Poly(self) for _ in range(maxdig)] for _ in src]
+        flat = [d for item in digits for d in item]
+        nd = C.c_int()
+        out = np.zeros(len(src) * maxdig, dtype=np.float64)
+        self._ck(self.lib.hb_break_into_digits_norm(_arr(src), len(src), pc, nc, _arr(flat), maxdig, C.byref(nd), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return [item[:nd.value] for item in digits], out.reshape(len(src), maxdig)[:, :nd.value]
+
+    cls.add_primes_norm, cls.scale_down_norm, cls.break_into_digits_norm = add_primes_norm, scale_down_norm, break_into_digits_norm
+    return cls
+
+
+_engine_norms(Engine)

@@ -122,6 +122,16 @@ int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_pol
 /* DoubleCRT::automorph (src/DoubleCRT.cpp:1160-1202): dst[j] = src[idx(rep(j)*k mod m)], dst != src */
 int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, uint64_t k);
 
+/* ---- noise metadata: canonical-embedding norms (embeddingLargestCoeff, src/norms.cpp:204-261,443-485),
+ * computed in FP64 on the device from the coefficient data the conversion kernels already hold.
+ * Same operations as above plus the norm outputs; these variants synchronise (they return host values).
+ *  hb_add_primes_norm        : log_norms[item] = ln max_j |f(zeta^j)| of the balanced polynomial being extended
+ *  hb_break_into_digits_norm : log_norms[item*maxdig+i] = ln ||E_i||  (breakIntoDigits returns their sum, src/DoubleCRT.cpp:542-545)
+ *  hb_scale_down_norm        : norms[item] = ||delta/P||  (the fdelta norms of Ctxt::modDownToSet, src/Ctxt.cpp:476-505) */
+int hb_add_primes_norm(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* add, int nadd, double* log_norms);
+int hb_break_into_digits_norm(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out, double* log_norms);
+int hb_scale_down_norm(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space, double* norms);
+
 /* ---- prime-sharded base conversion (one rank per GPU, rows sharded by prime index).
  * The exact conversion of hb_add_primes / hb_scale_down split where residues must cross shards:
  *   hb_conv_make_y : for the owned rows of the source set D: y_j = iNTT(row_j) * (Q_D/q_j)^-1 mod q_j,

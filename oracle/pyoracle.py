@@ -560,3 +560,23 @@ def key_switch_digits(digits, evk_a, evk_b):
         out1 = ta if out1 is None else out1.add(ta)
         out0 = tb if out0 is None else out0.add(tb)
     return out0, out1
+
+
+# ---------------------------------------------------------------------------
+# noise metadata (float64): canonical-embedding L-infinity norm
+# ---------------------------------------------------------------------------
+
+
+def embedding_largest_coeff(coeffs, m: int):
+    """embeddingLargestCoeff(ZZX, palg) for power-of-two m (src/norms.cpp:443-485 scale to <= 400 bits,
+    :204-261 max over j in Z_m^* of |f(zeta^j)|, zeta = e^(2 pi i/m)).  Returns (mantissa, log2 factor):
+    norm = mantissa * 2^shift, as the reference returns an xdouble."""
+    import numpy as np
+    n = m // 2
+    size = max((abs(int(c)).bit_length() for c in coeffs), default=0)
+    shift = max(0, size - 400)
+    ff = np.array([float(int(c) >> shift) if c >= 0 else -float((-int(c)) >> shift) for c in coeffs] + [0.0] * (n - len(coeffs)))
+    k = np.arange(n)
+    tw = np.exp(1j * np.pi * k / n)                 # zeta^k, zeta = e^(i pi / n)
+    vals = np.fft.ifft(ff * tw) * n                 # sum_k f_k zeta^k e^(+2 pi i k j / n) = f(zeta^(2j+1))
+    return float(np.max(np.abs(vals))), shift

@@ -199,3 +199,40 @@ def test_bgv_multiply_decrypts_to_product(lib, cfg):
     O.scale_down(r0, Sp, S, p); O.scale_down(r1, Sp, S, p)
     O.pointwise("mul", r1, S_dcrt, S); O.pointwise("add", r0, r1, S)
     assert orc.limbs_to_ints(O.to_poly(r0, S)) == dec
+
+
+@pytest.mark.parametrize("cfg", [(64, 257, 1, 120, 2), (4096, 17, 1, 160, 3), (1 << 17, 257, 1, 230, 2)])
+def test_embedding_norms_match_restated_reference(lib, cfg):
+    """Noise metadata: FP64 canonical-embedding norms returned next to the integer
+    results.  Floating point: relative tolerance 1e-9 against the numpy restatement of
+    embeddingLargestCoeff (src/norms.cpp:204-261,443-485); the integer rows stay bit-exact."""
+    import math
+    ch, psis, O, E = make(lib, *cfg)
+    p = ch.p ** ch.r
+    rng = np.random.default_rng(21)
+    S = ch.ctxt
+    Sp = sorted(S + ch.special)
+    x = O.random(rng, S)
+    P = E.poly(x, S)
+    digs, lognorms = E.break_into_digits_norm([P], S)
+    ref_d, polys = O.break_into_digits(x, S, want_polys=True)
+    for i, D in enumerate(digs[0]):
+        assert rows_equal(D.download(Sp), ref_d[i], Sp)
+        mant, shift = po.embedding_largest_coeff(orc.limbs_to_ints(polys[i]), ch.m)
+        ref_log = math.log(mant) + shift * math.log(2.0)
+        assert abs(lognorms[0, i] - ref_log) <= 1e-9 * abs(ref_log) + 1e-9
+    y = O.random(rng, Sp)
+    Y = E.poly(y, Sp)
+    norms = E.scale_down_norm([Y], Sp, S, p)
+    ref = y.copy()
+    delta = orc.limbs_to_ints(O.scale_down(ref, Sp, S, p, want_delta=True))
+    assert rows_equal(Y.download(S), ref, S)
+    Pd = ch.product(ch.special)
+    from fractions import Fraction
+    fdelta = [float(Fraction(d, Pd)) for d in delta]       # Ctxt::modDownToSet: fdelta = delta / diffProd (src/Ctxt.cpp:482-485)
+    n = ch.phim
+    k = np.arange(n)
+    vals = np.fft.ifft(np.array(fdelta) * np.exp(1j * np.pi * k / n)) * n
+    want = float(np.max(np.abs(vals)))
+    assert abs(norms[0] - want) <= 1e-9 * want
+    assert want <= p / 2.0 * n + 1
