@@ -140,8 +140,13 @@ def main():
             "alg_roofline": {"achieved_GBps": v * bks / 1e9, "peak_GBps": peak * world, "frac": v * bks / 1e9 / (peak * world)},
             "gpu_launches": launches, "cuda_graph": graphed,
         }))
+    # Leave without tearing NCCL down: destroy_process_group() after a captured graph that contains
+    # collectives can block for minutes; the results are already printed.
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -216,6 +216,7 @@ enum {
 
 struct HbPwJob {
   int op, logN;
+  u64 N;                    // row length = row stride (phi(m); not a power of two for general m)
   HbRows rows;
   u64 scal[HB_MAXROWS], scal_s[HB_MAXROWS];
   int nitems;
@@ -231,6 +232,7 @@ struct HbPwJob {
 
 struct HbKsJob {            // Ctxt::keySwitchDigits inner product
   int logN, ndig;
+  u64 N;
   HbRows rows;
   int nitems;
   const u64* dig[HB_MAXB][HB_MAXDIG];
@@ -238,6 +240,8 @@ struct HbKsJob {            // Ctxt::keySwitchDigits inner product
   const u64* evk_b[HB_MAXDIG];
   u64* out0[HB_MAXB];
   u64* out1[HB_MAXB];
+  int mode;                 // 0: out += sum;  1: out = scal[row]*out + sum (scal 0 => out = sum, old value not read):
+  u64 scal[HB_MAXROWS];     //    folds the addPrimesAndScale of the (1, s) parts (src/Ctxt.cpp:764-768) into the inner product
 };
 
 // ------------------------------------------------------------------------------------------
@@ -584,8 +588,8 @@ __global__ void __launch_bounds__(HB_THREADS) k_pointwise(const HbPrimeDev* __re
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
   const u64 q = P.q;
-  const size_t N = (size_t)1 << J.logN;
-  const size_t off = (size_t)pi << J.logN;
+  const size_t N = (size_t)J.N;
+  const size_t off = (size_t)pi * N;
   const int it = blockIdx.z;
   const u64 sc = J.scal[blockIdx.y], sc_s = J.scal_s[blockIdx.y];
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
@@ -622,12 +626,17 @@ __global__ void __launch_bounds__(HB_THREADS) k_pointwise(const HbPrimeDev* __re
 __global__ void __launch_bounds__(HB_THREADS) k_ks_inner(const HbPrimeDev* __restrict__ primes, HbKsJob J) {
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const size_t N = (size_t)1 << J.logN;
-  const size_t off = (size_t)pi << J.logN;
+  const size_t N = (size_t)J.N;
+  const size_t off = (size_t)pi * N;
   const int it = blockIdx.z;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
     const size_t o = off + k;
-    u64 h0 = 0, l0 = J.out0[it][o], h1 = 0, l1 = J.out1[it][o];
+    u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+    if (J.mode == 0) { l0 = J.out0[it][o]; l1 = J.out1[it][o]; }
+    else {
+      const u64 sc = J.scal[blockIdx.y];
+      if (sc) { hb_mac128(h0, l0, J.out0[it][o], sc); hb_mac128(h1, l1, J.out1[it][o], sc); }
+    }
     for (int i = 0; i < J.ndig; i++) {
       u64 d = J.dig[it][i][o];
       hb_mac128(h0, l0, d, J.evk_b[i][o]);

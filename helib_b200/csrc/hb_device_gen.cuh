@@ -1,0 +1,136 @@
+// hb_device_gen.cuh -- rows for general (non power-of-two) m: Bluestein transforms and the unfused
+// exact base conversion on plain coefficient rows.
+//
+// Reference: BluesteinInit / BluesteinFFT (src/bluestein.cpp:77-201) and the general-m branches of
+// Cmodulus::FFT_aux / iFFT (src/CModulus.cpp:148-180,431-443,555-577).
+//   forward : X_k = root^(k^2) * sum_i (x_i root^(i^2)) * root^(-(k-i)^2), k in Z_m^*  (row[j] = X_rep(j))
+//   inverse : scatter the row into Z_m^* positions, the same DFT with root^-1, reduce mod Phi_m(X), times m^-1.
+// The two chirp convolutions, and the two products of the division by Phi_m, are cyclic convolutions of
+// length L = 2^ceil(log2(2m-1)) done with the power-of-two transform kernels on *cyclic* twiddle tables
+// (same butterfly network, tables omega^brev instead of psi^brev).  The remainder mod Phi_m uses
+// rev(Phi)^-1 = rev((X^m-1)/Phi_m) mod X^(m-phi(m)), so no per-prime power-series inversion is needed.
+#pragma once
+#include "hb_device.cuh"
+
+struct HbGenPrime {
+  const ulonglong2* pw;    // [m]  root^(i^2)      (+Shoup)
+  const ulonglong2* ipw;   // [m]  root^(-i^2)     (+Shoup)
+  const u64* RbHat;        // [L]  cyclic transform of b[j] = root^(-(j-(m-1))^2), j = 0..2m-2
+  const u64* iRbHat;       // [L]  same for root^-1
+  const u64* invHat;       // [L]  cyclic transform of rev((X^m-1)/Phi_m) mod X^d
+  const u64* phiHat;       // [L]  cyclic transform of Phi_m
+  u64 minv, minv_s;        // m^-1 mod q
+};
+
+struct HbGenJob {
+  u64 m, phim, L, d;       // d = m - phi(m)
+  const int* rep;          // [phim] j-th unit of Z_m^*
+  const int* irep;         // [m]    index of unit i, or -1
+  HbRows rows;
+  int nitems;
+  const u64* src[HB_MAXB];  // polynomial rows, stride phim
+  u64* dst[HB_MAXB];
+  u64* w0[HB_MAXB];         // work buffers, row stride L
+  u64* w1[HB_MAXB];
+  int which;                // selects the fixed vector in k_gen_mulvec: 0 RbHat, 1 iRbHat, 2 invHat, 3 phiHat
+};
+
+enum { HB_GEN_PRE_FWD = 0, HB_GEN_POST_FWD, HB_GEN_PRE_INV, HB_GEN_POST_INV, HB_GEN_QREV, HB_GEN_FIN, HB_GEN_MULVEC };
+
+// grid = (blocks over max(L, m), nrows, nitems)
+__global__ void __launch_bounds__(HB_THREADS) k_gen(const HbPrimeDev* __restrict__ primes, const HbGenPrime* __restrict__ gp, HbGenJob J, int op) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const HbGenPrime G = gp[pi];
+  const u64 q = P.q;
+  const int it = blockIdx.z;
+  const size_t prow = (size_t)pi * J.phim, wrow = (size_t)pi * J.L;
+  const u64* src = J.src[it] ? J.src[it] + prow : nullptr;
+  u64* dst = J.dst[it] ? J.dst[it] + prow : nullptr;
+  u64* w0 = J.w0[it] + wrow;
+  u64* w1 = J.w1[it] ? J.w1[it] + wrow : nullptr;
+  const size_t m = J.m, phim = J.phim, L = J.L, d = J.d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
+    switch (op) {
+      case HB_GEN_PRE_FWD:   // y_i = x_i * root^(i^2), zero padded (src/bluestein.cpp:151-155)
+        w0[i] = i < phim ? hb_mul_shoup(src[i], G.pw[i].x, G.pw[i].y, q) : 0;
+        break;
+      case HB_GEN_POST_FWD:  // row[j] = z[rep(j) + m-1] * root^(rep(j)^2) (src/bluestein.cpp:190-196, src/CModulus.cpp:435-443)
+        if (i < phim) { const size_t k = (size_t)J.rep[i]; dst[i] = hb_mul_shoup(w0[k + m - 1], G.pw[k].x, G.pw[k].y, q); }
+        break;
+      case HB_GEN_PRE_INV: { // scatter into Z_m^* positions (src/CModulus.cpp:557-562) and chirp with root^-1
+        u64 v = 0;
+        if (i < m) { const int j = J.irep[i]; if (j >= 0) v = hb_mul_shoup(src[j], G.ipw[i].x, G.ipw[i].y, q); }
+        w0[i] = v;
+      } break;
+      case HB_GEN_POST_INV:  // A_k = z[k+m-1] * root^(-k^2); keep A_0..A_(phim-1) in dst, w1 = first d coefficients of rev(A)
+        if (i < phim) dst[i] = hb_mul_shoup(w0[i + m - 1], G.ipw[i].x, G.ipw[i].y, q);
+        if (i < d) { const size_t k = m - 1 - i; w1[i] = hb_mul_shoup(w0[k + m - 1], G.ipw[k].x, G.ipw[k].y, q); }
+        else w1[i] = 0;
+        break;
+      case HB_GEN_QREV:      // quotient by Phi_m: q_k = (rev(A) * rev(Phi)^-1 mod X^d)[d-1-k]
+        w0[i] = i < d ? w1[d - 1 - i] : 0;
+        break;
+      case HB_GEN_FIN:       // coefficients = (A - q*Phi) * m^-1 (src/CModulus.cpp:566-577)
+        if (i < phim) dst[i] = hb_mul_shoup(hb_submod(dst[i], w0[i], q), G.minv, G.minv_s, q);
+        break;
+      case HB_GEN_MULVEC: {
+        const u64* v = J.which == 0 ? G.RbHat : (J.which == 1 ? G.iRbHat : (J.which == 2 ? G.invHat : G.phiHat));
+        u64* w = J.which == 2 ? w1 : w0;   // the quotient product runs in w1
+        w[i] = hb_mulmod(w[i], v[i], P);
+      } break;
+    }
+  }
+}
+
+// Unfused exact base conversion on coefficient rows (general m): per coefficient y_j = r_j*(Q/q_j)^-1,
+// v = round(sum y_j/q_j) (+ BGV correction), then x mod q_t for every target.  Same arithmetic as the
+// fused kernels (hb_conv_v); src/dst are coefficient rows of stride N.
+struct HbPlainConvJob {
+  const HbConvDev* cv;
+  const u64* t; const u64* t_s;   // (Q/q_j)^-1 mod q_j (+Shoup), without N^-1
+  u64 N;
+  int nitems;
+  const u64* src[HB_MAXB];
+  u64* dst[HB_MAXB];
+  double* frac[HB_MAXB];
+  u64* stats;
+};
+__global__ void __launch_bounds__(HB_THREADS) k_conv_plain(const HbPrimeDev* __restrict__ primes, HbPlainConvJob J) {
+  const HbConvDev* cv = J.cv;
+  const int n = cv->n, nt = cv->nt;
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= J.N) return;
+  const u64* src = J.src[blockIdx.y];
+  u64* dst = J.dst[blockIdx.y];
+  u64 y[HB_MAXROWS];
+  for (int j = 0; j < n; j++) {
+    const int pi = cv->src_prime[j];
+    y[j] = hb_mul_shoup(src[(size_t)pi * J.N + k], J.t[j], J.t_s[j], primes[pi].q);
+  }
+  double f;
+  double* fr = J.frac[blockIdx.y];
+  const i64 v = hb_conv_v(cv, y, 1, J.stats, fr ? &f : nullptr);
+  if (fr) fr[k] = f;
+  for (int t = 0; t < nt; t++) {
+    const int pi = cv->tgt_prime[t];
+    const HbPrimeDev P = primes[pi];
+    const u64* ct = cv->c + (size_t)t * n;
+    u64 hi = 0, lo = 0;
+    for (int j = 0; j < n; j++) hb_mac128(hi, lo, y[j], ct[j]);
+    if (v >= 0) hb_mac128(hi, lo, (u64)v, cv->negQ[t]);
+    else hb_mac128(hi, lo, (u64)(-v), cv->Qmod[t]);
+    dst[(size_t)pi * J.N + k] = hb_reduce128(hi, lo, P);
+  }
+}
+
+// automorphism for general m: new[j] = old[idx(rep(j)*k mod m)] (src/DoubleCRT.cpp:1160-1202)
+struct HbGenAutoJob { u64 m, phim, k; const int* rep; const int* irep; HbRows rows; int nitems; const u64* src[HB_MAXB]; u64* dst[HB_MAXB]; };
+__global__ void __launch_bounds__(HB_THREADS) k_gen_automorph(HbGenAutoJob J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const size_t off = (size_t)pi * J.phim;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < J.phim; j += (size_t)gridDim.x * blockDim.x) {
+    const u64 r = ((u64)J.rep[j] * J.k) % J.m;   // m <= 2^20, so the product fits
+    J.dst[blockIdx.z][off + j] = J.src[blockIdx.z][off + J.irep[r]];
+  }
+}

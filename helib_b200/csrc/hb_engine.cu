@@ -5,6 +5,7 @@
 // in hb_device.cuh.  There is no CPU compute path: without a CUDA device hb_ctx_create fails.
 #include "hb_device.cuh"
 #include "hb_device_v1.cuh"
+#include "hb_device_gen.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -75,6 +76,17 @@ struct hb_ctx {
   size_t max_smem;
   bool force_v0;     // HB_FORCE_V0=1: generic radix-2 kernels only (A/B testing)
   int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
+  // general (non power-of-two) m: Bluestein state
+  struct Gen {
+    bool on = false;
+    u64 m = 0, phim = 0, L = 0, d = 0; int logL = 0, log_blk_L = 0;
+    int* d_rep = nullptr; int* d_irep = nullptr;
+    HbGenPrime* d_gp = nullptr;
+    HbPrimeDev* d_primes_cyc = nullptr;
+    void* tab = nullptr;
+    u64 *w0 = nullptr, *w1 = nullptr, *wt = nullptr;   // [HB_MAXB][nprimes][L]
+    u64 *cA = nullptr, *cB = nullptr;                   // [HB_MAXB][nprimes][phim]
+  } gen;
   // optional per-launch profiling (bench.py): CUDA events around every kernel launch
   bool profiling;
   struct ProfRec { const char* name; cudaEvent_t a, b; u64 bytes; };
@@ -139,15 +151,17 @@ static u64 find_psi(u64 q, u64 two_n) {
   return h_powmod(g, (q - 1) / two_n, q);
 }
 
+static int gen_init(hb_ctx* c, const uint64_t* psi);
 extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi) {
   if (!out || !q || nprimes <= 0) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: null argument or nprimes <= 0");
-  if (m < 4 || (m & (m - 1))) return hb_fail(HB_ERR_UNSUPPORTED, "hb_ctx_create: m=%llu is not a power of two >= 4 (Bluestein rows not built yet)", (unsigned long long)m);
+  if (m < 3 || m > (1ULL << 20)) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: m=%llu out of range [3, 2^20]", (unsigned long long)m);
+  const bool pow2 = (m & (m - 1)) == 0;
   int ndev = hb_device_count();
   if (ndev <= 0) return hb_fail(HB_ERR_NO_DEVICE, "hb_ctx_create: no CUDA device (the engine has no CPU path)");
   if (device < 0 || device >= ndev) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: device %d out of range [0,%d)", device, ndev);
   HB_CUDA(cudaSetDevice(device));
   hb_ctx* c = new hb_ctx();
-  c->device = device; c->m = m; c->N = m / 2; c->nprimes = nprimes;
+  c->device = device; c->m = m; c->N = pow2 ? m / 2 : 0; c->nprimes = nprimes;
   c->logN = 0; while (((size_t)1 << c->logN) < c->N) c->logN++;
   c->log_blk = c->logN >= 11 ? 8 : 0;
   c->tmpA = c->tmpB = nullptr; c->d_frac = nullptr; c->d_z = nullptr; c->d_max = nullptr; c->bytes = 0; c->launches = 0; c->ndigits = 0;
@@ -167,8 +181,11 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     u64 qi = q[i];
     // HElib primes are < 2^HELIB_SP_NBITS = 2^60 (src/macro.h:16-23); the lazy butterflies need 6q < 2^63
     if (qi < 3 || qi >= (1ULL << 60) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^60 with m | q-1", i, (unsigned long long)qi); }
-    u64 ps = psi ? psi[i] : find_psi(qi, m);
-    if (h_powmod(ps, N, qi) != qi - 1) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
+    u64 ps = 0;
+    if (pow2) {
+      ps = psi ? psi[i] : find_psi(qi, m);
+      if (h_powmod(ps, N, qi) != qi - 1) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
+    }
     c->q.push_back(qi); c->psi.push_back(ps);
   }
   HB_CUDA(cudaStreamCreate(&c->stream));
@@ -176,6 +193,30 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
 #ifndef HB_SIM
   HB_CUDA(cudaEventCreate(&c->ev0)); HB_CUDA(cudaEventCreate(&c->ev1));
 #endif
+  if (!pow2) {   // general m: Bluestein rows (src/bluestein.cpp); no negacyclic tables
+    c->h_primes.resize(nprimes);
+    for (int i = 0; i < nprimes; i++) {
+      u64 qi = c->q[i];
+      HbPrimeDev& P = c->h_primes[i];
+      memset(&P, 0, sizeof(P));
+      P.q = qi; P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi); P.one_s = (u64)(((u128)1 << 64) / qi);
+      P.nq = 0 - qi; P.q3 = 3 * qi;
+    }
+    HB_TRY(ctx_alloc(c, (void**)&c->d_primes, sizeof(HbPrimeDev) * nprimes));
+    HB_CUDA(cudaMemcpy(c->d_primes, c->h_primes.data(), sizeof(HbPrimeDev) * nprimes, cudaMemcpyHostToDevice));
+    HB_TRY(ctx_alloc(c, (void**)&c->d_stats, 4 * sizeof(u64)));
+    HB_CUDA(cudaMemset(c->d_stats, 0, 4 * sizeof(u64)));
+#ifndef HB_SIM
+    HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+#endif
+    int r = gen_init(c, psi);
+    if (r != HB_OK) return r;
+    *out = c;
+    return HB_OK;
+  }
   // twiddle tables: fw[k] = psi^brev(k), iw[k] = psi^-brev(k)
   std::vector<ulonglong2> tw((size_t)nprimes * 2 * N);
   std::vector<u64> pw(N);
@@ -224,6 +265,8 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
   cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max);
+  cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
+  cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -499,7 +542,7 @@ static int launch_pw(hb_ctx* c, const PwArgs& A, int nitems, const int32_t* idx,
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
     int nr = std::min(HB_MAXROWS, n - r0);
     HbPwJob J; memset(&J, 0, sizeof(J));
-    J.op = A.op; J.logN = c->logN; J.k = A.k; J.m = A.m;
+    J.op = A.op; J.logN = c->logN; J.N = c->N; J.k = A.k; J.m = A.m;
     fill_rows(J.rows, idx + r0, nr);
     for (int i = 0; i < nr; i++) if (A.scal) { J.scal[i] = A.scal[r0 + i]; J.scal_s[i] = h_shoup(A.scal[r0 + i], c->q[idx[r0 + i]]); }
     J.nitems = nitems;
@@ -654,14 +697,20 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   if (src_is_y) { for (int i = 0; i < nit; i++) tA[i] = polys[i]; }
   else HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
   if (v1_cols_ok(c)) {
-    // number of 64-thread row groups: best balance of the n source rows and nt target rows
+    // number of 64-thread row groups: balance of the n source rows / nt target rows, resident warps,
+    // and (for small source sets) co-residency of two CTAs so that one CTA's thin source phase
+    // overlaps the other's target phase
     int ng = 0; double best = -1; size_t smem1 = 0;
     for (int g = 10; g >= 4; g--) {
       size_t sm = ((size_t)(n + g) * HB1_TS + 1024) * sizeof(u64);
       if (sm > 224 * 1024) continue;
+      int by_smem = (int)((227 * 1024) / (sm + 1024)), by_regs = 65536 / (96 * 64 * g);
+      int ctas = std::max(1, std::min(std::min(by_smem, by_regs), 2));
       double work = n + 1.4 * nt, slots = (double)((n + g - 1) / g) + 1.4 * ((nt + g - 1) / g);
-      double util = work / slots;   // rows finished per row-time: rewards both balance and more groups
-      if (util > best) { best = util; ng = g; smem1 = sm; }
+      double balance = work / (slots * g);
+      double warps = std::min(20.0, 2.0 * g * ctas);
+      double score = balance * (0.5 + 0.5 * warps / 20.0) * (ctas >= 2 ? 1.15 : 1.0);
+      if (score > best) { best = score; ng = g; smem1 = sm; }
     }
     if (ng > 0) {
       Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
@@ -689,9 +738,217 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
 }
 
 // ------------------------------------------------------------------------------------------
+// general m (Bluestein rows)
+struct PlanScope {   // run the power-of-two transform launchers on the cyclic length-L plan
+  hb_ctx* c; int logN, log_blk; HbPrimeDev* dp; size_t N;
+  explicit PlanScope(hb_ctx* c_) : c(c_), logN(c_->logN), log_blk(c_->log_blk), dp(c_->d_primes), N(c_->N) {
+    c->logN = c->gen.logL; c->log_blk = c->gen.log_blk_L; c->d_primes = c->gen.d_primes_cyc; c->N = c->gen.L;
+  }
+  ~PlanScope() { c->logN = logN; c->log_blk = log_blk; c->d_primes = dp; c->N = N; }
+};
+static long h_phi(long m) { long r = m, n = m; for (long p = 2; p * p <= n; p++) if (n % p == 0) { while (n % p == 0) n /= p; r -= r / p; } if (n > 1) r -= r / n; return r; }
+static long h_gcd(long a, long b) { while (b) { long t = a % b; a = b; b = t; } return a; }
+static bool h_isprime_small(long n) { if (n < 2) return false; for (long p = 2; p * p <= n; p++) if (n % p == 0) return false; return true; }
+// FindPrimitiveRoot (src/NumbTh.cpp:435-493): deterministic
+static u64 h_find_primitive_root(u64 q, u64 e) {
+  u64 root = 1, n = e;
+  for (u64 p = 2; p <= n; p++) {
+    if (n % p) continue;
+    u64 pp = 1; while (n % p == 0) { n /= p; pp *= p; }
+    u64 g = 2;
+    for (;; g++) if (h_isprime_small((long)g) && h_powmod(g, (q - 1) / p, q) != 1) break;
+    root = h_mulmod(root, h_powmod(g, (q - 1) / pp, q), q);
+  }
+  return root;
+}
+// multiply / exactly divide an integer polynomial by (X^k - 1)
+static void poly_mul_binom(std::vector<long>& a, long k) { std::vector<long> r(a.size() + k, 0); for (size_t i = 0; i < a.size(); i++) { r[i + k] += a[i]; r[i] -= a[i]; } a.swap(r); }
+static void poly_div_binom(std::vector<long>& a, long k) {   // a / (X^k - 1), exact
+  std::vector<long> qv(a.size() - k, 0);
+  for (long i = (long)a.size() - 1; i >= k; i--) { long cq = a[i]; qv[i - k] = cq; a[i] -= cq; a[i - k] += cq; }
+  a.swap(qv);
+}
+static int h_mobius(long n) { int mu = 1; for (long p = 2; p * p <= n; p++) if (n % p == 0) { n /= p; if (n % p == 0) return 0; mu = -mu; } if (n > 1) mu = -mu; return mu; }
+// Phi_m = prod_{d|m} (X^(m/d) - 1)^mu(d)
+static std::vector<long> h_cyclotomic(long m) {
+  std::vector<long> a(1, 1);
+  for (long d = 1; d <= m; d++) if (m % d == 0 && h_mobius(d) == 1) poly_mul_binom(a, m / d);
+  for (long d = 1; d <= m; d++) if (m % d == 0 && h_mobius(d) == -1) poly_div_binom(a, m / d);
+  return a;
+}
+
+static int gen_cyc_ntt(hb_ctx* c, int dir, u64* const* w, u64* const* tmp, int nit, const int32_t* idx, int n) {
+  PlanScope ps(c);
+  if (dir > 0) { HB_TRY(launch_cols(c, +1, (const u64* const*)w, tmp, nit, idx, n)); return launch_blk(c, +1, (const u64* const*)tmp, w, nit, idx, n, 0, nullptr); }
+  HB_TRY(launch_blk(c, -1, (const u64* const*)w, tmp, nit, idx, n, 0, nullptr));
+  return launch_cols(c, -1, (const u64* const*)tmp, w, nit, idx, n);
+}
+static int gen_k(hb_ctx* c, int op, int which, const u64* const* src, u64* const* dst, int nit, const int32_t* idx, int n) {
+  hb_ctx::Gen& g = c->gen;
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    HbGenJob J; memset(&J, 0, sizeof(J));
+    J.m = g.m; J.phim = g.phim; J.L = g.L; J.d = g.d; J.rep = g.d_rep; J.irep = g.d_irep; J.which = which;
+    fill_rows(J.rows, idx + r0, nr);
+    J.nitems = nit;
+    for (int i = 0; i < nit; i++) {
+      J.src[i] = src ? src[i] : nullptr; J.dst[i] = dst ? dst[i] : nullptr;
+      J.w0[i] = g.w0 + (size_t)i * c->nprimes * g.L; J.w1[i] = g.w1 + (size_t)i * c->nprimes * g.L;
+    }
+    unsigned gx = (unsigned)std::max<size_t>(1, g.L / (HB_THREADS * 4));
+    pre_launch(c);
+    HB_LAUNCH(k_gen, dim3(gx, nr, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, g.d_gp, J, op);
+    HB_TRY(post_launch(c, "k_gen", (u64)2 * nr * nit * g.L * 8));
+  }
+  return HB_OK;
+}
+static void gen_wptrs(hb_ctx* c, u64* base, int nit, u64** out) { for (int i = 0; i < nit; i++) out[i] = base + (size_t)i * c->nprimes * c->gen.L; }
+// coefficient rows (src) -> evaluation rows (dst); Cmodulus::FFT general branch
+static int gen_fwd(hb_ctx* c, const u64* const* src, u64* const* dst, int nit, const int32_t* idx, int n) {
+  u64 *W0[HB_MAXB], *WT[HB_MAXB]; gen_wptrs(c, c->gen.w0, nit, W0); gen_wptrs(c, c->gen.wt, nit, WT);
+  HB_TRY(gen_k(c, HB_GEN_PRE_FWD, 0, src, nullptr, nit, idx, n));
+  HB_TRY(gen_cyc_ntt(c, +1, W0, WT, nit, idx, n));
+  HB_TRY(gen_k(c, HB_GEN_MULVEC, 0, nullptr, nullptr, nit, idx, n));
+  HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n));
+  return gen_k(c, HB_GEN_POST_FWD, 0, nullptr, dst, nit, idx, n);
+}
+// evaluation rows (src) -> coefficient rows in [0,q) (dst); Cmodulus::iFFT general branch
+static int gen_inv(hb_ctx* c, const u64* const* src, u64* const* dst, int nit, const int32_t* idx, int n) {
+  u64 *W0[HB_MAXB], *W1[HB_MAXB], *WT[HB_MAXB]; gen_wptrs(c, c->gen.w0, nit, W0); gen_wptrs(c, c->gen.w1, nit, W1); gen_wptrs(c, c->gen.wt, nit, WT);
+  HB_TRY(gen_k(c, HB_GEN_PRE_INV, 0, src, nullptr, nit, idx, n));
+  HB_TRY(gen_cyc_ntt(c, +1, W0, WT, nit, idx, n));
+  HB_TRY(gen_k(c, HB_GEN_MULVEC, 1, nullptr, nullptr, nit, idx, n));
+  HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n));
+  HB_TRY(gen_k(c, HB_GEN_POST_INV, 0, nullptr, dst, nit, idx, n));
+  if (c->gen.d > 0) {   // remainder modulo Phi_m(X)
+    HB_TRY(gen_cyc_ntt(c, +1, W1, WT, nit, idx, n));
+    HB_TRY(gen_k(c, HB_GEN_MULVEC, 2, nullptr, nullptr, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, -1, W1, WT, nit, idx, n));
+    HB_TRY(gen_k(c, HB_GEN_QREV, 0, nullptr, nullptr, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, +1, W0, WT, nit, idx, n));
+    HB_TRY(gen_k(c, HB_GEN_MULVEC, 3, nullptr, nullptr, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n));
+  } else {
+    HB_CUDA(cudaMemsetAsync(c->gen.w0, 0, (size_t)nit * c->nprimes * c->gen.L * sizeof(u64), c->stream));
+  }
+  return gen_k(c, HB_GEN_FIN, 0, nullptr, dst, nit, idx, n);
+}
+// exact conversion on coefficient rows: rows src of polys -> x mod q_t as evaluation rows tgt in cB
+static int gen_conv(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p) {
+  ConvEntry* E; HB_TRY(get_conv(c, src, n, tgt, nt, p, &E));
+  u64 *A[HB_MAXB], *B[HB_MAXB];
+  for (int i = 0; i < nit; i++) { A[i] = c->gen.cA + (size_t)i * c->nprimes * c->N; B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N; }
+  HB_TRY(gen_inv(c, (const u64* const*)polys, A, nit, src, n));
+  HbPlainConvJob J; memset(&J, 0, sizeof(J));
+  J.cv = E->d; J.t = E->d_t; J.t_s = E->d_t_s; J.N = c->N; J.nitems = nit; J.stats = c->d_stats;
+  for (int i = 0; i < nit; i++) { J.src[i] = A[i]; J.dst[i] = B[i]; }
+  pre_launch(c);
+  HB_LAUNCH(k_conv_plain, dim3((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS), nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+  HB_TRY(post_launch(c, "k_conv_plain", (u64)(n + nt) * nit * c->N * 8));
+  return gen_fwd(c, (const u64* const*)B, B, nit, tgt, nt);
+}
+
+static int gen_init(hb_ctx* c, const uint64_t* psi) {
+  hb_ctx::Gen& g = c->gen;
+  const long m = (long)c->m;
+  g.on = true; g.m = m; g.phim = h_phi(m); g.d = g.m - g.phim;
+  g.logL = 0; while ((1L << g.logL) < 2 * m - 1) g.logL++;
+  g.L = 1ULL << g.logL; g.log_blk_L = g.logL >= 11 ? 8 : 0;
+  c->N = g.phim; c->logN = -1; c->log_blk = 0;
+  const u64 e = m % 2 == 0 ? 2 * m : m;
+  const int np = c->nprimes; const size_t L = g.L;
+  std::vector<int> rep, irep(m, -1);
+  for (long i = 1; i < m; i++) if (h_gcd(i, m) == 1) { irep[i] = (int)rep.size(); rep.push_back((int)i); }
+  HB_TRY(ctx_alloc(c, (void**)&g.d_rep, sizeof(int) * rep.size()));
+  HB_TRY(ctx_alloc(c, (void**)&g.d_irep, sizeof(int) * m));
+  HB_CUDA(cudaMemcpy(g.d_rep, rep.data(), sizeof(int) * rep.size(), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(g.d_irep, irep.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  // integer polynomials Phi_m and rev((X^m-1)/Phi_m) mod X^d
+  std::vector<long> phi = h_cyclotomic(m);
+  std::vector<long> psiq(1, 1);   // (X^m - 1)/Phi_m = prod_{d|m, d>1} (X^(m/d)-1)^(-mu(d))
+  for (long dd = 2; dd <= m; dd++) if (m % dd == 0 && h_mobius(dd) == -1) poly_mul_binom(psiq, m / dd);
+  for (long dd = 2; dd <= m; dd++) if (m % dd == 0 && h_mobius(dd) == 1) poly_div_binom(psiq, m / dd);
+  if ((long)phi.size() != (long)g.phim + 1 || (long)psiq.size() != (long)g.d + 1) return hb_fail(HB_ERR_BAD_ARG, "internal: cyclotomic polynomial degree mismatch");
+  // device tables: per prime  pw[m] ipw[m] (ulonglong2)  | 4 vectors of L  | cyclic twiddles 2 x L (ulonglong2)
+  const size_t per = (size_t)2 * m * 16 + 4 * L * 8 + 2 * L * 16;
+  std::vector<unsigned char> tab(per * np);
+  HB_TRY(ctx_alloc(c, &g.tab, tab.size()));
+  std::vector<HbGenPrime> gp(np);
+  std::vector<HbPrimeDev> pc(np);
+  std::vector<unsigned> brev(L);
+  for (size_t k = 0; k < L; k++) { unsigned r = 0; for (int b = 0; b < g.logL; b++) if (k >> b & 1) r |= 1u << (g.logL - 1 - b); brev[k] = r; }
+  for (int i = 0; i < np; i++) {
+    const u64 q = c->q[i];
+    if ((q - 1) % e != 0 || (q - 1) % L != 0) return hb_fail(HB_ERR_UNSUPPORTED, "prime %d: q-1 is not divisible by %llu and the Bluestein length %llu", i, (unsigned long long)e, (unsigned long long)L);
+    const u64 root = psi ? psi[i] : h_find_primitive_root(q, e);
+    if (h_powmod(root, e, q) != 1) return hb_fail(HB_ERR_BAD_ARG, "psi[%d] is not a %llu-th root of unity", i, (unsigned long long)e);
+    c->psi[i] = root;
+    const u64 rinv = h_powmod(root, q - 2, q);
+    unsigned char* base = tab.data() + per * i;
+    ulonglong2* pw = (ulonglong2*)base; ulonglong2* ipw = pw + m;
+    u64* vec = (u64*)(ipw + m);   // RbHat, iRbHat, invHat, phiHat (raw here, transformed on the device below)
+    ulonglong2* fwc = (ulonglong2*)(vec + 4 * L); ulonglong2* iwc = fwc + L;
+    memset(vec, 0, 4 * L * 8);
+    for (long k = 0; k < m; k++) {
+      const u64 ex = (u64)(((u128)k * k) % e);
+      const u64 a = h_powmod(root, ex, q), b = h_powmod(rinv, ex, q);
+      pw[k] = make_ulonglong2(a, h_shoup(a, q)); ipw[k] = make_ulonglong2(b, h_shoup(b, q));
+      // chirp kernels b[m-1 +- k] (src/bluestein.cpp:118-128)
+      vec[0 * L + (m - 1 + k)] = b; vec[0 * L + (m - 1 - k)] = b;
+      vec[1 * L + (m - 1 + k)] = a; vec[1 * L + (m - 1 - k)] = a;
+    }
+    for (size_t k = 0; k < g.d; k++) { long v = psiq[g.d - k] % (long)q; vec[2 * L + k] = (u64)(v < 0 ? v + (long)q : v); }   // rev(Psi) mod X^d
+    for (size_t k = 0; k <= g.phim; k++) { long v = phi[k] % (long)q; vec[3 * L + k] = (u64)(v < 0 ? v + (long)q : v); }
+    // cyclic twiddles: fw[2^s + i] = omega^((L / 2^(s+1)) * brev_s(i))
+    u64 gnr = 2; while (h_powmod(gnr, (q - 1) / 2, q) != q - 1) gnr++;
+    const u64 om = h_powmod(gnr, (q - 1) / L, q), iom = h_powmod(om, q - 2, q);
+    std::vector<u64> opw(L), iopw(L);
+    { u64 w = 1, iw = 1; for (size_t k = 0; k < L; k++) { opw[k] = w; iopw[k] = iw; w = h_mulmod(w, om, q); iw = h_mulmod(iw, iom, q); } }
+    fwc[0] = iwc[0] = make_ulonglong2(1, h_shoup(1, q));
+    for (int s2 = 0; s2 < g.logL; s2++)
+      for (size_t ii = 0; ii < (1ULL << s2); ii++) {
+        const size_t br = s2 ? (brev[ii] >> (g.logL - s2)) : 0;
+        const size_t ex = (L >> (s2 + 1)) * br;
+        fwc[(1ULL << s2) + ii] = make_ulonglong2(opw[ex], h_shoup(opw[ex], q));
+        iwc[(1ULL << s2) + ii] = make_ulonglong2(iopw[ex], h_shoup(iopw[ex], q));
+      }
+    unsigned char* dbase = (unsigned char*)g.tab + per * i;
+    gp[i].pw = (const ulonglong2*)dbase; gp[i].ipw = gp[i].pw + m;
+    const u64* dvec = (const u64*)(gp[i].ipw + m);
+    gp[i].RbHat = dvec; gp[i].iRbHat = dvec + L; gp[i].invHat = dvec + 2 * L; gp[i].phiHat = dvec + 3 * L;
+    gp[i].minv = h_powmod((u64)m % q, q - 2, q); gp[i].minv_s = h_shoup(gp[i].minv, q);
+    pc[i] = c->h_primes[i];
+    pc[i].fw = (const ulonglong2*)(dvec + 4 * L); pc[i].iw = pc[i].fw + L;
+    pc[i].ninv = h_powmod((u64)L % q, q - 2, q); pc[i].ninv_s = h_shoup(pc[i].ninv, q);
+  }
+  HB_CUDA(cudaMemcpy(g.tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&g.d_gp, sizeof(HbGenPrime) * np));
+  HB_CUDA(cudaMemcpy(g.d_gp, gp.data(), sizeof(HbGenPrime) * np, cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&g.d_primes_cyc, sizeof(HbPrimeDev) * np));
+  HB_CUDA(cudaMemcpy(g.d_primes_cyc, pc.data(), sizeof(HbPrimeDev) * np, cudaMemcpyHostToDevice));
+  const size_t wsz = (size_t)HB_MAXB * np * L * sizeof(u64), csz = (size_t)HB_MAXB * np * c->N * sizeof(u64);
+  HB_TRY(ctx_alloc(c, (void**)&g.w0, wsz)); HB_TRY(ctx_alloc(c, (void**)&g.w1, wsz)); HB_TRY(ctx_alloc(c, (void**)&g.wt, wsz));
+  HB_TRY(ctx_alloc(c, (void**)&g.cA, csz)); HB_TRY(ctx_alloc(c, (void**)&g.cB, csz));
+  // transform the four fixed vectors of every prime in place (layout per prime is not [np][L], so one prime at a time)
+  for (int i = 0; i < np; i++) {
+    for (int v = 0; v < 4; v++) {
+      u64* dv = (u64*)((unsigned char*)g.tab + per * i + (size_t)2 * m * 16) + (size_t)v * L;
+      // stage through w0 row i so that the launchers' row addressing (prime index * L) applies
+      HB_CUDA(cudaMemcpyAsync(g.w0 + (size_t)i * L, dv, L * 8, cudaMemcpyDeviceToDevice, c->stream));
+      u64* W0[1] = {g.w0}; u64* WT[1] = {g.wt}; int32_t one[1] = {i};
+      HB_TRY(gen_cyc_ntt(c, +1, W0, WT, 1, one, 1));
+      HB_CUDA(cudaMemcpyAsync(dv, g.w0 + (size_t)i * L, L * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // C ABI: transforms and pointwise
 extern "C" int hb_ntt_fwd(hb_poly* const* polys, int nitems, const int32_t* idx, int n) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_ntt_fwd")); HB_TRY(check_idx(c, idx, n, "hb_ntt_fwd"));
+  if (c->gen.on) return for_items(nitems, [&](int i0, int nit) { u64* P[HB_MAXB]; ptrs_of(polys, i0, nit, P); return gen_fwd(c, (const u64* const*)P, P, nit, idx, n); });
   HB_TRY(ctx_scratch(c));
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpA, nit, tA);
@@ -701,6 +958,7 @@ extern "C" int hb_ntt_fwd(hb_poly* const* polys, int nitems, const int32_t* idx,
 }
 extern "C" int hb_ntt_inv(hb_poly* const* polys, int nitems, const int32_t* idx, int n) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_ntt_inv")); HB_TRY(check_idx(c, idx, n, "hb_ntt_inv"));
+  if (c->gen.on) return for_items(nitems, [&](int i0, int nit) { u64* P[HB_MAXB]; ptrs_of(polys, i0, nit, P); return gen_inv(c, (const u64* const*)P, P, nit, idx, n); });
   HB_TRY(ctx_scratch(c));
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpA, nit, tA);
@@ -775,6 +1033,16 @@ static int add_primes_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   if (nadd == 0) return HB_OK;  // src/DoubleCRT.cpp:569-572
   HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimes"));
   if (ncur == 0) return hb_zero_rows(polys, nitems, add, nadd);  // src/DoubleCRT.cpp:577-583
+  if (c->gen.on) {
+    if (log_norms) return hb_fail(HB_ERR_UNSUPPORTED, "embedding norms are only computed for power-of-two m");
+    return for_items(nitems, [&](int i0, int nit) {
+      u64* P[HB_MAXB]; u64* B[HB_MAXB]; ptrs_of(polys, i0, nit, P);
+      for (int i = 0; i < nit; i++) B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N;
+      HB_TRY(gen_conv(c, P, nit, cur, ncur, add, nadd, 1));
+      PwArgs A; memset(&A, 0, sizeof(A)); A.op = HB_PW_COPY; A.dst = P; A.a = (const u64* const*)B;
+      return launch_pw(c, A, nit, add, nadd);
+    });
+  }
   HB_TRY(ctx_scratch(c));
   double logQ = 0; for (int j = 0; j < ncur; j++) logQ += std::log((double)c->q[cur[j]]);
   return for_items(nitems, [&](int i0, int nit) {
@@ -808,6 +1076,16 @@ static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   if (diff.empty()) return HB_OK;  // src/DoubleCRT.cpp:1468-1470
   if (kept.empty()) return hb_fail(HB_ERR_INDEX_SET, "scaleDownToSet: s and the index set must have some intersection");  // :1474-1476
   std::vector<u64> sc; HB_TRY(scalars_by_primes(c, kept.data(), (int)kept.size(), diff.data(), (int)diff.size(), 1, sc));
+  if (c->gen.on) {
+    if (norms) return hb_fail(HB_ERR_UNSUPPORTED, "embedding norms are only computed for power-of-two m");
+    return for_items(nitems, [&](int i0, int nit) {
+      u64* P[HB_MAXB]; u64* B[HB_MAXB]; ptrs_of(polys, i0, nit, P);
+      for (int i = 0; i < nit; i++) B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N;
+      HB_TRY(gen_conv(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space));
+      PwArgs A; memset(&A, 0, sizeof(A)); A.op = HB_PW_SUBSCALE; A.dst = P; A.a = (const u64* const*)B; A.scal = sc.data();
+      return launch_pw(c, A, nit, kept.data(), (int)kept.size());
+    });
+  }
   HB_TRY(ctx_scratch(c));
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
@@ -830,14 +1108,20 @@ extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, u
   HB_TRY(check_idx(c, idx, n, "hb_to_poly", true));
   if (n == 0) { memset(out, 0, sizeof(u64) * c->N * Lout); return HB_OK; }  // src/DoubleCRT.cpp:931-935
   if (Lout < n) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly: Lout=%d limbs cannot hold a %d-prime product", Lout, n);
-  HB_TRY(ctx_scratch(c));
   ConvEntry* E; HB_TRY(get_conv(c, idx, n, nullptr, 0, 1, &E));
-  u64* P[1] = {p->d}; u64* tA[1] = {c->tmpA}; u64* tB[1] = {c->tmpB};
-  HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, 1, idx, n, 0, nullptr));
-  HB_TRY(launch_cols(c, -1, (const u64* const*)tA, tB, 1, idx, n));
+  u64* P[1] = {p->d};
+  const u64* coef;
+  if (c->gen.on) { u64* A[1] = {c->gen.cA}; HB_TRY(gen_inv(c, (const u64* const*)P, A, 1, idx, n)); coef = c->gen.cA; }
+  else {
+    HB_TRY(ctx_scratch(c));
+    u64* tA[1] = {c->tmpA}; u64* tB[1] = {c->tmpB};
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, 1, idx, n, 0, nullptr));
+    HB_TRY(launch_cols(c, -1, (const u64* const*)tA, tB, 1, idx, n));
+    coef = c->tmpB;
+  }
   u64* d_out; size_t bytes = c->N * (size_t)Lout * sizeof(u64);
   HB_CUDA(cudaMalloc((void**)&d_out, bytes));
-  HbCrtJob J; J.cv = E->d; J.N = (int)c->N; J.Lout = Lout; J.positive = positive; J.src = c->tmpB; J.out = d_out;
+  HbCrtJob J; J.cv = E->d; J.N = (int)c->N; J.Lout = Lout; J.positive = positive; J.src = coef; J.out = d_out;
   HbCrtTabs T; T.t = E->d_t; T.t_s = E->d_t_s;
   dim3 grid((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS));
   pre_launch(c);
@@ -855,6 +1139,7 @@ extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, u
 extern "C" int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned, hb_poly* const* ypolys) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_conv_make_y")); HB_TRY(check_polys(ypolys, nitems, &c, "hb_conv_make_y"));
   HB_TRY(check_idx(c, D, nD, "hb_conv_make_y")); HB_TRY(check_idx(c, owned, nOwned, "hb_conv_make_y(owned)", true));
+  if (c->gen.on) return hb_fail(HB_ERR_UNSUPPORTED, "prime-sharded conversion is only built for power-of-two m");
   if (nOwned == 0) return HB_OK;
   std::vector<u64> sc(nOwned);
   for (int k = 0; k < nOwned; k++) {
@@ -876,6 +1161,7 @@ extern "C" int hb_conv_from_y(hb_poly* const* ypolys, int nitems, const int32_t*
                               uint64_t ptxt_space, hb_poly* const* dst, int mode) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(ypolys, nitems, &c, "hb_conv_from_y")); HB_TRY(check_polys(dst, nitems, &c, "hb_conv_from_y"));
   HB_TRY(check_idx(c, D, nD, "hb_conv_from_y")); HB_TRY(check_idx(c, tgt, nT, "hb_conv_from_y(targets)", true));
+  if (c->gen.on) return hb_fail(HB_ERR_UNSUPPORTED, "prime-sharded conversion is only built for power-of-two m");
   if (nT == 0) return HB_OK;
   HB_TRY(check_disjoint(D, nD, tgt, nT, "hb_conv_from_y"));
   if (ptxt_space < 1 || mode < 0 || mode > 1) return hb_fail(HB_ERR_BAD_ARG, "hb_conv_from_y: bad ptxt_space or mode");
@@ -956,8 +1242,15 @@ static int break_into_digits_impl(hb_poly* const* src, int nitems, const int32_t
   return HB_OK;
 }
 
+static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal);
 extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                                    hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1) {
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr);
+}
+// scal (optional, [n]): out = scal[r]*out + sum (0 => out = sum): addPrimesAndScale folded in
+static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal) {
   hb_ctx* c = nullptr;
   HB_TRY(check_polys(out0, nitems, &c, "hb_keyswitch_digits")); HB_TRY(check_polys(out1, nitems, &c, "hb_keyswitch_digits"));
   if (ndig <= 0 || ndig > HB_MAXDIG || ndig > maxdig) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits: ndig=%d out of range", ndig);
@@ -968,8 +1261,9 @@ extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig,
     for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
       int nr = std::min(HB_MAXROWS, n - r0);
       HbKsJob J; memset(&J, 0, sizeof(J));
-      J.logN = c->logN; J.ndig = ndig; J.nitems = nit;
+      J.logN = c->logN; J.N = c->N; J.ndig = ndig; J.nitems = nit;
       fill_rows(J.rows, idx + r0, nr);
+      if (scal) { J.mode = 1; for (int i = 0; i < nr; i++) J.scal[i] = scal[r0 + i]; }
       for (int i = 0; i < ndig; i++) { J.evk_a[i] = evk_a[i]->d; J.evk_b[i] = evk_b[i]->d; }
       for (int it = 0; it < nit; it++) {
         J.out0[it] = out0[i0 + it]->d; J.out1[it] = out1[i0 + it]->d;
@@ -1006,8 +1300,21 @@ extern "C" int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const*
 extern "C" int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, uint64_t k) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(dst, nitems, &c, "hb_automorph")); HB_TRY(check_polys(src, nitems, &c, "hb_automorph"));
   HB_TRY(check_idx(c, idx, n, "hb_automorph"));
-  if ((k & 1) == 0 || k >= c->m) return hb_fail(HB_ERR_INDEX_SET, "DoubleCRT::automorph: k not in Zm*");  // src/DoubleCRT.cpp:1165-1167
+  if (k == 0 || k >= c->m || h_gcd((long)k, (long)c->m) != 1) return hb_fail(HB_ERR_INDEX_SET, "DoubleCRT::automorph: k not in Zm*");  // src/DoubleCRT.cpp:1165-1167
   for (int i = 0; i < nitems; i++) if (dst[i] == src[i]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph: dst must differ from src");
+  if (c->gen.on) return for_items(nitems, [&](int i0, int nit) {
+    for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+      int nr = std::min(HB_MAXROWS, n - r0);
+      HbGenAutoJob J; memset(&J, 0, sizeof(J));
+      J.m = c->gen.m; J.phim = c->gen.phim; J.k = k; J.rep = c->gen.d_rep; J.irep = c->gen.d_irep; J.nitems = nit;
+      fill_rows(J.rows, idx + r0, nr);
+      for (int i = 0; i < nit; i++) { J.src[i] = src[i0 + i]->d; J.dst[i] = dst[i0 + i]->d; }
+      pre_launch(c);
+      HB_LAUNCH(k_gen_automorph, dim3((unsigned)std::max<size_t>(1, c->N / HB_THREADS), nr, nit), dim3(HB_THREADS), 0, c->stream, J);
+      HB_TRY(post_launch(c, "k_gen_automorph", (u64)2 * nr * nit * c->N * 8));
+    }
+    return HB_OK;
+  });
   return for_items(nitems, [&](int i0, int nit) {
     u64* D[HB_MAXB]; u64* S[HB_MAXB]; ptrs_of(dst, i0, nit, D); ptrs_of(src, i0, nit, S);
     PwArgs A; memset(&A, 0, sizeof(A));
@@ -1027,14 +1334,16 @@ extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* c
   const int maxdig = c->ndigits;
   std::vector<hb_poly*> dig; HB_TRY(pool_get(c, nitems * maxdig, dig));
   std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
-  // parts with handle 1 / base s: addPrimesAndScale(special)  (src/Ctxt.cpp:764-768)
-  HB_TRY(hb_add_primes_and_scale(c0, nitems, S, nS, c->special.data(), (int)c->special.size()));
-  HB_TRY(hb_add_primes_and_scale(c1, nitems, S, nS, c->special.data(), (int)c->special.size()));
   // keySwitchPart (src/Ctxt.cpp:805-842)
   int nd = 0;
   HB_TRY(hb_break_into_digits(c2, nitems, S, nS, dig.data(), maxdig, &nd));
   if (nd > ndig_evk) return hb_fail(HB_ERR_BAD_ARG, "hb_relinearize: key-switching matrix has %d columns, need %d", ndig_evk, nd);
-  return hb_keyswitch_digits(dig.data(), maxdig, nd, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0, c1);
+  // parts with handle 1 / base s: addPrimesAndScale(special) (src/Ctxt.cpp:764-768) is folded into the
+  // inner product: rows of S are scaled by P mod q, special rows start from zero
+  std::vector<u64> sc(Sp.size(), 0);
+  for (size_t r = 0; r < Sp.size(); r++)
+    if (std::find(S, S + nS, Sp[r]) != S + nS) sc[r] = prod_mod(c, c->special.data(), (int)c->special.size(), c->q[Sp[r]]);
+  return keyswitch_digits_impl(dig.data(), maxdig, nd, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0, c1, sc.data());
 }
 
 extern "C" int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1, int nitems,

@@ -52,6 +52,19 @@ def load_library(path: str | None = None):
     return _LIB
 
 
+def _euler_phi(m):
+    r, n, p = m, m, 2
+    while p * p <= n:
+        if n % p == 0:
+            while n % p == 0:
+                n //= p
+            r -= r // p
+        p += 1
+    if n > 1:
+        r -= r // n
+    return r
+
+
 def _idx(idx):
     a = np.ascontiguousarray(np.asarray(list(idx), dtype=np.int32))
     return a, a.ctypes.data_as(i32p), len(a)
@@ -110,7 +123,7 @@ class Engine:
     def __init__(self, m, primes, psis=None, digits=None, special=None, device=0, lib=None):
         self.lib = lib if lib is not None else load_library()
         self.m = int(m)
-        self.N = self.m // 2
+        self.N = _euler_phi(self.m)      # row length phi(m) (= m/2 for the power-of-two rings)
         self.primes = [int(q) for q in primes]
         self.np = len(self.primes)
         self.h = C.c_void_p()

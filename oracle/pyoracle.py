@@ -580,3 +580,115 @@ def embedding_largest_coeff(coeffs, m: int):
     tw = np.exp(1j * np.pi * k / n)                 # zeta^k, zeta = e^(i pi / n)
     vals = np.fft.ifft(ff * tw) * n                 # sum_k f_k zeta^k e^(+2 pi i k j / n) = f(zeta^(2j+1))
     return float(np.max(np.abs(vals))), shift
+
+
+# ---------------------------------------------------------------------------
+# general (non power-of-two) m: Bluestein rows  (src/bluestein.cpp, src/CModulus.cpp:148-180,431-443,555-577)
+# ---------------------------------------------------------------------------
+
+
+def prime_factors(n: int):
+    out, p = [], 2
+    while p * p <= n:
+        if n % p == 0:
+            out.append(p)
+            while n % p == 0:
+                n //= p
+        p += 1
+    if n > 1:
+        out.append(n)
+    return out
+
+
+def find_primitive_root(q: int, e: int) -> int:
+    """FindPrimitiveRoot (src/NumbTh.cpp:435-493): deterministic.  For each prime p | e take the smallest
+    prime g with g^((q-1)/p) != 1 and multiply the elements g^((q-1)/pp) of order pp = p^v || e."""
+    assert (q - 1) % e == 0
+    root = 1
+    for p in prime_factors(e):
+        pp = p
+        ee = e // p
+        while ee % p == 0:
+            ee //= p
+            pp *= p
+        g = 2
+        while True:
+            if is_prime(g) and pow(g, (q - 1) // p, q) != 1:
+                break
+            g += 1
+        root = root * pow(g, (q - 1) // pp, q) % q
+    assert pow(root, e, q) == 1 and all(pow(root, e // p, q) != 1 for p in prime_factors(e))
+    return root
+
+
+def zms_rep(m: int):
+    """rep(j): the j-th element of Z_m^* in ascending order (PAlgebra zmsRep, src/PAlgebra.cpp:535-540)."""
+    return [j for j in range(1, m) if math.gcd(j, m) == 1] if m > 1 else []
+
+
+def cyclotomic_poly(m: int):
+    """Phi_m(X) over the integers (PAlgebra::getPhimX)."""
+    def polydiv_exact(a, b):  # a / b, integer polys as lists (low -> high), exact
+        a = list(a)
+        out = [0] * (len(a) - len(b) + 1)
+        for i in range(len(out) - 1, -1, -1):
+            c = a[i + len(b) - 1] // b[-1]
+            out[i] = c
+            for j, bj in enumerate(b):
+                a[i + j] -= c * bj
+        return out
+    phi = [-1] + [0] * (m - 1) + [1]            # X^m - 1
+    for d in range(1, m):
+        if m % d == 0:
+            phi = polydiv_exact(phi, cyclotomic_poly(d))
+    return phi
+
+
+def cmod_root(q: int, m: int) -> int:
+    """The root Cmodulus derives for general m (src/CModulus.cpp:148-165): primitive 2m-th root for even m,
+    m-th for odd m."""
+    return find_primitive_root(q, 2 * m if m % 2 == 0 else m)
+
+
+def bluestein_dft(x, n: int, root: int, q: int):
+    """What BluesteinFFT computes (src/bluestein.cpp:134-201): X_k = sum_i x_i root^(2ik), k = 0..n-1,
+    via X_k = root^(k^2) * sum_i (x_i root^(i^2)) root^(-(k-i)^2); exponents mod 2n (n even) or n (n odd)."""
+    e = 2 * n if n % 2 == 0 else n
+    pw = [pow(root, i * i % e, q) for i in range(n)]
+    rinv = pow(root, q - 2, q)
+    ipw = [pow(rinv, i * i % e, q) for i in range(n)]
+    y = [(int(x[i]) * pw[i]) % q if i < len(x) else 0 for i in range(n)]
+    out = []
+    for k in range(n):
+        acc = 0
+        for i in range(n):
+            if y[i]:
+                acc += y[i] * ipw[abs(k - i)]
+        out.append(acc % q * pw[k] % q)
+    return out
+
+
+def gen_fft(coeffs, q: int, m: int, root: int):
+    """Cmodulus::FFT for general m (src/CModulus.cpp:431-443): length-m Bluestein DFT, keep Z_m^* entries:
+    row[j] = f(zeta^rep(j)), zeta = root^2."""
+    X = bluestein_dft(list(coeffs), m, root, q)
+    return [X[r] for r in zms_rep(m)]
+
+
+def gen_ifft(row, q: int, m: int, root: int):
+    """Cmodulus::iFFT for general m (src/CModulus.cpp:555-577): scatter into Z_m^* positions, Bluestein DFT with
+    root^-1, reduce mod Phi_m(X), multiply by m^-1.  Coefficients in [0,q)."""
+    rep = zms_rep(m)
+    x = [0] * m
+    for j, r in enumerate(rep):
+        x[r] = int(row[j])
+    A = bluestein_dft(x, m, pow(root, q - 2, q), q)
+    phi = cyclotomic_poly(m)
+    A = list(A)
+    for k in range(m - 1, len(phi) - 2, -1):          # remainder mod Phi_m (monic)
+        c = A[k]
+        if c:
+            for j, pj in enumerate(phi):
+                A[k - (len(phi) - 1) + j] = (A[k - (len(phi) - 1) + j] - c * pj) % q
+    minv = pow(m, q - 2, q)
+    return [a * minv % q for a in A[:len(phi) - 1]]

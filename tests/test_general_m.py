@@ -1,0 +1,146 @@
+"""Rows for general (non power-of-two) m: Bluestein transforms and the DoubleCRT operations on top of
+them (reference src/bluestein.cpp:77-201, src/CModulus.cpp:148-180,
+431-443,555-577).  Checked against the Python restatement (definition-level DFT + remainder mod Phi_m).
+For general m the root is pinned: FindPrimitiveRoot is deterministic (src/NumbTh.cpp:435-493)."""
+import random
+
+import numpy as np
+import pytest
+
+import orc
+import pyoracle as po
+from helib_b200 import Engine
+
+
+def backends():
+    return [pytest.param("sim", id="sim"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=backends())
+def lib(request):
+    return request.getfixturevalue("sim_lib" if request.param == "sim" else "cuda_lib")
+
+
+CFGS = [(45, 2, 1, 100, 2), (28, 3, 1, 100, 2), (105, 2, 1, 120, 2), (1285, 2, 1, 120, 2)]
+
+
+def setup(lib, cfg):
+    m, p, r, bits, c = cfg
+    ch = po.build_mod_chain(m, p, r, bits, c)
+    roots = [po.cmod_root(q, m) for q in ch.primes]
+    E = Engine(m, ch.primes, None, ch.digits, ch.special, lib=lib)
+    assert E.psis == roots, "engine's FindPrimitiveRoot restatement disagrees with the oracle's"
+    assert E.N == ch.phim
+    return ch, roots, E
+
+
+def dense(ch, rows):
+    out = np.zeros((len(ch.primes), ch.phim), dtype=np.uint64)
+    for i, r in rows.items():
+        out[i] = np.array(r, dtype=np.uint64)
+    return out
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_bluestein_rows_match_definition(lib, cfg):
+    ch, roots, E = setup(lib, cfg)
+    rnd = random.Random(5)
+    idx = ch.ctxt + ch.special
+    coef = {i: [rnd.randrange(ch.primes[i]) for _ in range(ch.phim)] for i in idx}
+    P = E.poly(dense(ch, coef), idx)
+    E.ntt_fwd([P], idx)
+    got = P.download(idx)
+    small = ch.m <= 200
+    for i in idx[:3] if not small else idx:
+        ref = po.gen_fft(coef[i], ch.primes[i], ch.m, roots[i]) if small else None
+        if small:
+            assert list(got[i]) == ref
+        else:   # spot-check the definition row[j] = f(zeta^rep(j)) at a few j
+            q, zeta, rep = ch.primes[i], roots[i] * roots[i] % ch.primes[i], po.zms_rep(ch.m)
+            for j in (0, 1, ch.phim // 2, ch.phim - 1):
+                assert int(got[i][j]) == sum(cf * pow(zeta, rep[j] * k, q) for k, cf in enumerate(coef[i])) % q
+    E.ntt_inv([P], idx)
+    back = P.download(idx)
+    for i in idx:
+        assert list(back[i]) == coef[i]       # iFFT(FFT(f)) == f (tests/TestHEXL.cpp:189-218)
+
+
+@pytest.mark.parametrize("cfg", CFGS[:3])
+def test_general_m_doublecrt_ops(lib, cfg):
+    """toPoly / addPrimes / scaleDownToSet / breakIntoDigits / automorph on Bluestein rows vs big-int Python."""
+    ch, roots, E = setup(lib, cfg)
+    rnd = random.Random(6)
+    m, n = ch.m, ch.phim
+    S, Sp = ch.ctxt, sorted(ch.ctxt + ch.special)
+
+    class GenD:   # minimal big-int model of a DoubleCRT over general m
+        def __init__(self, rows):
+            self.rows = rows
+
+        def to_poly(self, idx):
+            Q = ch.product(idx)
+            cs = {i: po.gen_ifft(self.rows[i], ch.primes[i], m, roots[i]) for i in idx}
+            out = []
+            for k in range(n):
+                acc = 0
+                for i in idx:
+                    q = ch.primes[i]; Qi = Q // q
+                    acc += Qi * (cs[i][k] * pow(Qi % q, -1, q) % q)
+                out.append(po.bal(acc, Q))
+            return out
+
+    def rows_of_poly(poly, idx):
+        return {i: po.gen_fft([c % ch.primes[i] for c in poly], ch.primes[i], m, roots[i]) for i in idx}
+
+    x = {i: [rnd.randrange(ch.primes[i]) for _ in range(n)] for i in Sp}
+    X = GenD(x)
+    P = E.poly(dense(ch, x), Sp)
+    # toPoly
+    assert orc.limbs_to_ints(E.to_poly(P, S)) == X.to_poly(S)
+    # scaleDownToSet (drop the special primes), BGV correction with p
+    p = ch.p ** ch.r
+    Pd = ch.product(ch.special)
+    delta = X.to_poly(ch.special)
+    pinv = pow(Pd % p, -1, p)
+    for k, d in enumerate(delta):
+        u = d % p
+        if u:
+            u = u * pinv % p
+            if u > p // 2 or (p % 2 == 0 and u == p // 2 and d < 0):
+                u -= p
+            delta[k] = d - Pd * u
+    drows = rows_of_poly(delta, S)
+    want = {i: [((a - b) * pow(Pd % ch.primes[i], -1, ch.primes[i])) % ch.primes[i] for a, b in zip(x[i], drows[i])] for i in S}
+    E.scale_down([P], Sp, S, p)
+    got = P.download(S)
+    for i in S:
+        assert list(got[i]) == want[i]
+    # addPrimes back to the special primes: new rows are the balanced polynomial's residues
+    Y = GenD(want)
+    poly = Y.to_poly(S)
+    new = rows_of_poly(poly, ch.special)
+    E.add_primes([P], S, ch.special)
+    got = P.download(ch.special)
+    for i in ch.special:
+        assert list(got[i]) == new[i]
+    # breakIntoDigits: balanced mixed radix
+    digs = E.break_into_digits([P], S)[0]
+    acc, scale = [0] * n, 1
+    for dnum, D in enumerate(digs):
+        dset = [i for i in S if i in ch.digits[dnum]]
+        drow = D.download(Sp)
+        Ei = GenD({i: [int(v) for v in drow[i]] for i in dset}).to_poly(dset)
+        for i in Sp:     # every row of the digit is the same small polynomial
+            assert list(drow[i]) == rows_of_poly(Ei, [i])[i]
+        acc = [a + e * scale for a, e in zip(acc, Ei)]
+        scale *= ch.product(ch.digits[dnum])
+    assert [po.bal(a, ch.product(S)) for a in acc] == poly
+    # automorph: F(X) -> F(X^k)
+    k = [t for t in range(2, m) if np.gcd(t, m) == 1][1]
+    D = E.poly()
+    E.automorph([D], [P], S, k)
+    rep = po.zms_rep(m)
+    got = D.download(S)
+    cur = P.download(S)
+    for i in S:
+        assert [int(v) for v in got[i]] == [int(cur[i][rep.index(rep[j] * k % m)]) for j in range(n)]
