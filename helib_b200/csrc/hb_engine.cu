@@ -24,6 +24,7 @@ typedef unsigned __int128 u128;
 // ------------------------------------------------------------------------------------------
 // errors
 static thread_local char g_err[512] = "";
+static thread_local int g_chunk = 16;   // batch items per launch for the current call (hb_ctx::chunk)
 static int hb_fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
   return code;
@@ -75,6 +76,7 @@ struct hb_ctx {
   cudaEvent_t ev0, ev1;
   size_t max_smem;
   bool force_v0;     // HB_FORCE_V0=1: generic radix-2 kernels only (A/B testing)
+  int chunk;         // batch items per launch (<= HB_MAXB; HB_CHUNK overrides): keeps the phase scratch L2-sized
   int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
   // general (non power-of-two) m: Bluestein state
   struct Gen {
@@ -169,6 +171,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
   { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
+  { const char* e = getenv("HB_CHUNK"); int v = e ? atoi(e) : HB_MAXB; c->chunk = v >= 1 && v <= HB_MAXB ? v : HB_MAXB; }
   c->resident_ctas = 296;
 #ifdef HB_SIM
   c->resident_ctas = 7;   // few, odd: every simulated CTA walks several units and crosses (row, block-group) boundaries
@@ -356,7 +359,7 @@ static int check_polys(hb_poly* const* p, int n, hb_ctx** c, const char* who) {
   if (!p || n <= 0) return hb_fail(HB_ERR_BAD_ARG, "%s: no polynomials", who);
   for (int i = 0; i < n; i++) {
     if (!p[i]) return hb_fail(HB_ERR_BAD_ARG, "%s: null polynomial handle", who);
-    if (*c == nullptr) *c = p[i]->ctx;
+    if (*c == nullptr) { *c = p[i]->ctx; g_chunk = (*c)->chunk; }
     if (p[i]->ctx != *c) return hb_fail(HB_ERR_INDEX_SET, "%s: incompatible objects (different contexts)", who);  // src/DoubleCRT.cpp:222-223
   }
   return HB_OK;
@@ -566,9 +569,9 @@ static int launch_pw(hb_ctx* c, const PwArgs& A, int nitems, const int32_t* idx,
   return HB_OK;
 }
 
-// run f(item0, count) over chunks of at most HB_MAXB items
+// run f(item0, count) over chunks of at most `chunk` (<= HB_MAXB) items
 template <class F> static int for_items(int nitems, F f) {
-  for (int i0 = 0; i0 < nitems; i0 += HB_MAXB) HB_TRY(f(i0, std::min(HB_MAXB, nitems - i0)));
+  for (int i0 = 0; i0 < nitems; i0 += g_chunk) HB_TRY(f(i0, std::min(g_chunk, nitems - i0)));
   return HB_OK;
 }
 static void ptrs_of(hb_poly* const* p, int i0, int n, u64** out) { for (int i = 0; i < n; i++) out[i] = p[i0 + i]->d; }
