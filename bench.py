@@ -230,17 +230,16 @@ def main():
 
     upload_all()
     E.sync()
+    sampler = ClockSampler(local) if rank == 0 else None   # nvidia-smi needs ~0.2 s to deliver its first sample
     for _ in range(args.warmup):
         step()
     E.reset_stats()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     E.mark_begin()
     for _ in range(args.steps):
         step()
     ms = E.mark_end()
     barrier()
-    clocks = sampler.stop() if sampler else {}
     st = E.stats()
     launches = st["launches"]
     if world > 1:
@@ -268,6 +267,7 @@ def main():
                "h2d_bytes_per_step": B * 4 * len(S_in) * ROW_BYTES, "d2h_bytes_per_step": B * 2 * len(S) * ROW_BYTES,
                "ms_per_step": ems / args.steps}
 
+    clocks = sampler.stop() if sampler else {}   # sampled from warm-up through the timed region and the e2e loop
     # ---- per-kernel profile (one extra step bracketed by events per launch) -> roofline
     peak, peak_kind = peaks()
     E.profile(True)

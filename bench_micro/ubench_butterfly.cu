@@ -18,8 +18,10 @@ __global__ void __launch_bounds__(256) kb(u64* out, u64 q, u64 nq, u64 q3, u64 s
 #pragma unroll
   for (int i = 0; i < 15; i++) { u64 w = (seed * (i + 3) + 12345) % q; tw.t[i] = make_ulonglong2(w, (u64)(((unsigned __int128)w << 64) / q)); }
   for (int r = 0; r < rounds; r++) {
-    if (MODE == 0) hb1_r16_fwd(a, tw, nq, q3);
-    else if (MODE == 1) hb1_r16_inv(a, tw, nq, q3);
+    Hb1Mod M; M.nq = nq; M.q3 = q3; M.qt = (unsigned)((q - 1) >> 52); M.qsh = 20;   // q = 237*2^52 + 1
+    if (MODE == 0) hb1_r16_fwd<false>(a, tw, M);
+    else if (MODE == 1) hb1_r16_inv<false>(a, tw, M);
+    else if (MODE == 3) hb1_r16_fwd<true>(a, tw, M);
     else {
 #pragma unroll
       for (int k = 0; k < 4; k++) { const int d = 8 >> k;
@@ -57,19 +59,20 @@ int main() {
   u64* out; cudaMalloc(&out, 148 * 16 * 256 * 8);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int rounds = 2000;
-  for (int mode = 0; mode < 3; mode++)
-    for (int bps : {1, 2, 4, 8}) {
+  for (int mode = 0; mode < 4; mode++)
+    for (int bps : {2, 8}) {
       int blocks = 148 * bps;
       for (int rep = 0; rep < 2; rep++) {
         cudaEventRecord(e0);
         if (mode == 0) kb<0><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
         if (mode == 1) kb<1><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
         if (mode == 2) kb<2><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
+        if (mode == 3) kb<3><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
       }
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       double bf = (double)blocks * 256 * rounds * 32;
-      printf("mode %d (%s) blocks/SM %d: %.3f ms  %.3e butterflies/s\n", mode, mode == 0 ? "ct approx" : mode == 1 ? "gs approx" : "ct exact", bps, ms, bf / (ms * 1e-3));
+      printf("mode %d (%s) blocks/SM %d: %.3f ms  %.3e butterflies/s\n", mode, mode == 0 ? "ct approx" : mode == 1 ? "gs approx" : mode == 2 ? "ct exact" : "ct approx, q=t*2^s+1 shift form", bps, ms, bf / (ms * 1e-3));
     }
   for (int bps : {2, 8}) {
     int blocks = 148 * bps;

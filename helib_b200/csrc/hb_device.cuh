@@ -31,7 +31,9 @@ typedef unsigned long long u64;
 typedef long long i64;
 
 #define HB_MAXROWS 64   // rows per launch (larger sets are chunked by the host)
-#define HB_MAXB 16      // batch items per launch
+#ifndef HB_MAXB
+#define HB_MAXB 32      // batch items per launch
+#endif
 #define HB_MAXDIG 8     // digits per key-switching matrix
 #define HB_THREADS 256
 
@@ -43,6 +45,8 @@ struct HbPrimeDev {
   u64 c64, c64_s;          // 2^64 mod q (+ Shoup)
   u64 one_s;               // floor(2^64 / q)
   u64 nq, q3;              // 2^64 - q and 3q, kept as opaque table values so ptxas does not re-derive them from q
+  unsigned qt, qsh;        // HElib primes are q = qt*2^s + 1 with s >= 32 (PrimeGenerator picks k maximal,
+                           // src/PrimeGenerator.h:54-124): qsh = s-32, qt = (q-1)>>s.  qt = 0 if s < 32 or qt >= 2^32.
   const ulonglong2* fw;    // fw[k] = (psi^brev(k), shoup), k = 1..N-1   (Cooley-Tukey, merged twist)
   const ulonglong2* iw;    // iw[k] = (psi^-brev(k), shoup)              (Gentleman-Sande)
 };

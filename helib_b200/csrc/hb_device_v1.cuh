@@ -51,10 +51,23 @@ __device__ __forceinline__ u64 hb1_mulhi_approx(u64 a, u64 b) {
   const u64 p3 = (u64)ahi * bhi + (p1 >> 32);
   return p3 + (p2 >> 32);
 }
+// Modulus view of the butterfly network.  Generic: nq = 2^64 - q (the subtraction of hi*q is folded into
+// the multiply-add chain).  Special (HElib's q = qt*2^s + 1, s >= 32): hi*q mod 2^64 = hi + ((lo32(hi)*qt) << s),
+// one 32-bit IMAD and a shift instead of a 64-bit multiply -- the FMA-heavy pipe is the bottleneck of these kernels.
+struct Hb1Mod {
+  u64 nq, q3;
+  unsigned qt, qsh;
+};
 // y*w mod q up to a multiple of q: result in [0,3q) for ANY 64-bit y (Shoup quotient off by <= 2).
-// nq = 2^64 - q, so the subtraction is folded into the multiply-add chain.
-__device__ __forceinline__ u64 hb1_shoup3(u64 y, u64 w, u64 ws, u64 nq) {
-  return y * w + hb1_mulhi_approx(y, ws) * nq;
+template <bool SP>
+__device__ __forceinline__ u64 hb1_shoup3(u64 y, u64 w, u64 ws, const Hb1Mod& M) {
+  const u64 hi = hb1_mulhi_approx(y, ws);
+  if (SP) {
+    const unsigned tl = (unsigned)hi * M.qt;
+    const u64 hq = hi + ((u64)(tl << M.qsh) << 32);
+    return y * w - hq;
+  }
+  return y * w + hi * M.nq;
 }
 // x in [0,2m) -> [0,m) by one conditional subtraction decided on the sign of x-m (both < 2^63)
 __device__ __forceinline__ u64 hb1_csub(u64 x, u64 m) {
@@ -62,18 +75,20 @@ __device__ __forceinline__ u64 hb1_csub(u64 x, u64 m) {
   return (i64)d < 0 ? x : d;
 }
 // Cooley-Tukey butterfly, x,y in [0,6q) -> [0,6q)
-__device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, u64 nq, u64 q3) {
-  const u64 xr = hb1_csub(x, q3);
-  const u64 t = hb1_shoup3(y, w, ws, nq);
+template <bool SP>
+__device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, const Hb1Mod& M) {
+  const u64 xr = hb1_csub(x, M.q3);
+  const u64 t = hb1_shoup3<SP>(y, w, ws, M);
   x = xr + t;
-  y = xr - t + q3;
+  y = xr - t + M.q3;
 }
 // Gentleman-Sande butterfly, x,y in [0,3q) -> [0,3q)
-__device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, u64 nq, u64 q3) {
+template <bool SP>
+__device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, const Hb1Mod& M) {
   const u64 s = x + y;
-  const u64 d = x - y + q3;
-  x = hb1_csub(s, q3);
-  y = hb1_shoup3(d, w, ws, nq);
+  const u64 d = x - y + M.q3;
+  x = hb1_csub(s, M.q3);
+  y = hb1_shoup3<SP>(d, w, ws, M);
 }
 __device__ __forceinline__ u64 hb1_canon3(u64 x, u64 q) {  // [0,3q) -> [0,q)
   x = hb1_csub(x, q + q);
@@ -93,8 +108,8 @@ struct Hb1TwPtr {
   const ulonglong2* p[4];
   __device__ __forceinline__ ulonglong2 get(int k, int g) const { return p[k][g]; }
 };
-template <class TW>
-__device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 nq, u64 q3) {
+template <bool SP, class TW>
+__device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, const Hb1Mod& M) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int d = 8 >> k;
@@ -102,12 +117,12 @@ __device__ __forceinline__ void hb1_r16_fwd(u64 (&a)[16], const TW& tw, u64 nq, 
     for (int g = 0; g < (1 << k); g++) {
       const ulonglong2 w = tw.get(k, g);
 #pragma unroll
-      for (int o = 0; o < d; o++) hb1_ct(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, nq, q3);
+      for (int o = 0; o < d; o++) hb1_ct<SP>(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, M);
     }
   }
 }
-template <class TW>
-__device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 nq, u64 q3) {
+template <bool SP, class TW>
+__device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, const Hb1Mod& M) {
 #pragma unroll
   for (int k = 3; k >= 0; k--) {
     const int d = 8 >> k;
@@ -115,7 +130,7 @@ __device__ __forceinline__ void hb1_r16_inv(u64 (&a)[16], const TW& tw, u64 nq, 
     for (int g = 0; g < (1 << k); g++) {
       const ulonglong2 w = tw.get(k, g);
 #pragma unroll
-      for (int o = 0; o < d; o++) hb1_gs(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, nq, q3);
+      for (int o = 0; o < d; o++) hb1_gs<SP>(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, M);
     }
   }
 }
@@ -173,6 +188,7 @@ __device__ __forceinline__ Hb1Unit hb1_unit(long u, int G, int nitems) {
 // mod-down epilogue, the 16 old destination values of the CURRENT unit) into shared memory with
 // cp.async while it computes; the staging tile doubles as the exchange tile.
 // smem: S[2][HB1_STAGE] | O[16][256] | TW1[256]
+template <bool SP>
 __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
   u64* S = HB_SMEM;
@@ -205,13 +221,14 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
   }
   hb1_cp_commit();
   int key = -1, buf = 0;
-  u64 q = 0, nq = 0, q3 = 0, sc = 0, sc_s = 0;
+  u64 q = 0, sc = 0, sc_s = 0;
+  Hb1Mod M; M.nq = 0; M.q3 = 0; M.qt = 0; M.qsh = 0;
   Hb1TwReg tw2;
   for (long u = ubeg; u < uend; u++, buf ^= 1) {
     if (cur.rowi * G + cur.ug != key) {   // new (row, block group): reload modulus and twiddles
       key = cur.rowi * G + cur.ug;
       const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
-      q = P.q; nq = P.nq; q3 = P.q3;
+      q = P.q; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
       sc = J.scal[cur.rowi]; sc_s = J.scal_s[cur.rowi];
       const unsigned b1 = hb_brev((cur.ug << 4) + blk1, n1), b2 = hb_brev((cur.ug << 4) + blk2, n1);
       if (lo < 15) {  // entry e = (1<<k)-1+g of block blk1
@@ -246,19 +263,20 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
     u64 a[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = Sb[own + HB1_RS * r];
-    hb1_r16_fwd(a, tw1, nq, q3);
+    hb1_r16_fwd<SP>(a, tw1, M);
 #pragma unroll
     for (int r = 0; r < 16; r++) Sb[own + HB1_RS * r] = a[r];
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = Sb[blk2 * HB1_BS + HB1_RS * hi + l];
-    hb1_r16_fwd(a, tw2, nq, q3);
+    hb1_r16_fwd<SP>(a, tw2, M);
     hb1_cp_wait<1>();   // old destination values (epilogue) have landed
 #pragma unroll
     for (int l = 0; l < 16; l++) {
-      u64 v = hb1_canon6(a[l], q);
       const size_t o = (size_t)((hb1_brev4(l) << 4) | hrev) << n1;   // brev8(16*hi + l) * N1
-      if (epi) v = hb_mul_shoup(hb_submod(O[l * 256 + tid], v, q), sc, sc_s, q);
+      u64 v;
+      if (epi) v = hb1_canon3(hb1_shoup3<SP>(O[l * 256 + tid] - a[l] + 2 * M.q3, sc, sc_s, M), q);   // (old - x) * P^-1, x in [0,6q)
+      else v = hb1_canon6(a[l], q);
       dst[o] = v;
     }
     __syncthreads();   // exchange reads of Sb / TW1 done before they are overwritten
@@ -269,6 +287,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
 
 // Inverse "blk" phase (bit-reversal + first 8 GS stages), same decomposition and pipelining.
 // smem: S[2][HB1_STAGE] | TW1[256]
+template <bool SP>
 __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restrict__ primes, Hb1BlkJob J) {
   HB_SMEM_DECL
   u64* S = HB_SMEM;
@@ -296,14 +315,15 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
   }
   hb1_cp_commit();
   int key = -1, buf = 0;
-  u64 q = 0, nq = 0, q3 = 0;
+  u64 q = 0;
+  Hb1Mod M; M.nq = 0; M.q3 = 0; M.qt = 0; M.qsh = 0;
   unsigned b1 = 0;
   Hb1TwReg tw2;
   for (long u = ubeg; u < uend; u++, buf ^= 1) {
     if (cur.rowi * G + cur.ug != key) {
       key = cur.rowi * G + cur.ug;
       const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
-      q = P.q; nq = P.nq; q3 = P.q3;
+      q = P.q; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
       b1 = hb_brev((cur.ug << 4) + blk1, n1);
       const unsigned b2 = hb_brev((cur.ug << 4) + blk2, n1);
       if (lo < 15) {
@@ -332,13 +352,13 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
     u64 a[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = Sb[own + l];
-    hb1_r16_inv(a, tw2, nq, q3);
+    hb1_r16_inv<SP>(a, tw2, M);
 #pragma unroll
     for (int l = 0; l < 16; l++) Sb[own + l] = a[l];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = Sb[blk1 * HB1_BS + HB1_RS * r + lo];
-    hb1_r16_inv(a, tw1, nq, q3);
+    hb1_r16_inv<SP>(a, tw1, M);
     u64* dst = J.dst[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN) + ((size_t)b1 << 8) + lo;
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon3(a[r], q);
@@ -357,13 +377,14 @@ struct Hb1ColsJob {
 };
 
 // "cols" phases for n1 = 8 (N = 2^16): tile [256][16 columns].  grid = (16, nrows, item-groups).
+template <bool SP>
 __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restrict__ primes, Hb1ColsJob J) {
   HB_SMEM_DECL
   u64* T = HB_SMEM;
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, nq = P.nq, q3 = P.q3;
+  const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = lo in pass 1 (on r), hi in pass 2 (on lo)
@@ -380,25 +401,26 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
     u64 a[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = src[(size_t)(16 * r + x) << 8];
-    hb1_r16_fwd(a, tw1, nq, q3);
+    hb1_r16_fwd<SP>(a, tw1, M);
 #pragma unroll
     for (int r = 0; r < 16; r++) T[c * HB1_BS + HB1_RS * r + x] = a[r];
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = T[c * HB1_BS + HB1_RS * x + l];
-    hb1_r16_fwd(a, tw2, nq, q3);
+    hb1_r16_fwd<SP>(a, tw2, M);
 #pragma unroll
     for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = hb1_canon6(a[l], q);
     __syncthreads();
   }
 }
+template <bool SP>
 __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restrict__ primes, Hb1ColsJob J) {
   HB_SMEM_DECL
   u64* T = HB_SMEM;
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q, nq = P.nq, q3 = P.q3;
+  const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = hi in pass 1 (on lo), lo in pass 2 (on r)
@@ -415,13 +437,13 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
     u64 a[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = src[(size_t)(16 * x + l) << 8];
-    hb1_r16_inv(a, tw2, nq, q3);
+    hb1_r16_inv<SP>(a, tw2, M);
 #pragma unroll
     for (int l = 0; l < 16; l++) T[c * HB1_BS + HB1_RS * x + l] = a[l];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = T[c * HB1_BS + HB1_RS * r + x];
-    hb1_r16_inv(a, tw1, nq, q3);
+    hb1_r16_inv<SP>(a, tw1, M);
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[(size_t)(16 * r + x) << 8] = hb_mul_shoup(a[r], P.ninv, P.ninv_s, q);
     __syncthreads();
@@ -445,6 +467,7 @@ struct Hb1ConvJob {
   double* frac[HB_MAXB];   // optional x/Q per coefficient for the embedding norm
 };
 
+template <bool SP>
 __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__ primes, Hb1ConvJob J) {
   HB_SMEM_DECL
   const HbConvDev* cv = J.cv;
@@ -463,7 +486,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int j = grp; j < n; j += NG) {
     const int pi = cv->src_prime[j];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q, nq = P.nq, q3 = P.q3;
+    const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
     const u64* s = src + ((size_t)pi << J.logN) + c0 + c;
     u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS;
     u64 a[16];
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.iw + 16 + x; tw.p[1] = P.iw + 32 + 2 * x; tw.p[2] = P.iw + 64 + 4 * x; tw.p[3] = P.iw + 128 + 8 * x;
-      hb1_r16_inv(a, tw, nq, q3);
+      hb1_r16_inv<SP>(a, tw, M);
     }
 #pragma unroll
     for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
@@ -487,7 +510,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.iw + 1; tw.p[1] = P.iw + 2; tw.p[2] = P.iw + 4; tw.p[3] = P.iw + 8;
-      hb1_r16_inv(a, tw, nq, q3);
+      hb1_r16_inv<SP>(a, tw, M);
     }
     const u64 t = cv->tn[j], ts = cv->tn_s[j];
 #pragma unroll
@@ -508,7 +531,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int t = grp; t < nt; t += NG) {
     const int pi = cv->tgt_prime[t];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q, nq = P.nq, q3 = P.q3;
+    const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
     const u64* ct = cv->c + (size_t)t * n;
     u64 a[16];
     {
@@ -536,7 +559,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;
-      hb1_r16_fwd(a, tw, nq, q3);
+      hb1_r16_fwd<SP>(a, tw, M);
     }
     hb_group_sync(grp, 64);   // previous target's pass-2 reads of Wg are complete
 #pragma unroll
@@ -547,7 +570,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     {
       Hb1TwPtr tw;
       tw.p[0] = P.fw + 16 + x; tw.p[1] = P.fw + 32 + 2 * x; tw.p[2] = P.fw + 64 + 4 * x; tw.p[3] = P.fw + 128 + 8 * x;
-      hb1_r16_fwd(a, tw, nq, q3);
+      hb1_r16_fwd<SP>(a, tw, M);
     }
     u64* d = dst + ((size_t)pi << J.logN) + c0 + c;
 #pragma unroll

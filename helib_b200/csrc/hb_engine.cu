@@ -24,7 +24,7 @@ typedef unsigned __int128 u128;
 // ------------------------------------------------------------------------------------------
 // errors
 static thread_local char g_err[512] = "";
-static thread_local int g_chunk = 16;   // batch items per launch for the current call (hb_ctx::chunk)
+static thread_local int g_chunk = HB_MAXB;   // batch items per launch for the current call (hb_ctx::chunk)
 static int hb_fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
   return code;
@@ -204,6 +204,8 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
       memset(&P, 0, sizeof(P));
       P.q = qi; P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi); P.one_s = (u64)(((u128)1 << 64) / qi);
       P.nq = 0 - qi; P.q3 = 3 * qi;
+      { int sh = 0; u64 t = qi - 1; while ((t & 1) == 0) { t >>= 1; sh++; }
+        if (sh >= 32 && t < (1ULL << 32)) { P.qt = (unsigned)t; P.qsh = (unsigned)(sh - 32); } }
     }
     HB_TRY(ctx_alloc(c, (void**)&c->d_primes, sizeof(HbPrimeDev) * nprimes));
     HB_CUDA(cudaMemcpy(c->d_primes, c->h_primes.data(), sizeof(HbPrimeDev) * nprimes, cudaMemcpyHostToDevice));
@@ -212,8 +214,10 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
 #ifndef HB_SIM
     HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 #endif
     int r = gen_init(c, psi);
     if (r != HB_OK) return r;
@@ -242,6 +246,8 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi);
     P.one_s = (u64)(((u128)1 << 64) / qi);
     P.nq = 0 - qi; P.q3 = 3 * qi;
+    { int sh = 0; u64 t = qi - 1; while ((t & 1) == 0) { t >>= 1; sh++; }
+      if (sh >= 32 && t < (1ULL << 32)) { P.qt = (unsigned)t; P.qsh = (unsigned)(sh - 32); } else { P.qt = 0; P.qsh = 0; } }
     P.fw = c->d_tw + ((size_t)i * 2 + 0) * N;
     P.iw = c->d_tw + ((size_t)i * 2 + 1) * N;
   }
@@ -254,9 +260,12 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem + 1024));
   HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  HB_CUDA(cudaFuncSetAttribute(k1_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 #endif
   *out = c;
   return HB_OK;
@@ -441,6 +450,7 @@ static void fill_rows(HbRows& r, const int32_t* idx, int n) { r.n = n; for (int 
 static int logwb_of(hb_ctx* c) { int n1 = c->logN - c->log_blk; return std::min(n1, 10 - c->log_blk); }
 static int logw_cols(hb_ctx* c) { int n1 = c->logN - c->log_blk; int lw = 10 - n1; if (lw < 0) lw = 0; return std::min(lw, c->log_blk); }
 
+static bool all_special(hb_ctx* c) { for (auto& P : c->h_primes) if (P.qt == 0) return false; return !getenv("HB_NO_SPECIAL"); }
 static bool v1_blk_ok(hb_ctx* c) { return !c->force_v0 && c->log_blk == 8 && c->logN - 8 >= 4; }
 static bool v1_cols_ok(hb_ctx* c) { return !c->force_v0 && c->log_blk == 8 && c->logN - 8 == 8; }
 // number of item groups (gridDim.z): each CTA loops over ceil(nitems/z) items re-using its twiddles;
@@ -471,8 +481,9 @@ static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* 
     long units = (long)nr * nitems << (n1 - 4);
     dim3 grid((unsigned)std::min<long>(units, c->resident_ctas));   // persistent CTAs, balanced contiguous chunks
     pre_launch(c);
-    if (dir > 0) { HB_LAUNCH(k1_fwd_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k1_fwd_blk_subscale" : "k1_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
-    else { HB_LAUNCH(k1_inv_blk, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
+    const bool sp = all_special(c);
+    if (dir > 0) { if (sp) HB_LAUNCH(k1_fwd_blk<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_fwd_blk<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k1_fwd_blk_subscale" : "k1_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
+    else { if (sp) HB_LAUNCH(k1_inv_blk<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_inv_blk<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
 }
@@ -487,8 +498,9 @@ static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const*
     for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
     dim3 grid(16, nr, pick_item_groups(c, 16L * nr, nitems));
     pre_launch(c);
-    if (dir > 0) { HB_LAUNCH(k1_fwd_cols, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_fwd_cols", (u64)2 * nr * nitems * c->N * 8)); }
-    else { HB_LAUNCH(k1_inv_cols, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_cols", (u64)2 * nr * nitems * c->N * 8)); }
+    const bool sp = all_special(c);
+    if (dir > 0) { if (sp) HB_LAUNCH(k1_fwd_cols<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_fwd_cols<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_fwd_cols", (u64)2 * nr * nitems * c->N * 8)); }
+    else { if (sp) HB_LAUNCH(k1_inv_cols<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_inv_cols<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_cols", (u64)2 * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
 }
@@ -721,7 +733,8 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
       if (want_frac) for (int i = 0; i < nit; i++) J1.frac[i] = c->d_frac + (size_t)i * c->N;
       for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
       pre_launch(c);
-      HB_LAUNCH(k1_conv, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+      if (all_special(c)) HB_LAUNCH(k1_conv<true>, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+      else HB_LAUNCH(k1_conv<false>, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
       return post_launch(c, "k1_conv", (u64)(n + nt) * nit * c->N * 8);
     }
   }

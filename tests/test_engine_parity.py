@@ -252,3 +252,10 @@ def test_sim_full_ring_dimension_small_chain(sim_lib):
     E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, 257, EA, EB)
     r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, 257, evk_a, evk_b)
     assert rows_equal(A0[0].download(S), r0, S) and rows_equal(A1[0].download(S), r1, S)
+
+
+def test_sim_generic_modulus_path(sim_lib, monkeypatch):
+    """The register kernels have two modulus views: HElib's q = t*2^s+1 (s >= 32) shift form and the
+    generic 2^64-q form.  Force the generic one (HB_NO_SPECIAL) on the N = 2^16 circuit."""
+    monkeypatch.setenv("HB_NO_SPECIAL", "1")
+    test_sim_full_ring_dimension_small_chain(sim_lib)
