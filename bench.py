@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=6, help="multiplies timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="engine contexts (CUDA streams) the e2e loop spreads the batch over")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -248,16 +249,48 @@ def main():
         ms = float(t.item())
     value = world * B * args.steps / (ms / 1000.0)
 
-    # ---- e2e: host buffers -> H2D -> hot path -> D2H, every step
+    # ---- e2e: host buffers -> H2D -> hot path -> D2H, every step.  Two engine contexts (two CUDA
+    #      streams), each with half of the batch, so the PCIe copies of one half overlap the kernels of
+    #      the other -- the way a caller keeps the link busy; same pinned host buffers, same results.
     e2e = None
     if not args.no_e2e:
+        ns = max(1, min(args.e2e_streams, B))
+        engines = [E] + [Engine(w["m"], ch.primes, None, ch.digits, ch.special, device=local) for _ in range(ns - 1)]
+        halves = [(engines[k], list(range(k * B // ns, (k + 1) * B // ns))) for k in range(ns)]
+        ctxs = []
+        for eng, items in halves:
+            if eng is E:
+                ea, eb, pl = EA, EB, [polys[b] for b in items]
+            else:
+                ea = [eng.poly() for _ in range(nd)]
+                eb = [eng.poly() for _ in range(nd)]
+                tmp = np.zeros((npr, N), dtype=np.uint64)
+                for src, dst in list(zip(EA, ea)) + list(zip(EB, eb)):
+                    src.download(full, tmp)
+                    dst.upload(tmp, full)
+                pl = [[eng.poly() for _ in range(4)] for _ in items]
+            ctxs.append((eng, items, ea, eb, pl))
+
+        def e2e_step():
+            for eng, items, ea, eb, pl in ctxs:
+                for j, b in enumerate(items):
+                    for k in range(4):
+                        pl[j][k].upload_ptr(host_in[b, k].data_ptr(), S_in)
+                eng.mul_relin_moddown([p_[0] for p_ in pl], [p_[1] for p_ in pl], [p_[2] for p_ in pl], [p_[3] for p_ in pl], S_in, S, 1, ea, eb)
+                for j, b in enumerate(items):
+                    for k in range(2):
+                        pl[j][k].download_async_ptr(host_out[b, k].data_ptr(), S)
+
         for _ in range(2):
-            upload_all(); step(); download_all()
+            e2e_step()
         barrier()
-        E.mark_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         for _ in range(args.steps):
-            upload_all(); step(); download_all()
-        ems = E.mark_end()
+            e2e_step()
+        for eng, *_ in ctxs:
+            eng.sync()
+        ems = (time.perf_counter() - t0) * 1000.0   # host clock around fully synchronised work on both streams
         barrier()
         if world > 1:
             t = torch.tensor([ems], device="cuda", dtype=torch.float64)
@@ -265,7 +298,7 @@ def main():
             ems = float(t.item())
         e2e = {"value": world * B * args.steps / (ems / 1000.0), "unit": "mult/s",
                "h2d_bytes_per_step": B * 4 * len(S_in) * ROW_BYTES, "d2h_bytes_per_step": B * 2 * len(S) * ROW_BYTES,
-               "ms_per_step": ems / args.steps}
+               "ms_per_step": ems / args.steps, "streams": len(ctxs), "timing": "host perf_counter around synchronised streams"}
 
     clocks = sampler.stop() if sampler else {}   # sampled from warm-up through the timed region and the e2e loop
     # ---- per-kernel profile (one extra step bracketed by events per launch) -> roofline
@@ -276,11 +309,19 @@ def main():
     prof = sorted(E.profile_results(), key=lambda r: -r["ms"])
     tot_ms = sum(r["ms"] for r in prof) or 1.0
     roof = None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        tj = {}
     if prof:
         top = prof[0]
+        base = top["kernel"].replace("_subscale", "")
+        if base in tj:
+            traffic = tj[base].get("avg_dram_bytes_per_launch_at_batch8")
         ach = top["bytes"] / (top["ms"] / 1000.0) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_kind": peak_kind, "traffic": None, "share_of_step": top["ms"] / tot_ms,
+                "peak_kind": peak_kind, "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of run r01f)" if traffic else None, "share_of_step": top["ms"] / tot_ms,
                 "launches_per_step": top["launches"], "avg_launch_ms": top["ms"] / top["launches"],
                 "alg_bytes_per_launch": top["bytes"] / top["launches"]}
     kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot_ms, 4),
