@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "gather"], help="sharded mode: peer stores from the producing kernel, or pack/all_gather/unpack")
+    ap.add_argument("--profile", action="store_true", help="add a per-kernel table (CUDA events per launch, one eager step)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -58,7 +60,7 @@ def main():
     full = ch.ctxt + ch.special
     nd = len(ch.digits)
     sharded = args.mode == "sharded"
-    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, rank=rank if sharded else 0, world=world if sharded else 1, device=f"cuda:{local}")
+    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, rank=rank if sharded else 0, world=world if sharded else 1, device=f"cuda:{local}", p2p=(args.exchange == "p2p"))
     rng = np.random.Generator(np.random.Philox(20260922 + (4 if sharded else 3) + (0 if sharded else 1000 * rank)))
 
     def rand_rows(idx):
@@ -120,6 +122,14 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    kernels = None
+    if args.profile:
+        E.profile(True)
+        step()
+        E.profile(False)
+        prof = sorted(E.profile_results(), key=lambda r: -r["ms"])
+        kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4)} for r in prof]
+        kernels.append({"kernel": "sum_of_engine_kernels", "launches": sum(r["launches"] for r in prof), "ms": round(sum(r["ms"] for r in prof), 4)})
     total = (B if sharded else B * world) * args.steps
     if rank == 0:
         l, K, d = len(S), len(ch.special), nd
@@ -134,11 +144,11 @@ def main():
             "metric": "key_switches_per_s", "value": v, "unit": "keyswitch/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u64 (RNS limbs < 2^60)", "data": "synthetic",
-            "config": {"workload": wl["name"], "mode": args.mode, "N": N, "l": l, "K": K, "digits": d, "batch": B, "ptxt_space": p,
+            "config": {"workload": wl["name"], "mode": args.mode, "exchange": (args.exchange if (sharded and world > 1) else None), "N": N, "l": l, "K": K, "digits": d, "batch": B, "ptxt_space": p,
                        "collectives_per_keyswitch": (d + 1) if (sharded and world > 1) else 0,
                        "all_gather_bytes_per_keyswitch": (l + 2 * K) * ROW if (sharded and world > 1) else 0, "alg_bytes_per_keyswitch": bks},
             "alg_roofline": {"achieved_GBps": v * bks / 1e9, "peak_GBps": peak * world, "frac": v * bks / 1e9 / (peak * world)},
-            "gpu_launches": launches, "cuda_graph": graphed,
+            "gpu_launches": launches, "cuda_graph": graphed, "kernels": kernels,
         }))
     # Leave without tearing NCCL down: destroy_process_group() after a captured graph that contains
     # collectives can block for minutes; the results are already printed.

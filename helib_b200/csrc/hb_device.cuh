@@ -698,3 +698,31 @@ __global__ void __launch_bounds__(HB_THREADS) k_norm_stage(HbNormJob J, int logd
 #endif
   }
 }
+
+
+// Scale rows by per-row constants and write the result to the local destination AND to the same rows of
+// up to 8 peer GPUs' buffers (peer device memory mapped through CUDA IPC, stores travel over NVLink).
+// This is the tail of the prime-sharded conversion's "make y" step fused with its all-gather: the y rows
+// cross the fabric exactly once, straight into place (no pack / collective / unpack passes).
+#define HB_MAXPEERS 8
+struct HbBcastJob {
+  u64 N;
+  HbRows rows;
+  u64 scal[HB_MAXROWS], scal_s[HB_MAXROWS];
+  int nitems, npeers;
+  u64* loc[HB_MAXB];                   // in/out, local
+  u64* peer[HB_MAXPEERS][HB_MAXB];     // out, remote
+};
+__global__ void __launch_bounds__(HB_THREADS) k_scale_bcast(const HbPrimeDev* __restrict__ primes, const HbBcastJob* __restrict__ Jp) {
+  const HbBcastJob& J = *Jp;
+  const int pi = J.rows.prime[blockIdx.y];
+  const u64 q = primes[pi].q;
+  const size_t N = (size_t)J.N, off = (size_t)pi * N;
+  const int it = blockIdx.z;
+  const u64 sc = J.scal[blockIdx.y], sc_s = J.scal_s[blockIdx.y];
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+    const u64 v = hb_mul_shoup(J.loc[it][off + k], sc, sc_s, q);
+    J.loc[it][off + k] = v;
+    for (int p = 0; p < J.npeers; p++) J.peer[p][it][off + k] = v;
+  }
+}

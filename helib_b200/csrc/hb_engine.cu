@@ -70,6 +70,7 @@ struct hb_ctx {
   u64* tmpA; u64* tmpB;
   double* d_frac; void* d_z; unsigned long long* d_max;   // embedding-norm scratch (allocated on first use)
   u64* d_stats;
+  HbBcastJob* d_bcast = nullptr;   // job descriptor of k_scale_bcast (too large for kernel parameters)
   std::map<std::string, ConvEntry> convs;
   std::vector<hb_poly*> pool;
   size_t bytes; u64 launches;
@@ -96,7 +97,7 @@ struct hb_ctx {
   struct ProfAgg { std::string name; u64 launches; double ms; u64 bytes; };
   std::vector<ProfAgg> prof;
 };
-struct hb_poly { hb_ctx* ctx; u64* d; bool owned = true; };
+struct hb_poly { hb_ctx* ctx; u64* d; bool owned = true; bool ipc = false; };
 
 static int ctx_alloc(hb_ctx* c, void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
@@ -276,7 +277,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
-  cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max);
+  cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max); cudaFree(c->d_bcast);
   cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
@@ -354,6 +355,9 @@ extern "C" void hb_poly_destroy(hb_poly* p) {
   if (!p) return;
   cudaStreamSynchronize(p->ctx->stream);
   if (p->owned) { p->ctx->bytes -= (size_t)p->ctx->nprimes * p->ctx->N * sizeof(u64); cudaFree(p->d); }
+#ifndef HB_SIM
+  if (p->ipc) cudaIpcCloseMemHandle(p->d);
+#endif
   delete p;
 }
 static int check_idx(hb_ctx* c, const int32_t* idx, int n, const char* who, bool allow_empty = false) {
@@ -1171,6 +1175,66 @@ extern "C" int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* 
     return launch_cols(c, -1, (const u64* const*)tA, Y, nit, owned, nOwned);
   }));
   return pw_simple(HB_PW_SCALE, ypolys, nullptr, nitems, owned, nOwned, sc.data(), c);
+}
+// hb_conv_make_y whose last step also stores the y rows into the peers' y buffers (CUDA IPC mappings)
+extern "C" int hb_conv_make_y_bcast(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned,
+                                    hb_poly* const* ypolys, hb_poly* const* peer_ypolys, int npeers) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_conv_make_y_bcast")); HB_TRY(check_polys(ypolys, nitems, &c, "hb_conv_make_y_bcast"));
+  HB_TRY(check_idx(c, D, nD, "hb_conv_make_y_bcast")); HB_TRY(check_idx(c, owned, nOwned, "hb_conv_make_y_bcast(owned)", true));
+  if (c->gen.on) return hb_fail(HB_ERR_UNSUPPORTED, "prime-sharded conversion is only built for power-of-two m");
+  if (npeers < 0 || npeers > HB_MAXPEERS || (npeers && !peer_ypolys)) return hb_fail(HB_ERR_BAD_ARG, "hb_conv_make_y_bcast: npeers out of range");
+  if (nOwned == 0) return HB_OK;
+  if (nOwned > HB_MAXROWS) return hb_fail(HB_ERR_UNSUPPORTED, "hb_conv_make_y_bcast: more than %d owned rows", HB_MAXROWS);
+  std::vector<u64> sc(nOwned);
+  for (int k = 0; k < nOwned; k++) {
+    if (std::find(D, D + nD, owned[k]) == D + nD) return hb_fail(HB_ERR_INDEX_SET, "hb_conv_make_y_bcast: owned prime %d is not in the source set", owned[k]);
+    u64 q = c->q[owned[k]], r = 1 % q;
+    for (int j = 0; j < nD; j++) if (D[j] != owned[k]) r = h_mulmod(r, c->q[D[j]] % q, q);
+    sc[k] = h_powmod(r, q - 2, q);
+  }
+  HB_TRY(ctx_scratch(c));
+  if (!c->d_bcast) HB_TRY(ctx_alloc(c, (void**)&c->d_bcast, sizeof(HbBcastJob)));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
+    HB_TRY(launch_cols(c, -1, (const u64* const*)tA, Y, nit, owned, nOwned));
+    HbBcastJob J; memset(&J, 0, sizeof(J));
+    J.N = c->N; J.nitems = nit; J.npeers = npeers;
+    fill_rows(J.rows, owned, nOwned);
+    for (int k = 0; k < nOwned; k++) { J.scal[k] = sc[k]; J.scal_s[k] = h_shoup(sc[k], c->q[owned[k]]); }
+    for (int i = 0; i < nit; i++) { J.loc[i] = Y[i]; for (int p = 0; p < npeers; p++) J.peer[p][i] = peer_ypolys[(size_t)p * nitems + i0 + i]->d; }
+    HB_CUDA(cudaMemcpyAsync(c->d_bcast, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
+    unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
+    pre_launch(c);
+    HB_LAUNCH(k_scale_bcast, dim3(gx, nOwned, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, (const HbBcastJob*)c->d_bcast);
+    return post_launch(c, "k_scale_bcast", (u64)(2 + npeers) * nOwned * nit * c->N * 8);
+  });
+}
+// CUDA IPC: export a polynomial's device buffer / map a peer's buffer (one process per GPU)
+extern "C" int hb_poly_ipc_export(hb_poly* p, void* handle64) {
+  if (!p || !handle64) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_ipc_export: null");
+#ifdef HB_SIM
+  return hb_fail(HB_ERR_UNSUPPORTED, "CUDA IPC is not available in the simulator");
+#else
+  cudaIpcMemHandle_t h;
+  HB_CUDA(cudaIpcGetMemHandle(&h, p->d));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return HB_OK;
+#endif
+}
+extern "C" int hb_poly_ipc_open(hb_ctx* c, const void* handle64, hb_poly** out) {
+  if (!c || !handle64 || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_ipc_open: null");
+#ifdef HB_SIM
+  return hb_fail(HB_ERR_UNSUPPORTED, "CUDA IPC is not available in the simulator");
+#else
+  cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+  void* ptr = nullptr;
+  HB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  hb_poly* p = new hb_poly(); p->ctx = c; p->d = (u64*)ptr; p->owned = false; p->ipc = true;
+  *out = p;
+  return HB_OK;
+#endif
 }
 // mode 0: dst rows tgt = x mod q_t (addPrimes);  mode 1: dst rows tgt = (dst - x)/Q_D (scaleDownToSet)
 extern "C" int hb_conv_from_y(hb_poly* const* ypolys, int nitems, const int32_t* D, int nD, const int32_t* tgt, int nT,

@@ -389,3 +389,31 @@ def _engine_norms(cls):
 
 
 _engine_norms(Engine)
+
+
+def _engine_p2p(cls):
+    def ipc_export(self, poly) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.hb_poly_ipc_export(poly.h, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes):
+        p = Poly.__new__(Poly)
+        p.eng = self
+        p.h = C.c_void_p()
+        self._ck(self.lib.hb_poly_ipc_open(self.h, C.c_char_p(handle), C.byref(p.h)))
+        return p
+
+    def conv_make_y_bcast(self, polys, D, owned, ypolys, peer_ypolys):
+        """peer_ypolys: list (per peer) of lists (per item) of Poly opened with ipc_open."""
+        a, pd, nd = _idx(D)
+        b, po_, no = _idx(owned)
+        flat = [p for peer in peer_ypolys for p in peer]
+        self._ck(self.lib.hb_conv_make_y_bcast(_arr(polys), len(polys), pd, nd, po_, no, _arr(ypolys),
+                                               _arr(flat) if flat else None, len(peer_ypolys)))
+
+    cls.ipc_export, cls.ipc_open, cls.conv_make_y_bcast = ipc_export, ipc_open, conv_make_y_bcast
+    return cls
+
+
+_engine_p2p(Engine)

@@ -32,7 +32,7 @@ def owner_map(ctxt, special, world):
 
 
 class ShardedKeySwitch:
-    def __init__(self, eng, ctxt, special, digits, rank=None, world=None, device="cuda"):
+    def __init__(self, eng, ctxt, special, digits, rank=None, world=None, device="cuda", p2p=False):
         self.E = eng
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
@@ -40,6 +40,10 @@ class ShardedKeySwitch:
         self.owner = owner_map(self.ctxt, self.special, self.world)
         self.device = device
         self._bufs = {}
+        # p2p: the y rows are stored straight into the peers' buffers by the producing kernel (CUDA IPC mappings
+        # over NVLink) instead of pack -> all_gather -> unpack; needs real GPUs, one process per GPU.
+        self.p2p = bool(p2p) and self.world > 1
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device) if self.p2p else None
 
     def owned(self, idx):
         return [i for i in idx if self.owner[i] == self.rank]
@@ -47,9 +51,28 @@ class ShardedKeySwitch:
     # ---- exchange buffers: torch owns the memory, the engine aliases it
     def _ybuf(self, key):
         if key not in self._bufs:
-            t = torch.zeros((self.E.np, self.E.N), dtype=torch.int64, device=self.device)
-            self._bufs[key] = (t, self.E.wrap(t.data_ptr()))
+            if self.p2p:   # engine-owned buffer, exported to / imported from every peer (collective: same key order on all ranks)
+                mine = self.E.poly()
+                handles = [None] * self.world
+                dist.all_gather_object(handles, self.E.ipc_export(mine))
+                peers = [self.E.ipc_open(h) for r, h in enumerate(handles) if r != self.rank]
+                self._bufs[key] = (None, mine, peers)
+            else:
+                t = torch.zeros((self.E.np, self.E.N), dtype=torch.int64, device=self.device)
+                self._bufs[key] = (t, self.E.wrap(t.data_ptr()), None)
         return self._bufs[key]
+
+    def _exchange(self, polys, D, ys):
+        """y rows of the source set D: produced for the owned rows, present on every rank afterwards."""
+        E = self.E
+        if self.p2p:
+            npeer = self.world - 1
+            peers = [[y[2][p] for y in ys] for p in range(npeer)]
+            E.conv_make_y_bcast(polys, D, self.owned(D), [y[1] for y in ys], peers)
+            dist.all_reduce(self._flag)          # stream-ordered cross-rank barrier: all peers' stores have landed
+        else:
+            E.conv_make_y(polys, D, self.owned(D), [y[1] for y in ys])
+            self._all_gather_rows([y[0] for y in ys], D)
 
     def _all_gather_rows(self, tensors, D):
         """After this call every rank holds rows D of every tensor in `tensors` (each rank contributed the
@@ -112,8 +135,7 @@ class ShardedKeySwitch:
         for d in range(nd):
             col = [dp[d] for dp in dig_polys]
             ys = [self._ybuf(("dig", it)) for it in range(nit)]
-            E.conv_make_y(col, dsets[d], self.owned(dsets[d]), [y[1] for y in ys])
-            self._all_gather_rows([y[0] for y in ys], dsets[d])
+            self._exchange(col, dsets[d], ys)
             tgt = self.owned([i for i in Sp if i not in dsets[d]])
             E.conv_from_y([y[1] for y in ys], dsets[d], tgt, 1, col, 0)
             for j in range(d + 1, nd):   # digits[j] -= digits[d]; digits[j] /= prod(full digit d)
@@ -134,6 +156,5 @@ class ShardedKeySwitch:
         if not drop:
             return
         ys = [self._ybuf(("md", k)) for k in range(len(parts))]
-        E.conv_make_y(parts, drop, self.owned(drop), [y[1] for y in ys])
-        self._all_gather_rows([y[0] for y in ys], drop)
+        self._exchange(parts, drop, ys)
         E.conv_from_y([y[1] for y in ys], drop, self.owned(keep), ptxt_space, parts, 1)

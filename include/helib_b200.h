@@ -143,6 +143,15 @@ int hb_scale_down_norm(hb_poly* const* polys, int nitems, const int32_t* cur, in
 int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned, hb_poly* const* ypolys);
 int hb_conv_from_y(hb_poly* const* ypolys, int nitems, const int32_t* D, int nD, const int32_t* tgt, int nT,
                    uint64_t ptxt_space, hb_poly* const* dst, int mode);
+/* Fused "make y + all-gather": like hb_conv_make_y, but the final kernel also stores the y rows into the
+ * y buffers of up to 8 peer GPUs (peer_ypolys[p*nitems + item], obtained with hb_poly_ipc_open), so the rows
+ * cross NVLink once, straight into place.  The caller orders a cross-rank barrier (e.g. a 1-element NCCL
+ * all-reduce on the same stream) before hb_conv_from_y reads the buffers. */
+int hb_conv_make_y_bcast(hb_poly* const* polys, int nitems, const int32_t* D, int nD, const int32_t* owned, int nOwned,
+                         hb_poly* const* ypolys, hb_poly* const* peer_ypolys, int npeers);
+/* CUDA IPC export / import of a polynomial's device buffer (one process per GPU; 64-byte handle). */
+int hb_poly_ipc_export(hb_poly* p, void* handle64);
+int hb_poly_ipc_open(hb_ctx* ctx, const void* handle64, hb_poly** out);
 /* Alias caller-owned device memory (uint64[nprimes][N]) as a polynomial; hb_poly_destroy does not free it. */
 int hb_poly_wrap(hb_ctx* ctx, void* device_ptr, hb_poly** out);
 /* Issue the context's work on a caller-provided CUDA stream (cudaStream_t), e.g. the stream the caller's

@@ -44,7 +44,8 @@ def main():
     evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
     evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
     p = 1 if ch.p == -1 else ch.p ** ch.r
-    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, device=device)
+    p2p = len(sys.argv) > 3 and sys.argv[3] == "p2p"
+    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, device=device, p2p=p2p)
     own_full = KS.owned(full)
     EA = [E.poly(evk_a[i], own_full) for i in range(nd)]   # evk sharded identically: only owned rows uploaded
     EB = [E.poly(evk_b[i], own_full) for i in range(nd)]

@@ -10,9 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "mp", "sharded_worker.py")
 
 
-def run(backend, world, cfg, port):
+def run(backend, world, cfg, port, mode="gather"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, backend, cfg]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, backend, cfg, mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
@@ -42,3 +42,13 @@ def test_sharded_keyswitch_nccl(cuda_lib):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     run("cuda", 2, "8192,257,1,160,2", 29613)
+
+
+@pytest.mark.gpu
+def test_sharded_keyswitch_p2p_stores(cuda_lib):
+    """Same circuit with the fused make-y + peer-store kernel (CUDA IPC over NVLink) instead of all_gather."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    run("cuda", 2, "8192,257,1,160,2", 29614, "p2p")
+    run("cuda", 2, "131072,257,1,230,2", 29615, "p2p")
