@@ -713,8 +713,7 @@ struct HbBcastJob {
   u64* loc[HB_MAXB];                   // in/out, local
   u64* peer[HB_MAXPEERS][HB_MAXB];     // out, remote
 };
-__global__ void __launch_bounds__(HB_THREADS) k_scale_bcast(const HbPrimeDev* __restrict__ primes, const HbBcastJob* __restrict__ Jp) {
-  const HbBcastJob& J = *Jp;
+__global__ void __launch_bounds__(HB_THREADS) k_scale_bcast(const HbPrimeDev* __restrict__ primes, const HbBcastJob J) {
   const int pi = J.rows.prime[blockIdx.y];
   const u64 q = primes[pi].q;
   const size_t N = (size_t)J.N, off = (size_t)pi * N;

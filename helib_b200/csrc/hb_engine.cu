@@ -1193,7 +1193,6 @@ extern "C" int hb_conv_make_y_bcast(hb_poly* const* polys, int nitems, const int
     sc[k] = h_powmod(r, q - 2, q);
   }
   HB_TRY(ctx_scratch(c));
-  if (!c->d_bcast) HB_TRY(ctx_alloc(c, (void**)&c->d_bcast, sizeof(HbBcastJob)));
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
     HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
@@ -1203,10 +1202,9 @@ extern "C" int hb_conv_make_y_bcast(hb_poly* const* polys, int nitems, const int
     fill_rows(J.rows, owned, nOwned);
     for (int k = 0; k < nOwned; k++) { J.scal[k] = sc[k]; J.scal_s[k] = h_shoup(sc[k], c->q[owned[k]]); }
     for (int i = 0; i < nit; i++) { J.loc[i] = Y[i]; for (int p = 0; p < npeers; p++) J.peer[p][i] = peer_ypolys[(size_t)p * nitems + i0 + i]->d; }
-    HB_CUDA(cudaMemcpyAsync(c->d_bcast, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
     unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
     pre_launch(c);
-    HB_LAUNCH(k_scale_bcast, dim3(gx, nOwned, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, (const HbBcastJob*)c->d_bcast);
+    HB_LAUNCH(k_scale_bcast, dim3(gx, nOwned, nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);   // by value: graph-capturable
     return post_launch(c, "k_scale_bcast", (u64)(2 + npeers) * nOwned * nit * c->N * 8);
   });
 }

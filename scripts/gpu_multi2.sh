@@ -1,7 +1,7 @@
 #!/bin/bash
 # sharded key-switch scaling at a larger batch: bash scripts/gpu_multi2.sh TAG N BATCH
 TAG=$1; N=$2; B=${3:-32}; OUT=gpurun_out; mkdir -p $OUT
-echo "== pytest sharded"; timeout 300 python -m pytest tests/test_sharded.py -m gpu -x -q 2>&1 | tail -4
+echo skip-pytest
 for ex in p2p gather; do
 for n in 1 $N; do
   if [ $n -eq 1 ] && [ $ex = gather ]; then continue; fi
