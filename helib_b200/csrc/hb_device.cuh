@@ -246,6 +246,11 @@ struct HbKsJob {            // Ctxt::keySwitchDigits inner product
   u64* out1[HB_MAXB];
   int mode;                 // 0: out += sum;  1: out = scal[row]*out + sum (scal 0 => out = sum, old value not read):
   u64 scal[HB_MAXROWS];     //    folds the addPrimesAndScale of the (1, s) parts (src/Ctxt.cpp:764-768) into the inner product
+  // mode 2: hoisted automorphism (BasicAutomorphPrecon::automorph, src/matmul.cpp:112-184): the digits and the
+  // constant part are read through sigma_k (new[j] = old[idx(rep(j)*k mod m)], src/DoubleCRT.cpp:1160-1202):
+  //   out0 = scal*sigma_k(c0) + sum_i sigma_k(D_i)*b_i ,  out1 = sum_i sigma_k(D_i)*a_i       (power-of-two m)
+  u64 ak, am;
+  const u64* c0[HB_MAXB];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -635,14 +640,19 @@ __global__ void __launch_bounds__(HB_THREADS) k_ks_inner(const HbPrimeDev* __res
   const int it = blockIdx.z;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
     const size_t o = off + k;
+    size_t g = o;   // where the digit (and c0) element is read from
     u64 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
     if (J.mode == 0) { l0 = J.out0[it][o]; l1 = J.out1[it][o]; }
-    else {
+    else if (J.mode == 1) {
       const u64 sc = J.scal[blockIdx.y];
       if (sc) { hb_mac128(h0, l0, J.out0[it][o], sc); hb_mac128(h1, l1, J.out1[it][o], sc); }
+    } else {
+      g = off + ((((2 * (u64)k + 1) * J.ak) & (J.am - 1)) >> 1);
+      const u64 sc = J.scal[blockIdx.y];
+      if (sc) hb_mac128(h0, l0, J.c0[it][g], sc);
     }
     for (int i = 0; i < J.ndig; i++) {
-      u64 d = J.dig[it][i][o];
+      u64 d = J.dig[it][i][g];
       hb_mac128(h0, l0, d, J.evk_b[i][o]);
       hb_mac128(h1, l1, d, J.evk_a[i][o]);
     }

@@ -1321,14 +1321,33 @@ static int break_into_digits_impl(hb_poly* const* src, int nitems, const int32_t
 }
 
 static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
-                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal);
+                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal,
+                                 u64 autok, hb_poly* const* c0);
 extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                                    hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1) {
-  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr);
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr, 0, nullptr);
 }
-// scal (optional, [n]): out = scal[r]*out + sum (0 => out = sum): addPrimesAndScale folded in
+// Hoisted automorphism + key switch (next row 8f-1): BasicAutomorphPrecon::automorph (src/matmul.cpp:112-184).
+extern "C" int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* S, int nS,
+                                             hb_poly* const* c0, uint64_t k, hb_poly* const* evk_a, hb_poly* const* evk_b,
+                                             hb_poly* const* out0, hb_poly* const* out1) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(c0, nitems, &c, "hb_automorph_keyswitch_digits"));
+  HB_TRY(check_idx(c, S, nS, "hb_automorph_keyswitch_digits"));
+  if (c->gen.on) return hb_fail(HB_ERR_UNSUPPORTED, "hoisted automorphisms are only built for power-of-two m");
+  if ((k & 1) == 0 || k >= c->m) return hb_fail(HB_ERR_INDEX_SET, "automorph: k not in Zm*");
+  for (int i = 0; i < nitems; i++) if (c0[i] == out0[i] || c0[i] == out1[i]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph_keyswitch_digits: outputs must not alias c0");
+  for (int i = 0; i < nitems * maxdig; i++) for (int j = 0; j < nitems; j++) if (digits[i] == out0[j] || digits[i] == out1[j]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph_keyswitch_digits: outputs must not alias the digits");
+  std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
+  std::vector<u64> sc(Sp.size(), 0);
+  for (size_t r = 0; r < Sp.size(); r++)
+    if (std::find(S, S + nS, Sp[r]) != S + nS) sc[r] = prod_mod(c, c->special.data(), (int)c->special.size(), c->q[Sp[r]]);
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, out0, out1, sc.data(), k, c0);
+}
+// scal (optional, [n]): out = scal[r]*out + sum (0 => out = sum): addPrimesAndScale folded in.
+// autok != 0: digits and c0 are read through the automorphism sigma_autok (hoisting), out0/out1 are pure outputs.
 static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
-                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal) {
+                                 hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal,
+                                 u64 autok = 0, hb_poly* const* c0 = nullptr) {
   hb_ctx* c = nullptr;
   HB_TRY(check_polys(out0, nitems, &c, "hb_keyswitch_digits")); HB_TRY(check_polys(out1, nitems, &c, "hb_keyswitch_digits"));
   if (ndig <= 0 || ndig > HB_MAXDIG || ndig > maxdig) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits: ndig=%d out of range", ndig);
@@ -1342,6 +1361,7 @@ static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, i
       J.logN = c->logN; J.N = c->N; J.ndig = ndig; J.nitems = nit;
       fill_rows(J.rows, idx + r0, nr);
       if (scal) { J.mode = 1; for (int i = 0; i < nr; i++) J.scal[i] = scal[r0 + i]; }
+      if (autok) { J.mode = 2; J.ak = autok; J.am = c->m; for (int it = 0; it < nit; it++) J.c0[it] = c0[i0 + it]->d; }
       for (int i = 0; i < ndig; i++) { J.evk_a[i] = evk_a[i]->d; J.evk_b[i] = evk_b[i]->d; }
       for (int it = 0; it < nit; it++) {
         J.out0[it] = out0[i0 + it]->d; J.out1[it] = out1[i0 + it]->d;
@@ -1421,7 +1441,7 @@ extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* c
   std::vector<u64> sc(Sp.size(), 0);
   for (size_t r = 0; r < Sp.size(); r++)
     if (std::find(S, S + nS, Sp[r]) != S + nS) sc[r] = prod_mod(c, c->special.data(), (int)c->special.size(), c->q[Sp[r]]);
-  return keyswitch_digits_impl(dig.data(), maxdig, nd, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0, c1, sc.data());
+  return keyswitch_digits_impl(dig.data(), maxdig, nd, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0, c1, sc.data(), 0, nullptr);
 }
 
 extern "C" int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1, int nitems,

@@ -417,3 +417,18 @@ def _engine_p2p(cls):
 
 
 _engine_p2p(Engine)
+
+
+def _engine_hoist(cls):
+    def automorph_keyswitch_digits(self, digits, S, c0, k, evk_a, evk_b, out0, out1):
+        a, p, n = _idx(S)
+        nd = len(digits[0])
+        flat = [d for item in digits for d in item]
+        self._ck(self.lib.hb_automorph_keyswitch_digits(_arr(flat), nd, nd, len(digits), p, n, _arr(c0), C.c_uint64(int(k)),
+                                                        _arr(evk_a), _arr(evk_b), _arr(out0), _arr(out1)))
+
+    cls.automorph_keyswitch_digits = automorph_keyswitch_digits
+    return cls
+
+
+_engine_hoist(Engine)

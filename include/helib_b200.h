@@ -116,6 +116,14 @@ int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, in
  * every call, src/Ctxt.cpp:196-206; here they are expanded once by the host and cached). */
 int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                         hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1);
+/* Hoisted automorphism + key switch: BasicAutomorphPrecon::automorph (src/matmul.cpp:112-184),
+ * the rotation path of Ctxt::smartAutomorph (src/Ctxt.cpp:2462-2515).  The digits of the s-part are computed once
+ * with hb_break_into_digits; for each amount k (odd, < m) one launch applies sigma_k in the load stage:
+ *   out0 = P*sigma_k(c0) + sum_i sigma_k(D_i)*b_i ,  out1 = sum_i sigma_k(D_i)*a_i     over S | special
+ * (evk_a/evk_b: the matrix for s(X^k) -> s).  Outputs must not alias inputs.  Power-of-two m. */
+int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* S, int nS,
+                                  hb_poly* const* c0, uint64_t k, hb_poly* const* evk_a, hb_poly* const* evk_b,
+                                  hb_poly* const* out0, hb_poly* const* out1);
 /* Ctxt::tensorProduct of two canonical 2-part ciphertexts (src/Ctxt.cpp:1563-1608) */
 int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1,
               hb_poly* const* o0, hb_poly* const* o1, hb_poly* const* o2, int nitems, const int32_t* idx, int n);

@@ -259,3 +259,34 @@ def test_sim_generic_modulus_path(sim_lib, monkeypatch):
     generic 2^64-q form.  Force the generic one (HB_NO_SPECIAL) on the N = 2^16 circuit."""
     monkeypatch.setenv("HB_NO_SPECIAL", "1")
     test_sim_full_ring_dimension_small_chain(sim_lib)
+
+
+@pytest.mark.parametrize("cfg", [(64, 257, 1, 120, 2), (4096, 257, 1, 60, 2), (8192, -1, 1, 119, 2)])
+def test_hoisted_automorph_keyswitch(lib, cfg):
+    """one breakIntoDigits, many (automorph + keySwitchDigits) -- BasicAutomorphPrecon
+    (src/matmul.cpp:60-184).  Checked against the oracle doing automorph on every digit and on c0,
+    addPrimesAndScale, keySwitchDigits (src/matmul.cpp:152-170)."""
+    ch, psis, O, E = make(lib, *cfg)
+    rng = np.random.default_rng(31)
+    S = ch.ctxt
+    full = S + ch.special
+    Sp = sorted(full)
+    nd = len(ch.digits)
+    c0, c1 = O.random(rng, S), O.random(rng, S)
+    C0, C1 = E.poly(c0, S), E.poly(c1, S)
+    digs = E.break_into_digits([C1], S)
+    ref_digs = O.break_into_digits(c1, S)
+    for k in (3, 5, ch.m - 1):
+        evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+        evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+        EA = [E.poly(evk_a[i], full) for i in range(nd)]
+        EB = [E.poly(evk_b[i], full) for i in range(nd)]
+        O0, O1 = E.poly(), E.poly()
+        E.automorph_keyswitch_digits(digs, S, [C0], k, EA, EB, [O0], [O1])
+        r0 = c0.copy(); O.automorph(r0, S, k); O.add_primes_and_scale(r0, S, ch.special)
+        r1 = O.zeros()
+        rd = ref_digs.copy()
+        for i in range(rd.shape[0]):
+            O.automorph(rd[i], Sp, k)
+        O.keyswitch_digits(rd, Sp, evk_a, evk_b, r0, r1)
+        assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
