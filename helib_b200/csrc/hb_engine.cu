@@ -442,6 +442,65 @@ extern "C" int hb_ctx_profile_get(hb_ctx* c, int i, char* name, int namelen, uin
   if (bytes) *bytes = c->prof[i].bytes;
   return HB_OK;
 }
+// ---- wire format: DoubleCRT::writeTo / read (src/DoubleCRT.cpp:1530-1561) =
+// IndexSet::writeTo (int64 card, int64 indices; src/IndexSet.cpp:288-297) followed, per row in index order, by
+// write_ntl_vec_long (int32 length, int32 intSize = 8, then little-endian int64 values; src/binio.cpp:103-122).
+extern "C" int hb_poly_serialized_size(hb_poly* p, int n, uint64_t* bytes) {
+  if (!p || !bytes || n < 0) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_serialized_size: bad argument");
+  *bytes = 8 + 8ULL * n + (uint64_t)n * (8 + 8ULL * p->ctx->N);
+  return HB_OK;
+}
+extern "C" int hb_poly_serialize(hb_poly* p, const int32_t* idx, int n, void* buf, uint64_t buflen) {
+  if (!p || !buf) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_serialize: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_poly_serialize", true));
+  uint64_t need; hb_poly_serialized_size(p, n, &need);
+  if (buflen < need) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_serialize: buffer of %llu bytes, need %llu", (unsigned long long)buflen, (unsigned long long)need);
+  std::vector<int32_t> sorted(idx, idx + n); std::sort(sorted.begin(), sorted.end());   // IndexSet iterates in ascending order
+  unsigned char* o = (unsigned char*)buf;
+  int64_t card = n; memcpy(o, &card, 8); o += 8;
+  for (int i = 0; i < n; i++) { int64_t v = sorted[i]; memcpy(o, &v, 8); o += 8; }
+  for (int i = 0; i < n; i++) {
+    int32_t len = (int32_t)c->N, isz = 8; memcpy(o, &len, 4); memcpy(o + 4, &isz, 4); o += 8;
+    HB_CUDA(cudaMemcpyAsync(o, p->d + (size_t)sorted[i] * c->N, c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    o += c->N * 8;
+  }
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return HB_OK;
+}
+// idx_out receives the index set (capacity nprimes), *n_out its size; rows are uploaded into p.
+extern "C" int hb_poly_deserialize(hb_poly* p, const void* buf, uint64_t buflen, int32_t* idx_out, int* n_out) {
+  if (!p || !buf || !idx_out || !n_out) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: null");
+  hb_ctx* c = p->ctx;
+  const unsigned char* o = (const unsigned char*)buf; const unsigned char* end = o + buflen;
+  if (buflen < 8) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: truncated");
+  int64_t card; memcpy(&card, o, 8); o += 8;
+  if (card < 0 || card > c->nprimes || o + 8 * card > end) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: bad index-set size %lld", (long long)card);
+  for (int64_t i = 0; i < card; i++) {
+    int64_t v; memcpy(&v, o, 8); o += 8;
+    if (v < 0 || v >= c->nprimes) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: prime index %lld out of range", (long long)v);
+    idx_out[i] = (int32_t)v;
+  }
+  for (int64_t i = 0; i < card; i++) {
+    if (o + 8 > end) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: truncated row header");
+    int32_t len, isz; memcpy(&len, o, 4); memcpy(&isz, o + 4, 4); o += 8;
+    if (len != (int32_t)c->N) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: row length %d, expected phi(m)=%zu", len, c->N);
+    if (isz != 8 && isz != 4) return hb_fail(HB_ERR_BAD_ARG, "intSize must be 32 or 64 bit for binary IO");   // src/binio.cpp:107-109
+    if (o + (size_t)len * isz > end) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: truncated row");
+    const u64 q = c->q[idx_out[i]];
+    std::vector<u64> row(c->N);
+    for (size_t k = 0; k < c->N; k++) {
+      int64_t v;
+      if (isz == 8) memcpy(&v, o + 8 * k, 8); else { int32_t w; memcpy(&w, o + 4 * k, 4); v = w; }
+      if (v < 0 || (u64)v >= q) return hb_fail(HB_ERR_INDEX_SET, "DoubleCRT object has inconsistent data");   // DoubleCRT::verify, src/DoubleCRT.cpp:121-132
+      row[k] = (u64)v;
+    }
+    o += (size_t)len * isz;
+    HB_CUDA(cudaMemcpy(p->d + (size_t)idx_out[i] * c->N, row.data(), c->N * 8, cudaMemcpyHostToDevice));
+  }
+  *n_out = (int)card;
+  return HB_OK;
+}
 static int pool_get(hb_ctx* c, int n, std::vector<hb_poly*>& out) {
   while ((int)c->pool.size() < n) { hb_poly* p; HB_TRY(hb_poly_create(c, &p)); c->pool.push_back(p); }
   out.assign(c->pool.begin(), c->pool.begin() + n);

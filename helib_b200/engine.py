@@ -432,3 +432,25 @@ def _engine_hoist(cls):
 
 
 _engine_hoist(Engine)
+
+
+def _poly_io(cls):
+    def serialize(self, idx) -> bytes:
+        a, p, n = _idx(idx)
+        need = C.c_uint64()
+        self.eng._ck(self.eng.lib.hb_poly_serialized_size(self.h, n, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self.eng._ck(self.eng.lib.hb_poly_serialize(self.h, p, n, buf, need))
+        return buf.raw
+
+    def deserialize(self, data: bytes):
+        out = np.zeros(self.eng.np, dtype=np.int32)
+        n = C.c_int()
+        self.eng._ck(self.eng.lib.hb_poly_deserialize(self.h, data, C.c_uint64(len(data)), out.ctypes.data_as(i32p), C.byref(n)))
+        return [int(x) for x in out[:n.value]]
+
+    cls.serialize, cls.deserialize = serialize, deserialize
+    return cls
+
+
+_poly_io(Poly)

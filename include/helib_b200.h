@@ -84,6 +84,13 @@ int hb_poly_upload(hb_poly* p, const int32_t* idx, int n, const uint64_t* host_d
 int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t* host_dense);  /* synchronises */
 int hb_poly_download_async(hb_poly* p, const int32_t* idx, int n, uint64_t* host_dense); /* stream-ordered; hb_ctx_sync() before reading */
 
+/* Wire format: byte-compatible with DoubleCRT::writeTo / read (src/DoubleCRT.cpp:1530-1561):
+ * IndexSet (int64 card, int64 indices) then per row int32 length, int32 intSize(=8), little-endian int64 values
+ * (src/binio.cpp:103-122).  hb_poly_deserialize also accepts intSize=4 rows and rejects residues outside [0,q). */
+int hb_poly_serialized_size(hb_poly* p, int n, uint64_t* bytes);
+int hb_poly_serialize(hb_poly* p, const int32_t* idx, int n, void* buf, uint64_t buflen);
+int hb_poly_deserialize(hb_poly* p, const void* buf, uint64_t buflen, int32_t* idx_out, int* n_out);
+
 /* ---- per-prime transforms: Cmodulus::FFT / iFFT (src/CModulus.cpp:362-429, 486-553) -----
  * In place on rows idx of each poly: coefficient rows (values in [0,q)) <-> evaluation rows. */
 int hb_ntt_fwd(hb_poly* const* polys, int nitems, const int32_t* idx, int n);

@@ -236,3 +236,29 @@ def test_embedding_norms_match_restated_reference(lib, cfg):
     want = float(np.max(np.abs(vals)))
     assert abs(norms[0] - want) <= 1e-9 * want
     assert want <= p / 2.0 * n + 1
+
+
+def test_wire_format_matches_reference_layout(lib):
+    """SURVEY 8f-3: DoubleCRT::writeTo byte layout (src/DoubleCRT.cpp:1530-1541, src/IndexSet.cpp:288-297,
+    src/binio.cpp:103-122) built by hand with struct.pack; round trip; corrupt data is rejected."""
+    import struct
+    ch, psis, O, E = make(lib, 64, 257, 1, 120, 2)
+    rng = np.random.default_rng(41)
+    S = ch.ctxt
+    x = O.random(rng, S)
+    P = E.poly(x, S)
+    blob = P.serialize(list(reversed(S)))            # any order in -> ascending index order out
+    want = struct.pack("<q", len(S)) + b"".join(struct.pack("<q", i) for i in sorted(S))
+    for i in sorted(S):
+        want += struct.pack("<ii", ch.phim, 8) + b"".join(struct.pack("<q", int(v)) for v in x[i])
+    assert blob == want
+    Q = E.poly()
+    assert Q.deserialize(blob) == sorted(S)
+    assert rows_equal(Q.download(S), x, S)
+    bad = bytearray(blob)
+    off = 8 + 8 * len(S) + 8
+    bad[off:off + 8] = struct.pack("<q", ch.primes[sorted(S)[0]])      # residue == q: out of range
+    with pytest.raises(HbError):
+        Q.deserialize(bytes(bad))
+    with pytest.raises(HbError):
+        Q.deserialize(blob[:-5])
