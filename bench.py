@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="independent ciphertext pairs per step and GPU")
+    ap.add_argument("--batch", type=int, default=16, help="independent ciphertext pairs per step and GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=6, help="multiplies timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
