@@ -318,7 +318,8 @@ def main():
         top = prof[0]
         base = top["kernel"].replace("_subscale", "")
         if base in tj:
-            traffic = tj[base].get("avg_dram_bytes_per_launch_at_batch8")
+            t8 = tj[base].get("avg_dram_bytes_per_launch_at_batch8")
+            traffic = t8 * B / 8.0 if t8 else None      # captured at batch 8; DRAM bytes per launch scale with the items per launch
         ach = top["bytes"] / (top["ms"] / 1000.0) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_kind": peak_kind, "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of run r01f)" if traffic else None, "share_of_step": top["ms"] / tot_ms,

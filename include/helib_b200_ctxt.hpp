@@ -1,0 +1,326 @@
+// helib_b200_ctxt.hpp -- header-only C++17 mirror of the hot subset of helib::Ctxt over hb::DoubleCRT.
+//
+// Host orchestration stays on the host exactly as in the reference:
+// noise estimates in extended-range floating point, the choice of the prime set for a product
+// (computeIntervalForMul + ModuliSizes::getSet4Size), when to mod-switch and when to key-switch.  Every data
+// operation goes to the engine through hb::DoubleCRT.  Method names, argument meaning and failure behaviour
+// follow the reference (citations: paths in the HElib tree):
+//   SKHandle::mul                  include/helib/Ctxt.h:155-185
+//   modUpToSet / bringToSet        src/Ctxt.cpp:346-389
+//   modDownToSet                   src/Ctxt.cpp:393-562      (added noise from the device-computed ||delta/P||)
+//   dropSmallAndSpecialPrimes      src/Ctxt.cpp:589-662
+//   relin_CKKS_adjust              src/Ctxt.cpp:664-716
+//   reLinearize / keySwitchPart    src/Ctxt.cpp:720-842
+//   keySwitchDigits                src/Ctxt.cpp:191-230
+//   tensorProduct                  src/Ctxt.cpp:1563-1608
+//   computeIntervalForMul          src/Ctxt.cpp:1610-1656
+//   multLowLvl / multiplyBy        src/Ctxt.cpp:1681-1774
+//   modSwitchAddedNoiseBound       src/Ctxt.cpp:2560-2582
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <memory>
+
+#include "helib_b200_doublecrt.hpp"
+
+namespace hb {
+
+// NTL::xdouble stand-in: value = m * 2^e, enough range for noise bounds of 2^2000 and beyond.
+struct XD {
+  double m = 0; long e = 0;
+  XD() = default;
+  XD(double v) { int ex = 0; m = std::frexp(v, &ex); e = ex; }
+  static XD make(double m_, long e_) { XD r; int ex = 0; r.m = std::frexp(m_, &ex); r.e = e_ + ex; if (r.m == 0) r.e = 0; return r; }
+  static XD exp(double lnv) { double l2 = lnv / std::log(2.0); long fl = (long)std::floor(l2); return make(std::exp2(l2 - fl), fl); }
+  double ln() const { return m <= 0 ? -DBL_MAX : std::log(m) + e * std::log(2.0); }
+  double to_double() const { return std::ldexp(m, (int)std::max(-2000L, std::min(2000L, e))); }
+  XD operator*(const XD& o) const { return make(m * o.m, e + o.e); }
+  XD operator/(const XD& o) const { return make(m / o.m, e - o.e); }
+  XD operator+(const XD& o) const {
+    if (m == 0) return o; if (o.m == 0) return *this;
+    if (e >= o.e) { long d = e - o.e; return d > 1100 ? *this : make(m + std::ldexp(o.m, (int)-d), e); }
+    return o + *this;
+  }
+  bool operator<(const XD& o) const { if (m <= 0 || o.m <= 0) return m < o.m; return e != o.e ? e < o.e : m < o.m; }
+  bool operator>(const XD& o) const { return o < *this; }
+  bool operator<=(const XD& o) const { return !(o < *this); }
+};
+
+// include/helib/Ctxt.h:82-260
+struct SKHandle {
+  long powerOfS = 0, powerOfX = 1, secretKeyID = 0;
+  SKHandle() = default;
+  SKHandle(long s, long x, long id) : powerOfS(s), powerOfX(x), secretKeyID(id) {}
+  bool isOne() const { return powerOfS == 0; }
+  bool isBase(long id = 0) const { return powerOfS == 1 && powerOfX == 1 && (id < 0 || secretKeyID == id); }
+  bool operator==(const SKHandle& o) const { return powerOfS == o.powerOfS && powerOfX == o.powerOfX && secretKeyID == o.secretKeyID; }
+  bool mul(const SKHandle& a, const SKHandle& b) {   // include/helib/Ctxt.h:155-185
+    if (a.isOne()) { *this = b; return b.secretKeyID >= 0; }
+    if (b.isOne()) { *this = a; return a.secretKeyID >= 0; }
+    if (a.secretKeyID == -1 || b.secretKeyID == -1 || a.secretKeyID != b.secretKeyID || a.powerOfX != b.powerOfX) { secretKeyID = -1; return false; }
+    secretKeyID = a.secretKeyID; powerOfX = a.powerOfX; powerOfS = a.powerOfS + b.powerOfS;
+    return true;
+  }
+};
+
+struct CtxtPart {
+  DoubleCRT dcrt;
+  SKHandle skHandle;
+  CtxtPart(const DoubleCRT& d, const SKHandle& h) : dcrt(d), skHandle(h) {}
+};
+
+// helib::KeySwitch (include/helib/keySwitching.h:86-100) with the pseudo-random a_i expanded once
+struct KeySwitch {
+  SKHandle fromKey; long toKeyID = 0; long ptxtSpace = 0;
+  std::vector<DoubleCRT> a, b;
+  XD noiseBound;
+};
+
+// the part of helib::PubKey / Context the ciphertext logic consults
+struct KeyInfo {
+  const Context* context;
+  bool ckks = false;
+  double scale = 10.0;           // Context::scale (include/helib/Context.h:151)
+  long hwt = 0;                  // Context::getHwt()
+  double skBound = 0;            // PubKey::getSKeyBound (src/keys.cpp:280)
+  std::vector<KeySwitch> keySwitching;
+  const KeySwitch* getKeySWmatrix(const SKHandle& from, long toID) const {
+    for (auto& w : keySwitching) if (w.fromKey == from && w.toKeyID == toID) return &w;
+    return nullptr;
+  }
+  double noiseBoundForUniform(double mag, long deg) const { return scale * std::sqrt(double(deg) / 3.0) * mag; }   // include/helib/Context.h:475-478
+  double logOfProduct(const IndexSet& s) const { double x = 0; for (long i : s) x += std::log((double)context->ithPrime(i)); return x; }
+};
+
+class Ctxt {
+ public:
+  const KeyInfo& pubKey;
+  const Context& context;
+  std::vector<CtxtPart> parts;
+  IndexSet primeSet;
+  long ptxtSpace;
+  XD noiseBound;
+  long intFactor = 1;
+  XD ratFactor = XD(1.0), ptxtMag = XD(1.0);
+  static constexpr double safety = 0.6931471805599453;   // log 2, top of src/Ctxt.cpp
+
+  Ctxt(const KeyInfo& pk, long ptxtSp) : pubKey(pk), context(*pk.context), ptxtSpace(ptxtSp), noiseBound(0.0) {}
+  Ctxt& operator=(const Ctxt& o) {
+    parts = o.parts; primeSet = o.primeSet; ptxtSpace = o.ptxtSpace; noiseBound = o.noiseBound;
+    intFactor = o.intFactor; ratFactor = o.ratFactor; ptxtMag = o.ptxtMag;
+    return *this;
+  }
+  Ctxt(const Ctxt&) = default;
+  bool isCKKS() const { return pubKey.ckks; }
+  bool isEmpty() const { return parts.empty(); }
+  double logOfPrimeSet() const { return pubKey.logOfProduct(primeSet); }
+  long getPartIndexByHandle(const SKHandle& h) const { for (size_t i = 0; i < parts.size(); i++) if (parts[i].skHandle == h) return (long)i; return -1; }
+  bool inCanonicalForm(long keyID = 0) const {
+    if (parts.size() > 2) return false;
+    if (parts.size() > 0 && !parts[0].skHandle.isOne()) return false;
+    if (parts.size() > 1 && !parts[1].skHandle.isBase(keyID)) return false;
+    return true;
+  }
+  bool verifyPrimeSet() const {   // src/Ctxt.cpp:177-186
+    IndexSet s = primeSet & context.getSpecialPrimes();
+    if (!empty(s) && s != context.getSpecialPrimes()) return false;
+    return (primeSet & context.getCtxtPrimes()).isInterval();
+  }
+  XD modSwitchAddedNoiseBound() const {   // src/Ctxt.cpp:2560-2582
+    XD added(0.0);
+    for (auto& part : parts) {
+      if (part.skHandle.isOne()) added = added + XD(1.0);
+      else added = added + XD::exp(part.skHandle.powerOfS * std::log(pubKey.skBound));
+    }
+    return added * XD(pubKey.noiseBoundForUniform(double(ptxtSpace) / 2.0, context.getPhiM()));
+  }
+
+  void modUpToSet(const IndexSet& s) {   // src/Ctxt.cpp:346-371
+    IndexSet setDiff = s / primeSet;
+    if (empty(setDiff)) return;
+    double f = 0;
+    for (auto& part : parts) f = part.dcrt.addPrimesAndScale(setDiff);
+    noiseBound = noiseBound * XD::exp(f);
+    ratFactor = ratFactor * XD::exp(f);
+    primeSet.insert(setDiff);
+    if (!verifyPrimeSet()) throw LogicError("primeSet is no longer valid");
+  }
+  void modDownToSet(const IndexSet& s) {   // src/Ctxt.cpp:393-562 ("real mod switching" branch)
+    IndexSet intersection = primeSet & s;
+    if (empty(intersection)) throw RuntimeError("modDownToSet called with a disjoint set");
+    IndexSet setDiff = primeSet / intersection;
+    if (empty(setDiff)) return;
+    XD addedNoiseBound = modSwitchAddedNoiseBound();
+    XD addedNoise(0.0);
+    for (auto& part : parts) {
+      const double norm = part.dcrt.scaleDownToSetNorm(intersection, ptxtSpace);   // ||delta/P||_canon, computed on the device
+      if (part.skHandle.isOne()) addedNoise = addedNoise + XD(norm);
+      else addedNoise = addedNoise + XD(norm) * XD::exp(part.skHandle.powerOfS * std::log(pubKey.skBound));
+    }
+    XD f = XD::exp(pubKey.logOfProduct(setDiff));
+    ratFactor = ratFactor / f;
+    noiseBound = noiseBound / f;
+    noiseBound = noiseBound + addedNoise;
+    lastModSwitchRatio = (addedNoise / addedNoiseBound).to_double();   // the reference's "mod-switch-added-noise" statistic
+    primeSet.remove(setDiff);
+    if (!verifyPrimeSet()) throw LogicError("primeSet is no longer valid");
+  }
+  void bringToSet(const IndexSet& s) {   // src/Ctxt.cpp:373-389
+    if (empty(s)) { IndexSet tmp(context.getCtxtPrimes().first()); modUpToSet(tmp); modDownToSet(tmp); }
+    else { modUpToSet(s); modDownToSet(s); }
+  }
+  void dropSmallAndSpecialPrimes() {   // src/Ctxt.cpp:589-662
+    if (primeSet.disjointFrom(context.getSmallPrimes())) { modDownToSet(context.getCtxtPrimes()); return; }
+    IndexSet target = primeSet & context.getCtxtPrimes();
+    IndexSet dropping = primeSet / target;
+    double log_dropping = pubKey.logOfProduct(dropping);
+    double log_modswitch_noise = modSwitchAddedNoiseBound().ln();
+    double log_noise = noiseBound.m <= 0 ? -DBL_MAX : noiseBound.ln();
+    double log_compensation = 0;
+    log_modswitch_noise += 3 * std::log(2.0);
+    if (log_noise - log_dropping + log_compensation < log_modswitch_noise) {
+      IndexSet candidates = context.getCtxtPrimes() / target;
+      for (long i : candidates) {
+        target.insert(i);
+        log_compensation += std::log((double)context.ithPrime(i));
+        if (log_noise - log_dropping + log_compensation >= log_modswitch_noise) break;
+      }
+    }
+    bringToSet(target);
+  }
+  void relin_CKKS_adjust() {   // src/Ctxt.cpp:664-716
+    if (!isCKKS()) return;
+    long phim = context.getPhiM();
+    double h = pubKey.hwt == 0 ? phim / 2.0 : (double)pubKey.hwt;
+    double log_phim = std::max(1.0, std::log((double)phim));
+    double beta = pubKey.scale * std::sqrt(phim * log_phim * h / 12.0);
+    double gamma = beta * 8;
+    if (XD(gamma) > noiseBound) {
+      long xf = (long)std::ceil(gamma / noiseBound.to_double());
+      for (auto& part : parts) part.dcrt *= xf;
+      noiseBound = noiseBound * XD((double)xf);
+      ratFactor = ratFactor * XD((double)xf);
+    }
+  }
+  void addPart(const DoubleCRT& part, const SKHandle& handle) {   // src/Ctxt.cpp:851-893 (matchPrimeSet, non-negative)
+    if (!(primeSet <= part.getIndexSet())) throw RuntimeError("Ctxt::addPart: ctxt has primes not in part");
+    long j = getPartIndexByHandle(handle);
+    if (j >= 0) parts[j].dcrt.Add(part, /*matchIndexSets=*/false);
+    else {
+      parts.emplace_back(part, handle);
+      if (part.getIndexSet() != primeSet) parts.back().dcrt.removePrimes(part.getIndexSet() / primeSet);
+    }
+  }
+  // src/Ctxt.cpp:191-230 -- the two products per digit and their accumulation run as ONE engine launch
+  void keySwitchDigits(const KeySwitch& W, std::vector<DoubleCRT>& digits) {
+    long j0 = getPartIndexByHandle(SKHandle()), j1 = getPartIndexByHandle(SKHandle(1, 1, W.toKeyID));
+    if (j0 < 0) { parts.emplace_back(DoubleCRT(context, primeSet), SKHandle()); j0 = (long)parts.size() - 1; }
+    if (j1 < 0) { parts.emplace_back(DoubleCRT(context, primeSet), SKHandle(1, 1, W.toKeyID)); j1 = (long)parts.size() - 1; }
+    std::vector<hb_poly*> dg, ea, eb;
+    for (size_t i = 0; i < digits.size(); i++) { dg.push_back(digits[i].handle()); ea.push_back(W.a[i].handle()); eb.push_back(W.b[i].handle()); }
+    hb_poly* o0[1] = {parts[j0].dcrt.handle()}; hb_poly* o1[1] = {parts[j1].dcrt.handle()};
+    auto idx = primeSet.vec();
+    check(hb_keyswitch_digits(dg.data(), (int)digits.size(), (int)digits.size(), 1, idx.data(), (int)idx.size(), ea.data(), eb.data(), o0, o1));
+  }
+  void keySwitchPart(const CtxtPart& p, const KeySwitch& W) {   // src/Ctxt.cpp:805-842
+    if (!context.getSpecialPrimes().disjointFrom(p.dcrt.getIndexSet())) throw LogicError("Special primes and CtxtPart's index set have non-empty intersection");
+    if (p.skHandle.isOne() || p.skHandle.isBase(W.toKeyID)) {
+      CtxtPart pp = p;
+      pp.dcrt.addPrimesAndScale(context.getSpecialPrimes());
+      addPart(pp.dcrt, pp.skHandle);
+      return;
+    }
+    if (!(W.fromKey == p.skHandle)) throw LogicError("Secret key handles do not match");
+    std::vector<DoubleCRT> polyDigits;
+    XD addedNoise(0.0);
+    for (double ln : p.dcrt.breakIntoDigitsLogNorms(polyDigits)) addedNoise = addedNoise + XD::exp(ln);   // sum of ||E_i||, computed on the device
+    addedNoise = addedNoise * W.noiseBound;
+    keySwitchDigits(W, polyDigits);
+    lastKSNoiseRatio = (addedNoise / noiseBound).to_double();   // "KS-noise-ratio"
+    noiseBound = noiseBound + addedNoise;
+  }
+  void reLinearize(long keyID = 0) {   // src/Ctxt.cpp:720-786
+    if (isEmpty() || inCanonicalForm(keyID)) return;
+    dropSmallAndSpecialPrimes();
+    relin_CKKS_adjust();
+    double logProd = pubKey.logOfProduct(context.getSpecialPrimes());
+    Ctxt tmp(pubKey, ptxtSpace);
+    tmp.intFactor = intFactor; tmp.ptxtMag = ptxtMag;
+    tmp.noiseBound = noiseBound * XD::exp(logProd);
+    tmp.primeSet = primeSet | context.getSpecialPrimes();
+    tmp.ratFactor = ratFactor * XD::exp(logProd);
+    for (CtxtPart& part : parts) {
+      if (part.skHandle.isOne() || part.skHandle.isBase(keyID)) {
+        part.dcrt.addPrimesAndScale(context.getSpecialPrimes());
+        tmp.addPart(part.dcrt, part.skHandle);
+        continue;
+      }
+      const KeySwitch* W = pubKey.getKeySWmatrix(part.skHandle, keyID);
+      if (!W) throw LogicError("No key-switching matrix exists");
+      tmp.keySwitchPart(part, *W);
+    }
+    *this = tmp;
+  }
+  void tensorProduct(const Ctxt& c1, const Ctxt& c2) {   // src/Ctxt.cpp:1563-1608
+    parts.clear();
+    primeSet = c1.primeSet;
+    long ptxtSp = c1.ptxtSpace;
+    if (ptxtSp > 2) {
+      unsigned long q = 1;
+      for (long i : c1.primeSet) q = (unsigned long)(((unsigned __int128)q * (unsigned long)(context.ithPrime(i) % ptxtSp)) % (unsigned long)ptxtSp);
+      intFactor = (long)(((unsigned __int128)c1.intFactor * c2.intFactor) % ptxtSp);
+      intFactor = (long)(((unsigned __int128)intFactor * q) % ptxtSp);
+    }
+    for (auto& p1 : c1.parts)
+      for (auto& p2 : c2.parts) {
+        CtxtPart tmpPart = p2;
+        if (!tmpPart.skHandle.mul(p1.skHandle, tmpPart.skHandle)) throw LogicError("Ctxt::tensorProduct: cannot multiply secret-key handles");
+        tmpPart.dcrt *= p1.dcrt;
+        long k = getPartIndexByHandle(tmpPart.skHandle);
+        if (k >= 0) parts[k].dcrt += tmpPart.dcrt;
+        else parts.push_back(tmpPart);
+      }
+    if (isCKKS()) {
+      noiseBound = c1.noiseBound * c2.ptxtMag * c2.ratFactor + c2.noiseBound * c1.ptxtMag * c1.ratFactor + c1.noiseBound * c2.noiseBound;
+      ratFactor = c1.ratFactor * c2.ratFactor;
+      ptxtMag = c1.ptxtMag * c2.ptxtMag;
+    } else noiseBound = c1.noiseBound * c2.noiseBound;
+  }
+  static void computeIntervalForMul(double& lo, double& hi, const Ctxt& c1, const Ctxt& c2) {   // src/Ctxt.cpp:1610-1656
+    const double slack = 4 * std::log(2.0);
+    double cap1 = c1.logOfPrimeSet() - std::max(c1.noiseBound, XD(1.0)).ln();
+    double cap2 = c2.logOfPrimeSet() - std::max(c2.noiseBound, XD(1.0)).ln();
+    double adn1 = c1.modSwitchAddedNoiseBound().ln(), adn2 = c2.modSwitchAddedNoiseBound().ln();
+    if (c1.isCKKS()) { lo = std::max(cap1 + adn1, cap2 + adn2) + safety; hi = lo + slack; }
+    else { hi = std::min(cap1 + adn1, cap2 + adn2) - safety; lo = hi - slack; }
+  }
+  void multLowLvl(const Ctxt& other_orig) {   // src/Ctxt.cpp:1681-1753 (non-destructive, distinct operands)
+    if (isEmpty()) return;
+    if (other_orig.isEmpty()) { *this = other_orig; return; }
+    if (&context != &other_orig.context) throw LogicError("Context mismatch");
+    Ctxt other = other_orig;
+    double lo, hi;
+    computeIntervalForMul(lo, hi, *this, other);
+    auto f1 = primeSet.vec(), f2 = other.primeSet.vec();
+    std::vector<int32_t> out(context.numPrimes()); int nout = 0;
+    check(hb_chain_set4size(context.chain(), lo, hi, f1.data(), (int)f1.size(), f2.data(), (int)f2.size(), isCKKS() ? 1 : 0, out.data(), &nout));
+    IndexSet common(out.begin(), out.begin() + nout);
+    lastCommonPrimeSet = common;
+    bringToSet(common);
+    other.bringToSet(common);
+    Ctxt tmp(pubKey, ptxtSpace);
+    tmp.tensorProduct(*this, other);
+    *this = tmp;
+  }
+  void multiplyBy(const Ctxt& other) {   // src/Ctxt.cpp:1757-1774
+    if (isEmpty()) return;
+    if (other.isEmpty()) { *this = other; return; }
+    multLowLvl(other);
+    reLinearize();
+  }
+  // statistics the reference records through HELIB_STATS_UPDATE (src/Ctxt.cpp:537,835)
+  double lastModSwitchRatio = 0, lastKSNoiseRatio = 0;
+  IndexSet lastCommonPrimeSet;
+};
+
+}  // namespace hb

@@ -246,6 +246,50 @@ class DoubleCRT {
     check(hb_break_into_digits(s, 1, cur.data(), (int)cur.size(), dp.data(), (int)maxdig, &nd));
     digits.erase(digits.begin() + nd, digits.end());
   }
+  // scaleDownToSet that also returns ||delta/P||_canon, the quantity Ctxt::modDownToSet derives from the
+  // returned delta (src/Ctxt.cpp:476-505); computed on the device.
+  double scaleDownToSetNorm(const IndexSet& s, long ptxtSpace) {
+    IndexSet diff = set_ / s;
+    if (empty(diff)) return 0.0;
+    if (ptxtSpace < 1) throw InvalidArgument("ptxtSpace must be at least 1");
+    auto cur = set_.vec(), keep = (set_ & s).vec();
+    hb_poly* d[1] = {p_};
+    double norm = 0;
+    check(hb_scale_down_norm(d, 1, cur.data(), (int)cur.size(), keep.data(), (int)keep.size(), (uint64_t)ptxtSpace, &norm));
+    set_.remove(diff);
+    return norm;
+  }
+  // breakIntoDigits returning ln ||E_i||_canon per digit (the reference returns their sum, src/DoubleCRT.cpp:542-545)
+  std::vector<double> breakIntoDigitsLogNorms(std::vector<DoubleCRT>& digits) const {
+    const long maxdig = (long)context_->getDigits().size();
+    digits.clear();
+    IndexSet all = set_ | context_->getSpecialPrimes();
+    for (long i = 0; i < maxdig; i++) digits.emplace_back(*context_, all);
+    std::vector<hb_poly*> dp;
+    for (auto& d : digits) dp.push_back(d.p_);
+    auto cur = set_.vec();
+    hb_poly* s[1] = {p_};
+    int nd = 0;
+    std::vector<double> ln(maxdig);
+    check(hb_break_into_digits_norm(s, 1, cur.data(), (int)cur.size(), dp.data(), (int)maxdig, &nd, ln.data()));
+    digits.erase(digits.begin() + nd, digits.end());
+    ln.resize(nd);
+    return ln;
+  }
+  // multiply by the product of a set of chain primes (DoubleCRT::Op(ZZ, MulFun) with that ZZ, src/DoubleCRT.cpp:339-361)
+  DoubleCRT& multiplyByPrimes(const IndexSet& f) {
+    auto idx = set_.vec(), fi = f.vec();
+    if (!idx.empty() && !fi.empty()) { hb_poly* d[1] = {p_}; check(hb_scale_by_primes(d, 1, idx.data(), (int)idx.size(), fi.data(), (int)fi.size(), 0)); }
+    return *this;
+  }
+  // evaluation rows given directly (what DoubleCRT::randomize fills, src/DoubleCRT.cpp:1258-1378): dense [nprimes][N]
+  static DoubleCRT fromRows(const Context& ctx, const IndexSet& s, const std::vector<uint64_t>& dense) {
+    DoubleCRT r(ctx, s);
+    auto idx = s.vec();
+    if (!idx.empty()) check(hb_poly_upload(r.p_, idx.data(), (int)idx.size(), dense.data()));
+    check(hb_ctx_sync(ctx.handle()));
+    return r;
+  }
   // toPoly (src/DoubleCRT.cpp:925-1113): N x L little-endian two's-complement limbs
   std::vector<uint64_t> toPoly(const IndexSet& s, bool positive, int& L) const {
     auto idx = (set_ & s).vec();

@@ -1,0 +1,127 @@
+// End-to-end C++ test of the helib::Ctxt mirror (include/helib_b200_ctxt.hpp): BGV encrypt -> multiplyBy
+// (noise-driven prime-set choice through getSet4Size, mod-switch, tensor, relinearise with device-computed
+// norms) -> decrypt == plaintext product.  This is the reference's own test style (encrypt, operate, decrypt,
+// compare with a plaintext mirror: tests/TestCtxt.cpp:110-142, tests/GTestGeneral.cpp:298-353).
+// Exit codes: 0 ok, 3 no CUDA device, 1 failure.
+#include <cstdio>
+#include <random>
+
+#include "helib_b200_ctxt.hpp"
+
+using namespace hb;
+typedef unsigned __int128 u128;
+
+static std::vector<long> sample_ternary(std::mt19937_64& g, long n) { std::vector<long> v(n); for (auto& x : v) x = (long)(g() % 3) - 1; return v; }
+static std::vector<long> sample_gauss(std::mt19937_64& g, long n, double sigma) { std::normal_distribution<double> d(0, sigma); std::vector<long> v(n); for (auto& x : v) x = std::lround(d(g)); return v; }
+static DoubleCRT random_rows(const Context& ctx, const IndexSet& s, std::mt19937_64& g) {
+  const long N = ctx.getPhiM();
+  std::vector<uint64_t> dense((size_t)ctx.numPrimes() * N, 0);
+  for (long i : s) for (long k = 0; k < N; k++) dense[(size_t)i * N + k] = g() % (uint64_t)ctx.ithPrime(i);
+  return DoubleCRT::fromRows(ctx, s, dense);
+}
+
+int main() {
+  if (hb_device_count() <= 0) { std::printf("no CUDA device\n"); return 3; }
+  try {
+    const long m = 8192, p = 257;
+    Context ctx(m, p, 1, /*bits=*/300, /*c=*/2);
+    const long N = ctx.getPhiM();
+    std::mt19937_64 gen(20260922);
+    const double sigma = 3.2;
+    const IndexSet allq = ctx.getCtxtPrimes() | ctx.getSpecialPrimes();
+    KeyInfo pk; pk.context = &ctx; pk.ckks = false; pk.scale = 10.0; pk.hwt = 0;
+    pk.skBound = pk.scale * std::sqrt(double(N) * 2.0 / 3.0);    // high-probability bound on ||s||_canon for ternary s
+    // secret key and the s^2 -> s key-switching matrix (SecKey::GenKeySWmatrix, src/keys.cpp:1159-1256)
+    std::vector<long> s = sample_ternary(gen, N);
+    DoubleCRT S(s, ctx, allq);
+    DoubleCRT fromKey(S); fromKey *= S;                           // s^2
+    KeySwitch W; W.fromKey = SKHandle(2, 1, 0); W.toKeyID = 0; W.ptxtSpace = p;
+    fromKey.multiplyByPrimes(ctx.getSpecialPrimes());             // P * s^2
+    for (size_t i = 0; i < ctx.getDigits().size(); i++) {
+      W.a.push_back(random_rows(ctx, allq, gen));
+      std::vector<long> e = sample_gauss(gen, N, sigma);
+      DoubleCRT b(e, ctx, allq); b *= p;                           // RLWE1: b = p*e - a*s  (src/keys.cpp:40-72)
+      DoubleCRT t(W.a.back()); t *= S; b -= t;
+      b += fromKey;
+      W.b.push_back(b);
+      fromKey.multiplyByPrimes(ctx.getDigit(i));
+    }
+    W.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)));
+    pk.keySwitching.push_back(W);
+
+    auto encrypt = [&](const std::vector<long>& msg) {
+      Ctxt c(pk, p);
+      c.primeSet = ctx.getCtxtPrimes();
+      unsigned long Qp = 1;
+      for (long i : c.primeSet) Qp = (unsigned long)(((u128)Qp * (unsigned long)(ctx.ithPrime(i) % p)) % (unsigned long)p);
+      std::vector<long> e = sample_gauss(gen, N, sigma), pt(N);
+      for (long k = 0; k < N; k++) pt[k] = p * e[k] + (long)(((u128)Qp * (unsigned long)msg[k]) % (unsigned long)p);   // decrypts to Q*m (src/keys.cpp:1408-1417)
+      DoubleCRT c1 = random_rows(ctx, c.primeSet, gen);
+      DoubleCRT c0(pt, ctx, c.primeSet);
+      DoubleCRT t(c1); t.Mul(S, false); c0 -= t;
+      c.parts.emplace_back(c0, SKHandle());
+      c.parts.emplace_back(c1, SKHandle(1, 1, 0));
+      c.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)) + pk.noiseBoundForUniform(p / 2.0, N));
+      return c;
+    };
+    auto decrypt = [&](const Ctxt& c, double* maxabs) {   // SecKey::Decrypt, src/keys.cpp:1327-1420
+      DoubleCRT acc(ctx, c.primeSet);
+      for (auto& part : c.parts) {
+        if (part.skHandle.isOne()) { acc += part.dcrt; continue; }
+        DoubleCRT key(S); key.removePrimes(allq / c.primeSet);
+        if (part.skHandle.powerOfS == 2) key *= key;
+        key *= part.dcrt; acc += key;
+      }
+      int L; std::vector<uint64_t> limbs = acc.toPoly(c.primeSet, false, L);
+      unsigned long f = 1;
+      for (long i : c.primeSet) f = (unsigned long)(((u128)f * (unsigned long)(ctx.ithPrime(i) % p)) % (unsigned long)p);
+      f = (unsigned long)(((u128)f * (unsigned long)c.intFactor) % (unsigned long)p);
+      unsigned long finv = 1; for (unsigned long x = 1; x < (unsigned long)p; x++) if (x * f % p == 1) finv = x;
+      std::vector<long> out(N);
+      double mx = 0;
+      for (long k = 0; k < N; k++) {
+        // value mod p of a two's-complement L-limb integer; |value| as double for the noise check
+        bool neg = limbs[(size_t)k * L + L - 1] >> 63;
+        unsigned long r = 0; double mag = 0;
+        for (int l = L - 1; l >= 0; l--) { uint64_t w = limbs[(size_t)k * L + l]; if (neg) w = ~w; r = (unsigned long)((((u128)r << 64) | w) % (unsigned long)p); mag = mag * 18446744073709551616.0 + (double)w; }
+        if (neg) { r = (unsigned long)((p - (r + 1) % p) % p); mag += 1; }
+        mx = std::max(mx, mag);
+        out[k] = (long)(r * finv % p);
+      }
+      if (maxabs) *maxabs = mx;
+      return out;
+    };
+
+    std::vector<long> ma(N), mb(N);
+    for (long k = 0; k < N; k++) { ma[k] = (long)(gen() % p); mb[k] = (long)(gen() % p); }
+    Ctxt ca = encrypt(ma), cb = encrypt(mb);
+    { std::vector<long> chk = decrypt(ca, nullptr); if (chk != ma) { std::printf("fresh decrypt mismatch\n"); return 1; } }
+    const long before = ca.primeSet.card();
+    ca.multiplyBy(cb);
+    if (!ca.inCanonicalForm()) { std::printf("result not canonical\n"); return 1; }
+    if (!(ctx.getSpecialPrimes() <= ca.primeSet)) { std::printf("special primes missing after reLinearize\n"); return 1; }
+    const long common = ca.lastCommonPrimeSet.card();
+    if (common >= before || common < 1) { std::printf("getSet4Size did not drop primes (%ld -> %ld)\n", before, common); return 1; }
+    double maxabs = 0;
+    std::vector<long> got = decrypt(ca, &maxabs);
+    // plaintext mirror: negacyclic product mod p (spot-check 64 coefficients to keep it fast)
+    for (long t = 0; t < 64; t++) {
+      long k = (t * 131) % N; long acc = 0;
+      for (long i = 0; i < N; i++) { long j = k - i; long term = j >= 0 ? ma[i] * mb[j] : -(ma[i] * mb[j + N]); acc = (acc + term) % p; }
+      acc = ((acc % p) + p) % p;
+      if (got[k] != acc) { std::printf("product mismatch at %ld: %ld vs %ld\n", k, got[k], acc); return 1; }
+    }
+    const double est = ca.noiseBound.ln() / std::log(2.0), act = std::log2(std::max(maxabs, 1.0));
+    if (act > est) { std::printf("noise estimate too small: 2^%.1f < actual 2^%.1f\n", est, act); return 1; }
+    // drop the special primes again (cleanUp path) and decrypt once more
+    ca.dropSmallAndSpecialPrimes();
+    if (decrypt(ca, nullptr) != got) { std::printf("mod-down changed the plaintext\n"); return 1; }
+    ctx.sync();
+    std::printf("ctxt OK: primes %ld -> common %ld, log2 noise est %.1f >= actual %.1f, KS-noise-ratio %.3g, mod-switch ratio %.3g\n",
+                before, common, est, act, ca.lastKSNoiseRatio, ca.lastModSwitchRatio);
+    return 0;
+  } catch (const std::exception& e) {
+    std::printf("exception: %s\n", e.what());
+    return 1;
+  }
+}

@@ -9,13 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
 
 
-def build_exe():
-    src = os.path.join(ROOT, "tests", "cpp", "test_shim.cpp")
-    deps = [src, os.path.join(ROOT, "include", "helib_b200_doublecrt.hpp"), os.path.join(ROOT, "helib_b200", "libhelib_b200.so")]
-    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
+def build_exe(name="test_shim"):
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", name)
+    deps = [src, os.path.join(ROOT, "include", "helib_b200_doublecrt.hpp"), os.path.join(ROOT, "include", "helib_b200_ctxt.hpp"),
+            os.path.join(ROOT, "helib_b200", "libhelib_b200.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
                                "-L" + os.path.join(ROOT, "helib_b200"), "-lhelib_b200", "-Wl,-rpath," + os.path.join(ROOT, "helib_b200")])
-    return EXE
+    return exe
 
 
 def test_shim_compiles_links_and_refuses_without_gpu():
@@ -33,3 +35,18 @@ def test_shim_runs_on_gpu():
     exe = build_exe()
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "shim OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_ctxt_mirror_compiles_and_refuses_without_gpu():
+    from helib_b200 import load_library
+    exe = build_exe("test_ctxt")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == (3 if load_library().hb_device_count() <= 0 else 0), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_ctxt_multiplyBy_decrypts_on_gpu():
+    """helib::Ctxt mirror: BGV encrypt -> multiplyBy (noise-driven prime sets, device norms) -> decrypt == product."""
+    exe = build_exe("test_ctxt")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ctxt OK" in r.stdout, r.stdout + r.stderr
