@@ -108,6 +108,8 @@ class Ctxt {
   Ctxt& operator=(const Ctxt& o) {
     parts = o.parts; primeSet = o.primeSet; ptxtSpace = o.ptxtSpace; noiseBound = o.noiseBound;
     intFactor = o.intFactor; ratFactor = o.ratFactor; ptxtMag = o.ptxtMag;
+    if (o.lastKSNoiseRatio != 0) lastKSNoiseRatio = o.lastKSNoiseRatio;
+    if (o.lastModSwitchRatio != 0) lastModSwitchRatio = o.lastModSwitchRatio;
     return *this;
   }
   Ctxt(const Ctxt&) = default;
@@ -305,7 +307,7 @@ class Ctxt {
     std::vector<int32_t> out(context.numPrimes()); int nout = 0;
     check(hb_chain_set4size(context.chain(), lo, hi, f1.data(), (int)f1.size(), f2.data(), (int)f2.size(), isCKKS() ? 1 : 0, out.data(), &nout));
     IndexSet common(out.begin(), out.begin() + nout);
-    lastCommonPrimeSet = common;
+    lastCommonPrimeSet = common; lastLo = lo; lastHi = hi;
     bringToSet(common);
     other.bringToSet(common);
     Ctxt tmp(pubKey, ptxtSpace);
@@ -319,7 +321,7 @@ class Ctxt {
     reLinearize();
   }
   // statistics the reference records through HELIB_STATS_UPDATE (src/Ctxt.cpp:537,835)
-  double lastModSwitchRatio = 0, lastKSNoiseRatio = 0;
+  double lastModSwitchRatio = 0, lastKSNoiseRatio = 0, lastLo = 0, lastHi = 0;
   IndexSet lastCommonPrimeSet;
 };
 

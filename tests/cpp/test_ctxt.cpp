@@ -92,33 +92,53 @@ int main() {
       return out;
     };
 
-    std::vector<long> ma(N), mb(N);
-    for (long k = 0; k < N; k++) { ma[k] = (long)(gen() % p); mb[k] = (long)(gen() % p); }
-    Ctxt ca = encrypt(ma), cb = encrypt(mb);
+    std::vector<long> ma(N), mb(N), mc(N);
+    for (long k = 0; k < N; k++) { ma[k] = (long)(gen() % p); mb[k] = (long)(gen() % p); mc[k] = (long)(gen() % p); }
+    Ctxt ca = encrypt(ma), cb = encrypt(mb), cc = encrypt(mc);
     { std::vector<long> chk = decrypt(ca, nullptr); if (chk != ma) { std::printf("fresh decrypt mismatch\n"); return 1; } }
-    const long before = ca.primeSet.card();
+    auto negacyclic_at = [&](const std::vector<long>& x, const std::vector<long>& y, long k) {
+      long acc = 0;
+      for (long i = 0; i < N; i++) { long j = k - i; long term = j >= 0 ? x[i] * y[j] : -(x[i] * y[j + N]); acc = (acc + term) % p; }
+      return ((acc % p) + p) % p;
+    };
+    const double ln2 = std::log(2.0);
+    double logq0 = pk.logOfProduct(ca.primeSet);
+    // ---- first product: fresh operands, getSet4Size picks a set inside [lo, hi] (may even add small primes)
     ca.multiplyBy(cb);
     if (!ca.inCanonicalForm()) { std::printf("result not canonical\n"); return 1; }
     if (!(ctx.getSpecialPrimes() <= ca.primeSet)) { std::printf("special primes missing after reLinearize\n"); return 1; }
-    const long common = ca.lastCommonPrimeSet.card();
-    if (common >= before || common < 1) { std::printf("getSet4Size did not drop primes (%ld -> %ld)\n", before, common); return 1; }
+    double logq1 = pk.logOfProduct(ca.lastCommonPrimeSet);
+    if (logq1 > ca.lastHi + 1e-9 || logq1 < ca.lastLo - ln2 - 1e-9) { std::printf("common set size %.1f outside [%.1f, %.1f] bits\n", logq1 / ln2, ca.lastLo / ln2, ca.lastHi / ln2); return 1; }
+    if (!(ca.lastCommonPrimeSet & ctx.getCtxtPrimes()).isInterval()) { std::printf("common ctxt primes are not an interval\n"); return 1; }
     double maxabs = 0;
-    std::vector<long> got = decrypt(ca, &maxabs);
-    // plaintext mirror: negacyclic product mod p (spot-check 64 coefficients to keep it fast)
-    for (long t = 0; t < 64; t++) {
-      long k = (t * 131) % N; long acc = 0;
-      for (long i = 0; i < N; i++) { long j = k - i; long term = j >= 0 ? ma[i] * mb[j] : -(ma[i] * mb[j + N]); acc = (acc + term) % p; }
-      acc = ((acc % p) + p) % p;
-      if (got[k] != acc) { std::printf("product mismatch at %ld: %ld vs %ld\n", k, got[k], acc); return 1; }
+    std::vector<long> ab_full = decrypt(ca, &maxabs);
+    std::vector<long> ab(N);
+    for (long k = 0; k < N; k++) ab[k] = ab_full[k];
+    for (long t = 0; t < 48; t++) {
+      long k = (t * 131) % N;
+      if (ab[k] != negacyclic_at(ma, mb, k)) { std::printf("product mismatch at %ld\n", k); return 1; }
     }
-    const double est = ca.noiseBound.ln() / std::log(2.0), act = std::log2(std::max(maxabs, 1.0));
+    double est = ca.noiseBound.ln() / ln2, act = std::log2(std::max(maxabs, 1.0));
     if (act > est) { std::printf("noise estimate too small: 2^%.1f < actual 2^%.1f\n", est, act); return 1; }
+    // ---- second product: the noisy product times a fresh ciphertext must shrink the modulus
+    ca.multiplyBy(cc);
+    double logq2 = pk.logOfProduct(ca.lastCommonPrimeSet);
+    if (logq2 >= logq1) { std::printf("second product did not shrink the modulus (%.1f -> %.1f bits)\n", logq1 / ln2, logq2 / ln2); return 1; }
+    std::vector<long> abc = decrypt(ca, &maxabs);
+    for (long t = 0; t < 32; t++) {
+      long k = (t * 257 + 5) % N;
+      if (abc[k] != negacyclic_at(ab, mc, k)) { std::printf("second product mismatch at %ld\n", k); return 1; }
+    }
+    est = ca.noiseBound.ln() / ln2; act = std::log2(std::max(maxabs, 1.0));
+    if (act > est) { std::printf("noise estimate too small after 2 products: 2^%.1f < actual 2^%.1f\n", est, act); return 1; }
     // drop the special primes again (cleanUp path) and decrypt once more
     ca.dropSmallAndSpecialPrimes();
-    if (decrypt(ca, nullptr) != got) { std::printf("mod-down changed the plaintext\n"); return 1; }
+    if (decrypt(ca, nullptr) != abc) { std::printf("mod-down changed the plaintext\n"); return 1; }
+    const long before = ctx.getCtxtPrimes().card(), common = ca.lastCommonPrimeSet.card();
+    const double logq_before = logq0, logq_common = logq2;
     ctx.sync();
-    std::printf("ctxt OK: primes %ld -> common %ld, log2 noise est %.1f >= actual %.1f, KS-noise-ratio %.3g, mod-switch ratio %.3g\n",
-                before, common, est, act, ca.lastKSNoiseRatio, ca.lastModSwitchRatio);
+    std::printf("ctxt OK: %ld primes (%.0f bits) -> common %ld primes (%.0f bits), log2 noise est %.1f >= actual %.1f, KS-noise-ratio %.3g, mod-switch ratio %.3g\n",
+                before, logq_before / std::log(2.0), common, logq_common / std::log(2.0), est, act, ca.lastKSNoiseRatio, ca.lastModSwitchRatio);
     return 0;
   } catch (const std::exception& e) {
     std::printf("exception: %s\n", e.what());
