@@ -721,6 +721,9 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
   size_t o_fs = put(fshift.data(), sizeof(int) * n);
   size_t o_t = put(t.data(), 8 * n), o_ts = put(t_s.data(), 8 * n), o_tn = put(tn.data(), 8 * n), o_tns = put(tn_s.data(), 8 * n);
   size_t o_fm = put(fmul.data(), 8 * n), o_c = put(cmat.data(), 8 * std::max<size_t>(cmat.size(), 1));
+  std::vector<u64> c30(cmat.size());
+  for (size_t i = 0; i < cmat.size(); i++) c30[i] = (cmat[i] & 0x3fffffffULL) | ((cmat[i] >> 30) << 32);
+  size_t o_c30 = put(c30.data(), 8 * c30.size());
   size_t o_nq = put(negQ.data(), 8 * std::max(nt, 1)), o_qm = put(Qmod.data(), 8 * std::max(nt, 1)), o_cp = put(cp.data(), 8 * n);
   size_t o_Q = put(Q.data(), 8 * L), o_Qh = put(Qhalf.data(), 8 * L), o_Qj = put(Qj.data(), 8 * (size_t)n * L);
   HB_TRY(ctx_alloc(c, &E.blob, blob.size()));
@@ -729,7 +732,7 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
   H.src_prime = (const int*)(B + o_src); H.tgt_prime = (const int*)(B + o_tgt); H.fshift = (const int*)(B + o_fs);
   E.d_t = (const u64*)(B + o_t); E.d_t_s = (const u64*)(B + o_ts);
   H.tn = (const u64*)(B + o_tn); H.tn_s = (const u64*)(B + o_tns); H.fmul = (const u64*)(B + o_fm);
-  H.c = (const u64*)(B + o_c); H.negQ = (const u64*)(B + o_nq); H.Qmod = (const u64*)(B + o_qm); H.cp = (const u64*)(B + o_cp);
+  H.c = (const u64*)(B + o_c); H.c30 = (const u64*)(B + o_c30); H.negQ = (const u64*)(B + o_nq); H.Qmod = (const u64*)(B + o_qm); H.cp = (const u64*)(B + o_cp);
   H.Q = (const u64*)(B + o_Q); H.Qhalf = (const u64*)(B + o_Qh); H.Qj = (const u64*)(B + o_Qj);
   HB_TRY(ctx_alloc(c, (void**)&E.d, sizeof(HbConvDev)));
   HB_CUDA(cudaMemcpy(E.d, &H, sizeof(HbConvDev), cudaMemcpyHostToDevice));
