@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     for (int l = 0; l < 16; l++) a[l] = s[(size_t)(16 * x + l) << 8];
     if (J.src_is_y) {   // uniform per launch: no transform, just stage the tile
 #pragma unroll
-      for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = hb_pack30(a[l]);
+      for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
       continue;
     }
     {
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     }
     const u64 t = cv->tn[j], ts = cv->tn_s[j];
 #pragma unroll
-    for (int r = 0; r < 16; r++) Yj[HB1_RS * r + x] = hb_pack30(hb_mul_shoup(a[r], t, ts, q));   // 30-bit halves for the carry-free MACs
+    for (int r = 0; r < 16; r++) Yj[HB1_RS * r + x] = hb_mul_shoup(a[r], t, ts, q);
   }
   __syncthreads();
   // ---- v (multiple of Q to subtract, incl. the BGV correction) per coefficient
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     const int cc = e >> 8, i1 = e & 255;
     double* fr = J.frac[blockIdx.y];
     double f;
-    Vb[e] = hb_conv_v<true>(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
+    Vb[e] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
     if (fr) fr[((size_t)i1 << 8) + c0 + cc] = f;
   }
   __syncthreads();
@@ -539,50 +539,25 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     const u64* ct = cv->c + (size_t)t * n;
     u64 a[16];
     {
-      // x mod q_t = sum_j y_j*c_{j,t} + |v|*(+-Q mod q_t): both factors are < 2^60 and kept as 30-bit halves, so the
-      // four partial products of a term are < 2^60 each and accumulate in plain 64-bit registers (IMAD.WIDE with
-      // accumulate, no carry chain) for up to 15 terms; one fold + one lazy reduction per coefficient.
       const u64 negq = cv->negQ[t], posq = cv->Qmod[t];
-      const u64* c30 = cv->c30 + (size_t)t * n;
 #pragma unroll
-      for (int h = 0; h < 4; h++) {   // four groups of 4 coefficients: 16 accumulator registers pairs live
-        u64 ll[4], lh[4], hl[4], hh[4], fhi[4], flo[4];
+      for (int h = 0; h < 2; h++) {   // two halves of 8 coefficients: 32 accumulator registers live
+        u64 ahi[8], alo[8];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const i64 v = Vb[c * 256 + 16 * (4 * h + r) + x];
+        for (int r = 0; r < 8; r++) {
+          const i64 v = Vb[c * 256 + 16 * (8 * h + r) + x];
           const u64 m = v >= 0 ? (u64)v : (u64)(-v);
           const u64 f = v >= 0 ? negq : posq;
-          const unsigned ml = (unsigned)(m & 0x3fffffffULL), mh = (unsigned)(m >> 30), fl = (unsigned)(f & 0x3fffffffULL), fh = (unsigned)(f >> 30);
-          ll[r] = (u64)ml * fl; lh[r] = (u64)ml * fh; hl[r] = (u64)mh * fl; hh[r] = (u64)mh * fh;
-          fhi[r] = 0; flo[r] = 0;
+          alo[r] = m * f; ahi[r] = __umul64hi(m, f);
         }
-        int terms = 1;
         for (int j = 0; j < n; j++) {
-          const u64 cj = c30[j];
-          const unsigned cl = (unsigned)cj, ch = (unsigned)(cj >> 32);
-          const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x + HB1_RS * 4 * h;
+          const u64 cj = ct[j];
+          const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x + HB1_RS * 8 * h;
 #pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const u64 yp = Yj[HB1_RS * r];
-            const unsigned yl = (unsigned)yp, yh = (unsigned)(yp >> 32);
-            ll[r] += (u64)yl * cl; lh[r] += (u64)yl * ch; hl[r] += (u64)yh * cl; hh[r] += (u64)yh * ch;
-          }
-          if (++terms == 15 || j == n - 1) {   // fold: value += ll + (lh + hl) * 2^30 + hh * 2^60
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-              u64 lo = flo[r], hi = fhi[r], tmp;
-              tmp = lo + ll[r]; hi += tmp < lo; lo = tmp;
-              tmp = lo + (lh[r] << 30); hi += (lh[r] >> 34) + (tmp < lo); lo = tmp;
-              tmp = lo + (hl[r] << 30); hi += (hl[r] >> 34) + (tmp < lo); lo = tmp;
-              tmp = lo + (hh[r] << 60); hi += (hh[r] >> 4) + (tmp < lo); lo = tmp;
-              flo[r] = lo; fhi[r] = hi;
-              ll[r] = lh[r] = hl[r] = hh[r] = 0;
-            }
-            terms = 0;
-          }
+          for (int r = 0; r < 8; r++) hb1_mac128(ahi[r], alo[r], Yj[HB1_RS * r], cj);
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++) a[4 * h + r] = hb_reduce128_lazy(fhi[r], flo[r], P);   // [0,4q): fine for the CT network
+        for (int r = 0; r < 8; r++) a[8 * h + r] = hb_reduce128_lazy(ahi[r], alo[r], P);   // [0,4q): fine for the CT network
       }
     }
     {
