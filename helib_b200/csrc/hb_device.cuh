@@ -186,7 +186,6 @@ struct HbConvDev {
   const int* fshift;      // [n]  b_j - 1
   const int* tgt_prime;   // [nt]
   const u64* c;           // [nt][n]  (Q/q_j) mod q_t
-  const u64* c30;         // [nt][n]  the same constants split in 30-bit halves: lo30 | hi30 << 32
   const u64* negQ;        // [nt]  (-Q) mod q_t
   const u64* Qmod;        // [nt]  Q mod q_t
   u64 p, p_c64, p_c64_s, p_one_s;  // plaintext modulus (has_p) as a pseudo-prime for hb_reduce128
@@ -214,11 +213,12 @@ struct HbCrtJob {            // DoubleCRT::toPoly: exact balanced integer per co
   int N, Lout, positive;
   const u64* src;            // coefficient-form rows (after full inverse transform incl. N^-1 ... see k_crt)
   u64* out;                  // [N][Lout] two's complement limbs
+  u64 factor, factor_s;      // k_crt_modp: result multiplier mod p (+Shoup wrt p)
 };
 
 enum {
   HB_PW_ADD = 0, HB_PW_SUB, HB_PW_MUL, HB_PW_NEG, HB_PW_SCALE, HB_PW_SUBSCALE, HB_PW_ZERO, HB_PW_COPY,
-  HB_PW_TENSOR, HB_PW_AUTOMORPH
+  HB_PW_TENSOR, HB_PW_AUTOMORPH, HB_PW_MULADD
 };
 
 struct HbPwJob {
@@ -471,7 +471,7 @@ __device__ HB_NOINLINE int hb_crt_exact(const HbConvDev* cv, const u64* y, int y
 // the rounding boundary.  With has_p: also the BGV correction of DoubleCRT::scaleDownToSet
 // (src/DoubleCRT.cpp:1485-1511) folded into the returned multiple of Q.
 template <bool PACKED = false>
-__device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int ystride, u64* stats, double* frac = nullptr) {
+__device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int ystride, u64* stats, double* frac = nullptr, bool bgv = true) {
   const int n = cv->n;
   u64 shi = 0, slo = 0;
   for (int j = 0; j < n; j++) {
@@ -492,7 +492,7 @@ __device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int 
     v = hb_crt_exact(cv, y, ystride, &sign, nullptr, 0, 0, PACKED ? 1 : 0);
     if (stats) atomicAdd(stats, 1ULL);
   }
-  if (cv->has_p) {
+  if (bgv && cv->has_p) {
     const u64 p = cv->p;
     u64 hi = 0, lo = 0;
     for (int j = 0; j < n; j++) { u64 yj = y[(size_t)j * ystride]; if (PACKED) yj = hb_unpack30(yj); hb_mac128(hi, lo, yj, cv->cp[j]); }
@@ -597,6 +597,60 @@ __global__ void __launch_bounds__(HB_THREADS) k_crt(const HbPrimeDev* __restrict
   hb_crt_exact(cv, y, 1, &sign, J.out + k * J.Lout, J.Lout, J.positive);
 }
 
+// Tail of SecKey::Decrypt (src/keys.cpp:1381-1399): the balanced integer x = toPoly(ptxt) is never materialised;
+// out[k] = factor * (x mod p) mod p in [0,p), from x = sum_j y_j*(Q/q_j) - v*Q with the exact v.
+__global__ void __launch_bounds__(HB_THREADS) k_crt_modp(const HbPrimeDev* __restrict__ primes, HbCrtJob J, HbCrtTabs tabs) {
+  const HbConvDev* cv = J.cv;
+  const int n = cv->n;
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (size_t)J.N) return;
+  u64 y[HB_MAXROWS];
+  for (int j = 0; j < n; j++) {
+    int pi = cv->src_prime[j];
+    y[j] = hb_mul_shoup(J.src[(size_t)pi * J.N + k], tabs.t[j], tabs.t_s[j], primes[pi].q);
+  }
+  const i64 v = hb_conv_v(cv, y, 1, nullptr, nullptr, false);
+  u64 hi = 0, lo = 0;
+  for (int j = 0; j < n; j++) hb_mac128(hi, lo, y[j], cv->cp[j]);
+  hb_mac128(hi, lo, (u64)v, cv->negQ_p);
+  const u64 u = hb_reduce128(hi, lo, cv->p, cv->p_c64, cv->p_c64_s, cv->p_one_s);
+  J.out[k] = hb_mul_shoup(u, J.factor, J.factor_s, cv->p);
+}
+
+// DoubleCRT(const zzX&/ZZX&, context, s) -> FFT(poly, s) (src/DoubleCRT.cpp:68-105): the per-prime reduction of the
+// coefficients (src/CModulus.cpp:453-457, timer FFT_remainder) done on the device from ONE copy of the polynomial.
+struct HbFromJob {
+  u64 N; int L, nitems;
+  HbRows rows;
+  const u64* src[HB_MAXB];   // [N] signed 64-bit coefficients (L == 0) or [N][L] two's-complement limbs
+  u64* dst[HB_MAXB];
+};
+__global__ void __launch_bounds__(HB_THREADS) k_from_coeffs(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT HbFromJob J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const u64 q = P.q;
+  const size_t N = (size_t)J.N;
+  const int it = blockIdx.z, L = J.L;
+  u64 top = 0;                       // 2^(64 L) mod q: what a negative two's-complement value is short of
+  if (L > 0) { top = 1; for (int l = 0; l < L; l++) top = hb_reduce128(top, 0, P); }
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+    u64 r;
+    if (L == 0) {
+      const i64 c = (i64)J.src[it][k];
+      const u64 a = c < 0 ? 0 - (u64)c : (u64)c;
+      r = a - __umul64hi(a, P.one_s) * q;
+      if (r >= q) r -= q;
+      if (c < 0 && r) r = q - r;
+    } else {
+      const u64* x = J.src[it] + k * (size_t)L;
+      r = 0;
+      for (int l = L - 1; l >= 0; l--) r = hb_reduce128(r, x[l], P);
+      if (x[L - 1] >> 63) r = hb_submod(r, top, q);
+    }
+    J.dst[it][(size_t)pi * N + k] = r;
+  }
+}
+
 // Row-wise pointwise operations: DoubleCRT::Op<Add/Sub/Mul>, Negate, operator/=, Op(ZZ)
 // (src/DoubleCRT.cpp:216-384,1122-1139), addPrimesAndScale's scaling (src/DoubleCRT.cpp:620-636),
 // Ctxt::tensorProduct (src/Ctxt.cpp:1563-1608), DoubleCRT::automorph (src/DoubleCRT.cpp:1160-1202).
@@ -628,6 +682,11 @@ __global__ void __launch_bounds__(HB_THREADS) k_pointwise(const HbPrimeDev* __re
         hb_mac128(hi, lo, a1, b0);
         J.dst1[it][o] = hb_reduce128(hi, lo, P);
         J.dst2[it][o] = hb_mulmod(a1, b1, P);
+      } break;
+      case HB_PW_MULADD: {   // dst += a*b (one read-modify-write pass instead of a product temp + an add)
+        u64 hi = 0, lo = J.dst[it][o];
+        hb_mac128(hi, lo, J.a[it][o], J.b[it][o]);
+        J.dst[it][o] = hb_reduce128(hi, lo, P);
       } break;
       case HB_PW_AUTOMORPH: {
         // new[j] = old[idx(rep(j)*k mod m)], rep(j) = 2j+1, idx(r) = (r-1)/2  (power-of-two m)

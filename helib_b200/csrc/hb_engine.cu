@@ -635,8 +635,8 @@ static int launch_pw(hb_ctx* c, const PwArgs& A, int nitems, const int32_t* idx,
     }
     unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
     dim3 grid(gx, nr, nitems);
-    static const int rw[] = {3, 3, 3, 2, 2, 3, 1, 2, 7, 2};  // rows moved per element, by op
-    static const char* nm[] = {"k_pw_add", "k_pw_sub", "k_pw_mul", "k_pw_neg", "k_pw_scale", "k_pw_subscale", "k_pw_zero", "k_pw_copy", "k_pw_tensor", "k_pw_automorph"};
+    static const int rw[] = {3, 3, 3, 2, 2, 3, 1, 2, 7, 2, 4};  // rows moved per element, by op
+    static const char* nm[] = {"k_pw_add", "k_pw_sub", "k_pw_mul", "k_pw_neg", "k_pw_scale", "k_pw_subscale", "k_pw_zero", "k_pw_copy", "k_pw_tensor", "k_pw_automorph", "k_pw_muladd"};
     pre_launch(c);
     HB_LAUNCH(k_pointwise, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
     HB_TRY(post_launch(c, nm[A.op], (u64)rw[A.op] * nr * nitems * c->N * 8));
@@ -721,9 +721,6 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
   size_t o_fs = put(fshift.data(), sizeof(int) * n);
   size_t o_t = put(t.data(), 8 * n), o_ts = put(t_s.data(), 8 * n), o_tn = put(tn.data(), 8 * n), o_tns = put(tn_s.data(), 8 * n);
   size_t o_fm = put(fmul.data(), 8 * n), o_c = put(cmat.data(), 8 * std::max<size_t>(cmat.size(), 1));
-  std::vector<u64> c30(cmat.size());
-  for (size_t i = 0; i < cmat.size(); i++) c30[i] = (cmat[i] & 0x3fffffffULL) | ((cmat[i] >> 30) << 32);
-  size_t o_c30 = put(c30.data(), 8 * c30.size());
   size_t o_nq = put(negQ.data(), 8 * std::max(nt, 1)), o_qm = put(Qmod.data(), 8 * std::max(nt, 1)), o_cp = put(cp.data(), 8 * n);
   size_t o_Q = put(Q.data(), 8 * L), o_Qh = put(Qhalf.data(), 8 * L), o_Qj = put(Qj.data(), 8 * (size_t)n * L);
   HB_TRY(ctx_alloc(c, &E.blob, blob.size()));
@@ -732,7 +729,7 @@ static int get_conv(hb_ctx* c, const int32_t* src, int n, const int32_t* tgt, in
   H.src_prime = (const int*)(B + o_src); H.tgt_prime = (const int*)(B + o_tgt); H.fshift = (const int*)(B + o_fs);
   E.d_t = (const u64*)(B + o_t); E.d_t_s = (const u64*)(B + o_ts);
   H.tn = (const u64*)(B + o_tn); H.tn_s = (const u64*)(B + o_tns); H.fmul = (const u64*)(B + o_fm);
-  H.c = (const u64*)(B + o_c); H.c30 = (const u64*)(B + o_c30); H.negQ = (const u64*)(B + o_nq); H.Qmod = (const u64*)(B + o_qm); H.cp = (const u64*)(B + o_cp);
+  H.c = (const u64*)(B + o_c); H.negQ = (const u64*)(B + o_nq); H.Qmod = (const u64*)(B + o_qm); H.cp = (const u64*)(B + o_cp);
   H.Q = (const u64*)(B + o_Q); H.Qhalf = (const u64*)(B + o_Qh); H.Qj = (const u64*)(B + o_Qj);
   HB_TRY(ctx_alloc(c, (void**)&E.d, sizeof(HbConvDev)));
   HB_CUDA(cudaMemcpy(E.d, &H, sizeof(HbConvDev), cudaMemcpyHostToDevice));
@@ -1212,6 +1209,85 @@ extern "C" int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, u
   if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_to_poly: copy failed: %s", cudaGetErrorString(e)); }
   cudaFree(d_out);
   return r;
+}
+
+extern "C" int hb_to_poly_mod_p(hb_poly* p, const int32_t* idx, int n, uint64_t ptxt_space, uint64_t factor, int64_t* out) {
+  if (!p || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly_mod_p: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_to_poly_mod_p", true));
+  if (ptxt_space < 2) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly_mod_p: ptxt_space must be >= 2");
+  if (factor >= ptxt_space) return hb_fail(HB_ERR_BAD_ARG, "hb_to_poly_mod_p: factor not reduced mod ptxt_space");
+  if (n == 0) { memset(out, 0, sizeof(int64_t) * c->N); return HB_OK; }
+  ConvEntry* E; HB_TRY(get_conv(c, idx, n, nullptr, 0, ptxt_space, &E));
+  u64* P[1] = {p->d};
+  const u64* coef;
+  if (c->gen.on) { u64* A[1] = {c->gen.cA}; HB_TRY(gen_inv(c, (const u64* const*)P, A, 1, idx, n)); coef = c->gen.cA; }
+  else {
+    HB_TRY(ctx_scratch(c));
+    u64* tA[1] = {c->tmpA}; u64* tB[1] = {c->tmpB};
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, 1, idx, n, 0, nullptr));
+    HB_TRY(launch_cols(c, -1, (const u64* const*)tA, tB, 1, idx, n));
+    coef = c->tmpB;
+  }
+  u64* d_out; size_t bytes = c->N * sizeof(u64);
+  HB_CUDA(cudaMalloc((void**)&d_out, bytes));
+  HbCrtJob J; memset(&J, 0, sizeof(J));
+  J.cv = E->d; J.N = (int)c->N; J.src = coef; J.out = d_out; J.factor = factor; J.factor_s = h_shoup(factor, ptxt_space);
+  HbCrtTabs T; T.t = E->d_t; T.t_s = E->d_t_s;
+  dim3 grid((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS));
+  pre_launch(c);
+  HB_LAUNCH(k_crt_modp, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J, T);
+  int r = post_launch(c, "k_crt_modp", (u64)(n + 1) * c->N * 8);
+  if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_to_poly_mod_p: copy failed: %s", cudaGetErrorString(e)); }
+  cudaFree(d_out);
+  return r;
+}
+
+// coefficient polynomial(s) -> evaluation rows: one H2D copy of the polynomial, per-prime reduction and NTT on the device
+static int from_coeffs_impl(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const void* host, int L, const char* who) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, who)); HB_TRY(check_idx(c, idx, n, who, true));
+  if (!host) return hb_fail(HB_ERR_BAD_ARG, "%s: null coefficients", who);
+  if (n == 0) return HB_OK;
+  const size_t per = c->N * (size_t)(L > 0 ? L : 1) * sizeof(u64);
+  u64* d_src;
+  HB_CUDA(cudaMalloc((void**)&d_src, per * nitems));
+  cudaError_t e = cudaMemcpyAsync(d_src, host, per * nitems, cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) { cudaFree(d_src); return hb_fail(HB_ERR_CUDA, "%s: copy failed: %s", who, cudaGetErrorString(e)); }
+  int r = for_items(nitems, [&](int i0, int nit) {
+    for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+      int nr = std::min(HB_MAXROWS, n - r0);
+      HbFromJob J; memset(&J, 0, sizeof(J));
+      J.N = c->N; J.L = L; J.nitems = nit;
+      fill_rows(J.rows, idx + r0, nr);
+      for (int i = 0; i < nit; i++) { J.src[i] = (const u64*)((const char*)d_src + per * (i0 + i)); J.dst[i] = polys[i0 + i]->d; }
+      dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>(c->N / (HB_THREADS * 4), 64)), nr, nit);
+      pre_launch(c);
+      HB_LAUNCH(k_from_coeffs, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+      HB_TRY(post_launch(c, "k_from_coeffs", (u64)nit * c->N * 8 * ((L > 0 ? L : 1) + nr)));
+    }
+    return HB_OK;
+  });
+  if (r == HB_OK) r = hb_ntt_fwd(polys, nitems, idx, n);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_src);
+  return r;
+}
+extern "C" int hb_poly_from_i64(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const int64_t* coeffs) {
+  return from_coeffs_impl(polys, nitems, idx, n, coeffs, 0, "hb_poly_from_i64");
+}
+extern "C" int hb_poly_from_limbs(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const uint64_t* limbs, int L) {
+  if (L < 1 || L > 1024) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_from_limbs: L=%d", L);
+  return from_coeffs_impl(polys, nitems, idx, n, limbs, L, "hb_poly_from_limbs");
+}
+extern "C" int hb_muladd(hb_poly* const* dst, hb_poly* const* a, hb_poly* const* b, int nitems, const int32_t* idx, int n) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(dst, nitems, &c, "hb_muladd")); HB_TRY(check_polys(a, nitems, &c, "hb_muladd")); HB_TRY(check_polys(b, nitems, &c, "hb_muladd"));
+  HB_TRY(check_idx(c, idx, n, "hb_muladd"));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* D[HB_MAXB]; u64* A_[HB_MAXB]; u64* B_[HB_MAXB]; ptrs_of(dst, i0, nit, D); ptrs_of(a, i0, nit, A_); ptrs_of(b, i0, nit, B_);
+    PwArgs A; memset(&A, 0, sizeof(A));
+    A.op = HB_PW_MULADD; A.dst = D; A.a = (const u64* const*)A_; A.b = (const u64* const*)B_;
+    return launch_pw(c, A, nit, idx, n);
+  });
 }
 
 // ------------------------------------------------------------------------------------------

@@ -243,6 +243,31 @@ class Engine:
         self._ck(self.lib.hb_to_poly(poly.h, p, n, int(positive), out.ctypes.data_as(u64p), L))
         return out
 
+    def to_poly_mod_p(self, poly, idx, ptxt_space, factor=1):
+        a, p, n = _idx(idx)
+        out = np.zeros(self.N, dtype=np.int64)
+        self._ck(self.lib.hb_to_poly_mod_p(poly.h, p, n, C.c_uint64(int(ptxt_space)), C.c_uint64(int(factor)),
+                                           out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def from_i64(self, polys, idx, coeffs):
+        """coeffs: [len(polys)][N] signed integers -> evaluation rows idx of each poly."""
+        a, p, n = _idx(idx)
+        buf = np.ascontiguousarray(np.asarray(coeffs, dtype=np.int64).reshape(len(polys), self.N))
+        self._ck(self.lib.hb_poly_from_i64(_arr(polys), len(polys), p, n, buf.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def from_limbs(self, polys, idx, limbs):
+        """limbs: [len(polys)][N][L] two's-complement uint64 limbs (hb_to_poly layout)."""
+        a, p, n = _idx(idx)
+        buf = np.ascontiguousarray(np.asarray(limbs, dtype=np.uint64))
+        L = buf.shape[-1]
+        assert buf.size == len(polys) * self.N * L
+        self._ck(self.lib.hb_poly_from_limbs(_arr(polys), len(polys), p, n, buf.ctypes.data_as(u64p), L))
+
+    def muladd(self, dst, a_, b_, idx):
+        a, p, n = _idx(idx)
+        self._ck(self.lib.hb_muladd(_arr(dst), _arr(a_), _arr(b_), len(dst), p, n))
+
     def break_into_digits(self, src, cur, digits=None):
         """digits: list (per item) of lists (per digit) of Poly; allocated if None."""
         a, pc, nc = _idx(cur)

@@ -115,6 +115,21 @@ int hb_scale_down(hb_poly* const* polys, int nitems, const int32_t* cur, int ncu
 /* DoubleCRT::toPoly (src/DoubleCRT.cpp:925-1113): balanced (or positive) big integers,
  * out[N][Lout] little-endian two's-complement limbs.  Synchronises. */
 int hb_to_poly(hb_poly* p, const int32_t* idx, int n, int positive, uint64_t* out_limbs, int Lout);
+/* Tail of SecKey::Decrypt (src/keys.cpp:1381-1399): PolyRed(toPoly(ptxt), ptxt_space) times factor
+ * (= (intFactor*Q)^-1 mod ptxt_space, or 1), out[N] in [0, ptxt_space).  The big integers stay on the device:
+ * N words come back instead of N*(n+1).  ptxt_space >= 2, coprime to the primes in idx.  Synchronises. */
+int hb_to_poly_mod_p(hb_poly* p, const int32_t* idx, int n, uint64_t ptxt_space, uint64_t factor, int64_t* out);
+/* DoubleCRT(const zzX&, context, s) / FFT(const zzX&, s) (src/DoubleCRT.cpp:87-105, src/CModulus.cpp:339-356):
+ * coeffs[nitems][N] signed 64-bit coefficients (|c| < 2^63) are copied once, reduced modulo every prime in idx
+ * and transformed on the device.  Synchronises (the host buffer may be reused on return). */
+int hb_poly_from_i64(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const int64_t* coeffs);
+/* DoubleCRT(const ZZX&, context, s) / FFT(const ZZX&, s) (src/DoubleCRT.cpp:68-85; the per-prime `convert`,
+ * src/CModulus.cpp:453-457, timer FFT_remainder): limbs[nitems][N][L] little-endian two's-complement big
+ * integers (the layout hb_to_poly produces).  Synchronises. */
+int hb_poly_from_limbs(hb_poly* const* polys, int nitems, const int32_t* idx, int n, const uint64_t* limbs, int L);
+/* dst += a * b row-wise: `key *= part; ptxt += key` of SecKey::Decrypt (src/keys.cpp:1373-1374) and
+ * `parts[i] *= r; parts[i] += e` of PubKey::Encrypt (src/keys.cpp:416,443) in one pass. */
+int hb_muladd(hb_poly* const* dst, hb_poly* const* a, hb_poly* const* b, int nitems, const int32_t* idx, int n);
 /* DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:479-561).  src rows cur (ctxt primes only);
  * digits[item*maxdig + i] receives digit i over cur | special.  *ndig_out = number of digits. */
 int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out);

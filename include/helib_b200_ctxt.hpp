@@ -17,9 +17,14 @@
 //   multLowLvl / multiplyBy        src/Ctxt.cpp:1681-1774
 //   modSwitchAddedNoiseBound       src/Ctxt.cpp:2560-2582
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <complex>
+#include <functional>
 #include <memory>
+#include <numeric>
+#include <random>
 
 #include "helib_b200_doublecrt.hpp"
 
@@ -89,6 +94,11 @@ struct KeyInfo {
     return nullptr;
   }
   double noiseBoundForUniform(double mag, long deg) const { return scale * std::sqrt(double(deg) / 3.0) * mag; }   // include/helib/Context.h:475-478
+  double noiseBoundForMod(long modulus, long deg) const {   // include/helib/Context.h:517-524
+    double var = double(modulus) * double(modulus) / 12.0; if (modulus % 2 == 0) var += 1.0 / 6.0;
+    return scale * std::sqrt(deg * var);
+  }
+  double noiseBoundForGaussian(double sigma, long deg) const { return scale * std::sqrt(double(deg)) * sigma; }   // include/helib/Context.h:541-544
   double logOfProduct(const IndexSet& s) const { double x = 0; for (long i : s) x += std::log((double)context->ithPrime(i)); return x; }
 };
 
@@ -123,6 +133,9 @@ class Ctxt {
     if (parts.size() > 1 && !parts[1].skHandle.isBase(keyID)) return false;
     return true;
   }
+  XD totalNoiseBound() const { return isCKKS() ? ptxtMag * ratFactor + noiseBound : noiseBound; }   // include/helib/Ctxt.h:1358-1364
+  // src/Ctxt.cpp:116-127; polyNormBnd = 1 for power-of-two m (PAlgebra::getPolyNormBnd), else supplied by the caller
+  bool isCorrect(double polyNormBnd = 1.0) const { return (totalNoiseBound() * XD(polyNormBnd)).ln() <= std::log(0.48) + logOfPrimeSet(); }
   bool verifyPrimeSet() const {   // src/Ctxt.cpp:177-186
     IndexSet s = primeSet & context.getSpecialPrimes();
     if (!empty(s) && s != context.getSpecialPrimes()) return false;
@@ -324,5 +337,151 @@ class Ctxt {
   double lastModSwitchRatio = 0, lastKSNoiseRatio = 0, lastLo = 0, lastHi = 0;
   IndexSet lastCommonPrimeSet;
 };
+
+// ---- the steps either side of the path ------------------------------------------------------------
+// Sampling follows the reference's DISTRIBUTIONS (src/sample.cpp); its bit stream (NTL's PRG) is not restated, so
+// the sampled values are an input of Encrypt below and "parity unpinned" is confined to them.
+struct EncryptionSample {
+  std::vector<long> r, e0, e1;
+  double r_bound = 0, e0_bound = 0, e1_bound = 0;   // what sampleSmallBounded / sampleGaussianBounded return
+};
+// max_j |f(zeta^(2j+1))| for power-of-two m (embeddingLargestCoeff, src/norms.cpp:204-261): twist + N-point FFT on the host
+inline double embeddingLargestCoeff(const std::vector<long>& f, long m) {
+  const long N = m / 2;
+  if (m < 4 || (m & (m - 1)) != 0) throw LogicError("embeddingLargestCoeff: host version is for power-of-two m");
+  std::vector<std::complex<double>> z((size_t)N);
+  const double pi = 3.14159265358979323846;
+  for (long k = 0; k < N; k++) z[k] = (k < (long)f.size() ? double(f[k]) : 0.0) * std::polar(1.0, pi * double(k) / double(N));
+  for (long i = 1, j = 0; i < N; i++) { long bit = N >> 1; for (; j & bit; bit >>= 1) j ^= bit; j ^= bit; if (i < j) std::swap(z[i], z[j]); }
+  for (long len = 2; len <= N; len <<= 1) {
+    const std::complex<double> wl = std::polar(1.0, 2 * pi / double(len));
+    for (long i = 0; i < N; i += len) { std::complex<double> w(1.0, 0.0);
+      for (long k = 0; k < len / 2; k++) { auto u = z[i + k], v = z[i + k + len / 2] * w; z[i + k] = u + v; z[i + k + len / 2] = u - v; w *= wl; } }
+  }
+  double mx = 0; for (auto& c : z) mx = std::max(mx, std::abs(c));
+  return mx;
+}
+template <class Gen> void sampleSmall(std::vector<long>& poly, long n, Gen& g) {   // src/sample.cpp:67-103 (prob = 1/2)
+  poly.assign((size_t)n, 0);
+  for (long i = 0; i < n; i++) { unsigned u = (unsigned)(g() & 3u); poly[i] = (u & 1u) ? long(u & 2u) - 1 : 0; }
+}
+template <class Gen> void sampleGaussian(std::vector<long>& poly, long n, double stdev, Gen& g) {   // src/sample.cpp:140-187
+  std::normal_distribution<double> d(0.0, stdev);
+  poly.assign((size_t)n, 0);
+  for (long i = 0; i < n; i++) poly[i] = std::lround(d(g));
+}
+template <class Gen> double sampleSmallBounded(std::vector<long>& poly, const Context& ctx, Gen& g) {   // src/sample.cpp:342-396
+  const long phim = ctx.getPhiM();
+  const double bound = std::sqrt(phim * std::log(double(phim)) / 2.0);
+  double val; long count = 0;
+  do { sampleSmall(poly, phim, g); val = embeddingLargestCoeff(poly, ctx.getM()); } while (++count < 1000 && val > bound);
+  if (val > bound) throw RuntimeError("Error: sampleSmallBounded, after 1000 trials, still val > bound");
+  return bound;
+}
+template <class Gen> double sampleGaussianBounded(std::vector<long>& poly, const Context& ctx, double stdev, Gen& g) {   // src/sample.cpp:459-512
+  const long phim = ctx.getPhiM();
+  const double bound = stdev * std::sqrt(phim * std::log(double(phim)));
+  double val; long count = 0;
+  do { sampleGaussian(poly, phim, stdev, g); val = embeddingLargestCoeff(poly, ctx.getM()); } while (++count < 1000 && val > bound);
+  if (val > bound) throw RuntimeError("Error: sampleGaussianBounded, after 1000 trials, still val > bound");
+  return bound;
+}
+template <class Gen> EncryptionSample drawEncryptionSample(const Context& ctx, double stdev, Gen& g) {
+  EncryptionSample s;
+  s.r_bound = sampleSmallBounded(s.r, ctx, g);
+  s.e0_bound = sampleGaussianBounded(s.e0, ctx, stdev, g);
+  s.e1_bound = sampleGaussianBounded(s.e1, ctx, stdev, g);
+  return s;
+}
+
+// PubKey::Encrypt, BGV branch (src/keys.cpp:358-488): ctxt = r*pk + p*(e0,e1) + (ptxt_fixed, 0).  Three polynomials
+// cross the bus as phi(m) words each; the products, sums and transforms run on the device.
+// tieCoin stands for NTL::RandomBnd(2) in balanced_MulMod (src/NumbTh.cpp:876-892, even ptxtSpace only).
+inline long Encrypt(Ctxt& ctxt, const Ctxt& pubEncrKey, const std::vector<long>& ptxt, long ptxtSpace,
+                    const EncryptionSample& smp, const std::function<bool()>& tieCoin = [] { return false; }) {
+  const Context& context = pubEncrKey.context;
+  if (&ctxt.pubKey != &pubEncrKey.pubKey) throw LogicError("Public key and context public key mismatch");
+  if (pubEncrKey.isCKKS()) throw LogicError("Encrypt: BGV only (CKKSencrypt is separate in the reference)");
+  if (pubEncrKey.parts.size() != 2) throw LogicError("Encrypt: public encryption key must have two parts");
+  if (ptxtSpace != pubEncrKey.ptxtSpace) {
+    ptxtSpace = std::gcd(ptxtSpace, pubEncrKey.ptxtSpace);
+    if (ptxtSpace <= 1) throw RuntimeError("Plaintext-space mismatch on encryption");
+  }
+  const long phim = context.getPhiM();
+  if ((long)ptxt.size() > phim) throw InvalidArgument("plaintext degree >= phi(m)");
+  ctxt = pubEncrKey;
+  const IndexSet& S = ctxt.primeSet;
+  DoubleCRT r(smp.r, context, S);
+  ctxt.noiseBound = XD(smp.r_bound) * pubEncrKey.noiseBound;
+  unsigned long QmodP = 1;
+  for (long i : S) QmodP = (unsigned long)(((unsigned __int128)QmodP * (unsigned long)(context.ithPrime(i) % ptxtSpace)) % (unsigned long)ptxtSpace);
+  for (size_t i = 0; i < ctxt.parts.size(); i++) {
+    const std::vector<long>& ei = i == 0 ? smp.e0 : smp.e1;
+    std::vector<long> c((size_t)phim, 0);
+    for (long k = 0; k < phim && k < (long)ei.size(); k++) {
+      const __int128 v = (__int128)ei[k] * ptxtSpace;
+      if (v > ((__int128)1 << 61) || v < -((__int128)1 << 61)) throw InvalidArgument("Encrypt: ptxtSpace * e does not fit a word");
+      c[k] = (long)v;
+    }
+    if (i == 0)
+      for (long k = 0; k < (long)ptxt.size(); k++) {   // ptxt_fixed = balanced(ptxt * (Q mod p) mod p)  (:453-455)
+        long t = ptxt[k] % ptxtSpace; if (t < 0) t += ptxtSpace;
+        long f = (long)(((unsigned __int128)(unsigned long)t * QmodP) % (unsigned long)ptxtSpace);
+        if (f > ptxtSpace / 2 || (ptxtSpace % 2 == 0 && f == ptxtSpace / 2 && tieCoin())) f -= ptxtSpace;
+        c[k] += f;
+      }
+    DoubleCRT e(c, context, S);                    // p*e_i (+ ptxt_fixed)
+    e.mulAdd(ctxt.parts[i].dcrt, r);               // + pk_i * r      (:416,443)
+    ctxt.parts[i].dcrt = e;
+    XD e_bound = XD((i == 0 ? smp.e0_bound : smp.e1_bound) * double(ptxtSpace));
+    if (i == 1) e_bound = e_bound * XD(pubEncrKey.pubKey.skBound);
+    ctxt.noiseBound = ctxt.noiseBound + e_bound;
+  }
+  ctxt.noiseBound = ctxt.noiseBound + XD(pubEncrKey.pubKey.noiseBoundForMod(ptxtSpace, phim));   // (:462,476)
+  ctxt.ptxtSpace = ptxtSpace;
+  ctxt.intFactor = 1;
+  return ptxtSpace;
+}
+
+// SecKey::Decrypt (src/keys.cpp:1327-1400).  sKeys[id] = the secret key polynomials in DoubleCRT form.
+// BGV: plaintxt in [0, ptxtSpace).  CKKS (or f_limbs != nullptr): the integer polynomial before reduction is
+// returned as phi(m) x L two's-complement limbs.
+inline void Decrypt(std::vector<long>& plaintxt, const Ctxt& c, const std::vector<DoubleCRT>& sKeys,
+                    std::vector<uint64_t>* f_limbs = nullptr, int* L = nullptr, double polyNormBnd = 1.0) {
+  if (!c.isCorrect(polyNormBnd)) throw LogicError("Decrypting with too much noise");
+  const Context& context = c.context;
+  const IndexSet& P = c.primeSet;
+  DoubleCRT ptxt(context, P);
+  for (const CtxtPart& part : c.parts) {
+    if (part.skHandle.isOne()) { ptxt.Add(part.dcrt, false); continue; }
+    DoubleCRT key = sKeys.at((size_t)part.skHandle.secretKeyID);
+    key.addPrimes(P / key.getIndexSet());              // key.setPrimes(ptxtPrimes)  (include/helib/DoubleCRT.h:275-279)
+    key.removePrimes(key.getIndexSet() / P);
+    if (part.skHandle.powerOfX > 1) key.automorph(part.skHandle.powerOfX);
+    if (part.skHandle.powerOfS > 1) { DoubleCRT base(key); for (long e = 1; e < part.skHandle.powerOfS; e++) key *= base; }   // Exp (src/DoubleCRT.cpp:1142-1156)
+    ptxt.mulAdd(key, part.dcrt);
+  }
+  if (c.isCKKS() || f_limbs) {
+    int l = 0; std::vector<uint64_t> limbs = ptxt.toPoly(P, false, l);
+    if (f_limbs) *f_limbs = std::move(limbs);
+    if (L) *L = l;
+    if (c.isCKKS()) return;
+  }
+  const long p = c.ptxtSpace;
+  long factor = 1;
+  if (p > 2) {   // multiply by (intFactor * Q)^-1 mod p  (:1388-1398)
+    unsigned long f = 1;
+    for (long i : P) f = (unsigned long)(((unsigned __int128)f * (unsigned long)(context.ithPrime(i) % p)) % (unsigned long)p);
+    long jf = c.intFactor % p; if (jf < 0) jf += p;
+    f = (unsigned long)(((unsigned __int128)f * (unsigned long)jf) % (unsigned long)p);
+    if (f != 1) {   // InvMod by extended Euclid
+      long a = (long)f, b = p, x0 = 1, x1 = 0;
+      while (b) { long q = a / b, t = a - q * b; a = b; b = t; t = x0 - q * x1; x0 = x1; x1 = t; }
+      if (a != 1) throw LogicError("Decrypt: intFactor*Q not invertible mod ptxtSpace");
+      factor = x0 % p; if (factor < 0) factor += p;
+    }
+  }
+  plaintxt = ptxt.toPolyModP(P, p, factor);
+}
 
 }  // namespace hb

@@ -126,17 +126,25 @@ class DoubleCRT {
   // DoubleCRT(context, indexSet): zero object on the given primes (DoubleCRT.h:153-158)
   DoubleCRT(const Context& ctx, const IndexSet& s) : context_(&ctx), set_(s) { alloc(); }
   // DoubleCRT(zzX poly, context, indexSet): small-coefficient polynomial (DoubleCRT.h:140-151)
+  // One copy of the coefficients crosses the bus; the per-prime reduction and the transforms run on the device.
   DoubleCRT(const std::vector<long>& poly, const Context& ctx, const IndexSet& s) : context_(&ctx), set_(s) {
     alloc();
-    const long N = ctx.getPhiM(), np = ctx.numPrimes();
+    const long N = ctx.getPhiM();
     if ((long)poly.size() > N) throw InvalidArgument("polynomial degree >= phi(m)");
-    std::vector<uint64_t> dense((size_t)np * N, 0);
-    for (long i : s) {
-      const long q = ctx.ithPrime(i);
-      for (size_t k = 0; k < poly.size(); k++) { long v = poly[k] % q; dense[(size_t)i * N + k] = (uint64_t)(v < 0 ? v + q : v); }
-    }
+    std::vector<int64_t> c(poly.begin(), poly.end()); c.resize((size_t)N, 0);
     auto idx = s.vec();
-    if (!idx.empty()) { check(hb_poly_upload(p_, idx.data(), (int)idx.size(), dense.data())); hb_poly* arr[1] = {p_}; check(hb_ntt_fwd(arr, 1, idx.data(), (int)idx.size())); }
+    hb_poly* arr[1] = {p_};
+    if (!idx.empty()) check(hb_poly_from_i64(arr, 1, idx.data(), (int)idx.size(), c.data()));
+  }
+  // DoubleCRT(ZZX poly, context, indexSet) (DoubleCRT.h:129-138): big coefficients as N x L little-endian
+  // two's-complement limbs (the layout toPoly returns; NTL side: BytesFromZZ + sign)
+  static DoubleCRT fromLimbs(const Context& ctx, const IndexSet& s, const std::vector<uint64_t>& limbs, int L) {
+    if (L < 1 || limbs.size() != (size_t)ctx.getPhiM() * L) throw InvalidArgument("fromLimbs: expected phi(m) x L limbs");
+    DoubleCRT r(ctx, s);
+    auto idx = s.vec();
+    hb_poly* arr[1] = {r.p_};
+    if (!idx.empty()) check(hb_poly_from_limbs(arr, 1, idx.data(), (int)idx.size(), limbs.data(), L));
+    return r;
   }
   DoubleCRT(const DoubleCRT& o) : context_(o.context_), set_(o.set_) {
     alloc();
@@ -297,6 +305,23 @@ class DoubleCRT {
     std::vector<uint64_t> out((size_t)context_->getPhiM() * L);
     check(hb_to_poly(p_, idx.data(), (int)idx.size(), positive ? 1 : 0, out.data(), L));
     return out;
+  }
+  // *this += a * b on this object's primes (both operands must cover them): `key *= part; ptxt += key`
+  // (src/keys.cpp:1373-1374) and `parts[i] *= r; parts[i] += e` (src/keys.cpp:416,443) without the temporary
+  DoubleCRT& mulAdd(const DoubleCRT& a, const DoubleCRT& b) {
+    if (context_ != a.context_ || context_ != b.context_) throw RuntimeError("DoubleCRT::Op: incompatible objects");  // src/DoubleCRT.cpp:222-223
+    if (!(set_ <= a.set_) || !(set_ <= b.set_)) throw RuntimeError("DoubleCRT::Op: !(map.getIndexSet() <= other.map.getIndexSet())");
+    auto idx = set_.vec();
+    hb_poly* d[1] = {p_}; hb_poly* x[1] = {a.p_}; hb_poly* y[1] = {b.p_};
+    if (!idx.empty()) check(hb_muladd(d, x, y, 1, idx.data(), (int)idx.size()));
+    return *this;
+  }
+  // PolyRed(toPoly(s), ptxtSpace, abs=true) * factor mod ptxtSpace: the tail of SecKey::Decrypt (src/keys.cpp:1381-1399)
+  std::vector<long> toPolyModP(const IndexSet& s, long ptxtSpace, long factor = 1) const {
+    auto idx = (set_ & s).vec();
+    std::vector<int64_t> out((size_t)context_->getPhiM());
+    check(hb_to_poly_mod_p(p_, idx.data(), (int)idx.size(), (uint64_t)ptxtSpace, (uint64_t)factor, out.data()));
+    return std::vector<long>(out.begin(), out.end());
   }
   // getOneRow (DoubleCRT.h:332-336)
   std::vector<long> getOneRow(long i) const {

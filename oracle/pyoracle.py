@@ -692,3 +692,56 @@ def gen_ifft(row, q: int, m: int, root: int):
                 A[k - (len(phi) - 1) + j] = (A[k - (len(phi) - 1) + j] - c * pj) % q
     minv = pow(m, q - 2, q)
     return [a * minv % q for a in A[:len(phi) - 1]]
+
+
+# ---------------------------------------------------------------------------------------------
+# Encryption / decryption data path.  Randomness is an INPUT here: the reference draws it from
+# NTL's PRG (src/sample.cpp), which is not restated -- "parity unpinned" for the sampled values themselves; the
+# arithmetic on them is what these functions pin.
+
+def balanced_mulmod(f, a: int, q: int, coin=lambda: 0):
+    """balanced_MulMod (src/NumbTh.cpp:876-892): c = f_i*a mod q moved to (-q/2, q/2]; for even q the tie
+    c == q/2 is resolved by a coin (NTL::RandomBnd(2)) supplied by the caller."""
+    out = []
+    for c in f:
+        c = (c % q) * a % q
+        if c > q // 2 or (q % 2 == 0 and c == q // 2 and coin()):
+            c -= q
+        out.append(c)
+    return out
+
+
+def encrypt_bgv(chain, psis, pk0: "PyDCRT", pk1: "PyDCRT", r, e0, e1, ptxt, ptxt_space: int, idxs, coin=lambda: 0):
+    """PubKey::Encrypt, BGV branch (src/keys.cpp:381-455): ctxt = r*pk + p*(e0,e1) + (ptxt_fixed, 0) with
+    ptxt_fixed = balanced(ptxt * (Q mod p) mod p), Q the product of the ciphertext's primes."""
+    rr = PyDCRT.from_poly(chain, psis, r, idxs)
+    parts = []
+    for pk, e in ((pk0, e0), (pk1, e1)):
+        part = PyDCRT(chain, psis, {i: list(pk.rows[i]) for i in idxs})
+        part.mul(rr)                                                               # parts[i] *= r   (:416)
+        part.add(PyDCRT.from_poly(chain, psis, [ptxt_space * x for x in e], idxs))  # e *= p; parts[i] += e (:436-443)
+        parts.append(part)
+    q_mod_p = chain.product(idxs) % ptxt_space                                     # (:453)
+    fixed = balanced_mulmod(list(ptxt) + [0] * (chain.phim - len(ptxt)), q_mod_p, ptxt_space, coin)
+    parts[0].add(PyDCRT.from_poly(chain, psis, fixed, idxs))                       # (:454-455)
+    return parts
+
+
+def decrypt_bgv(chain, psis, parts, keys, ptxt_space: int, int_factor: int, idxs):
+    """SecKey::Decrypt (src/keys.cpp:1327-1400): ptxt = sum_i part_i * key_i (key None = handle "one"),
+    toPoly (balanced), PolyRed to [0,p), times (intFactor*Q)^-1 mod p when p > 2.
+    Returns (plaintext mod p, f = the integer polynomial before reduction)."""
+    acc = PyDCRT(chain, psis, {i: [0] * chain.phim for i in idxs})
+    for part, key in zip(parts, keys):
+        t = PyDCRT(chain, psis, {i: list(part.rows[i]) for i in idxs})
+        if key is not None:
+            t.mul(key)                                                             # key *= part      (:1373)
+        acc.add(t)                                                                 # ptxt += key      (:1374)
+    f = acc.to_poly(idxs)
+    out = [c % ptxt_space for c in f]                                              # PolyRed(..., abs=true) (:1386)
+    if ptxt_space > 2:
+        factor = chain.product(idxs) % ptxt_space * (int_factor % ptxt_space) % ptxt_space   # (:1389-1392)
+        if factor != 1:
+            inv = pow(factor, -1, ptxt_space)
+            out = [c * inv % ptxt_space for c in out]
+    return out, f

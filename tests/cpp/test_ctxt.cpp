@@ -49,46 +49,37 @@ int main() {
     W.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)));
     pk.keySwitching.push_back(W);
 
-    auto encrypt = [&](const std::vector<long>& msg) {
-      Ctxt c(pk, p);
-      c.primeSet = ctx.getCtxtPrimes();
-      unsigned long Qp = 1;
-      for (long i : c.primeSet) Qp = (unsigned long)(((u128)Qp * (unsigned long)(ctx.ithPrime(i) % p)) % (unsigned long)p);
-      std::vector<long> e = sample_gauss(gen, N, sigma), pt(N);
-      for (long k = 0; k < N; k++) pt[k] = p * e[k] + (long)(((u128)Qp * (unsigned long)msg[k]) % (unsigned long)p);   // decrypts to Q*m (src/keys.cpp:1408-1417)
-      DoubleCRT c1 = random_rows(ctx, c.primeSet, gen);
-      DoubleCRT c0(pt, ctx, c.primeSet);
+    // public encryption key: an RLWE1 encryption of zero over the ctxt primes (SecKey::GenSecKey, src/keys.cpp:1129-1157)
+    Ctxt pubEncrKey(pk, p);
+    {
+      pubEncrKey.primeSet = ctx.getCtxtPrimes();
+      std::vector<long> e = sample_gauss(gen, N, sigma);
+      DoubleCRT c1 = random_rows(ctx, pubEncrKey.primeSet, gen);
+      DoubleCRT c0(e, ctx, pubEncrKey.primeSet); c0 *= p;
       DoubleCRT t(c1); t.Mul(S, false); c0 -= t;
-      c.parts.emplace_back(c0, SKHandle());
-      c.parts.emplace_back(c1, SKHandle(1, 1, 0));
-      c.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)) + pk.noiseBoundForUniform(p / 2.0, N));
+      pubEncrKey.parts.emplace_back(c0, SKHandle());
+      pubEncrKey.parts.emplace_back(c1, SKHandle(1, 1, 0));
+      pubEncrKey.noiseBound = XD(double(p) * pk.noiseBoundForGaussian(sigma, N));
+    }
+    std::vector<DoubleCRT> sKeys; sKeys.push_back(S);
+    auto encrypt = [&](const std::vector<long>& msg) {     // PubKey::Encrypt through the mirror (device path)
+      Ctxt c(pk, p);
+      hb::EncryptionSample smp = hb::drawEncryptionSample(ctx, sigma, gen);
+      if (hb::Encrypt(c, pubEncrKey, msg, p, smp) != p) throw hb::LogicError("Encrypt changed the plaintext space");
       return c;
     };
-    auto decrypt = [&](const Ctxt& c, double* maxabs) {   // SecKey::Decrypt, src/keys.cpp:1327-1420
-      DoubleCRT acc(ctx, c.primeSet);
-      for (auto& part : c.parts) {
-        if (part.skHandle.isOne()) { acc += part.dcrt; continue; }
-        DoubleCRT key(S); key.removePrimes(allq / c.primeSet);
-        if (part.skHandle.powerOfS == 2) key *= key;
-        key *= part.dcrt; acc += key;
+    auto decrypt = [&](const Ctxt& c, double* maxabs) {   // SecKey::Decrypt through the mirror (device path)
+      std::vector<long> out; std::vector<uint64_t> limbs; int L = 0;
+      hb::Decrypt(out, c, sKeys, maxabs ? &limbs : nullptr, &L);
+      if (maxabs) {
+        double mx = 0;
+        for (long k = 0; k < N; k++) {
+          bool neg = limbs[(size_t)k * L + L - 1] >> 63; double mag = 0;
+          for (int l = L - 1; l >= 0; l--) { uint64_t w = limbs[(size_t)k * L + l]; if (neg) w = ~w; mag = mag * 18446744073709551616.0 + (double)w; }
+          mx = std::max(mx, mag + (neg ? 1 : 0));
+        }
+        *maxabs = mx;
       }
-      int L; std::vector<uint64_t> limbs = acc.toPoly(c.primeSet, false, L);
-      unsigned long f = 1;
-      for (long i : c.primeSet) f = (unsigned long)(((u128)f * (unsigned long)(ctx.ithPrime(i) % p)) % (unsigned long)p);
-      f = (unsigned long)(((u128)f * (unsigned long)c.intFactor) % (unsigned long)p);
-      unsigned long finv = 1; for (unsigned long x = 1; x < (unsigned long)p; x++) if (x * f % p == 1) finv = x;
-      std::vector<long> out(N);
-      double mx = 0;
-      for (long k = 0; k < N; k++) {
-        // value mod p of a two's-complement L-limb integer; |value| as double for the noise check
-        bool neg = limbs[(size_t)k * L + L - 1] >> 63;
-        unsigned long r = 0; double mag = 0;
-        for (int l = L - 1; l >= 0; l--) { uint64_t w = limbs[(size_t)k * L + l]; if (neg) w = ~w; r = (unsigned long)((((u128)r << 64) | w) % (unsigned long)p); mag = mag * 18446744073709551616.0 + (double)w; }
-        if (neg) { r = (unsigned long)((p - (r + 1) % p) % p); mag += 1; }
-        mx = std::max(mx, mag);
-        out[k] = (long)(r * finv % p);
-      }
-      if (maxabs) *maxabs = mx;
       return out;
     };
 

@@ -53,6 +53,18 @@ int main() {
     std::vector<hb::DoubleCRT> digits;
     F.breakIntoDigits(digits);
     if (digits.size() != ctx.getDigits().size()) { std::printf("digit count\n"); return 1; }
+    // ZZX-style construction: toPoly limbs -> rows reproduces the object (DoubleCRT(ZZX) o toPoly = identity)
+    {
+      hb::DoubleCRT R = hb::DoubleCRT::fromLimbs(ctx, S, hp, L);
+      if (R.getOneRow(S.first()) != H.getOneRow(S.first()) || R.getOneRow(S.last()) != H.getOneRow(S.last())) { std::printf("fromLimbs round trip\n"); return 1; }
+      // mulAdd: Z = G; Z += F*G  ==  H + G
+      hb::DoubleCRT Z(G); Z.mulAdd(F, G);
+      hb::DoubleCRT W(H); W += G;
+      if (Z.getOneRow(S.first()) != W.getOneRow(S.first())) { std::printf("mulAdd mismatch\n"); return 1; }
+      // toPolyModP == the balanced coefficients reduced into [0,p)
+      std::vector<long> mp = H.toPolyModP(S, 257, 1);
+      for (long k : {0L, 1L, N / 2, N - 1}) { long v = coeff_of(hp, L, k) % 257; if (v < 0) v += 257; if (mp[k] != v) { std::printf("toPolyModP mismatch at %ld\n", k); return 1; } }
+    }
     // error behaviour
     bool threw = false;
     try { hb::DoubleCRT A(ctx, S), B(ctx, hb::IndexSet(S.first())); A += B; } catch (const hb::RuntimeError&) { threw = true; }

@@ -9,14 +9,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "test_shim")
 
 
-def build_exe(name="test_shim"):
+def build_exe(name="test_shim", sim=False):
+    """sim=True links the same test against the CPU kernel-logic simulator build of the library (tests/cusim):
+    the mirror's host logic and the kernels' arithmetic are then exercised without a GPU."""
     src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
-    exe = os.path.join(ROOT, "tests", "cpp", name)
-    deps = [src, os.path.join(ROOT, "include", "helib_b200_doublecrt.hpp"), os.path.join(ROOT, "include", "helib_b200_ctxt.hpp"),
-            os.path.join(ROOT, "helib_b200", "libhelib_b200.so")]
+    exe = os.path.join(ROOT, "tests", "cpp", name + ("_sim" if sim else ""))
+    if sim:
+        from conftest import build_sim
+        libpath = build_sim()
+    else:
+        libpath = os.path.join(ROOT, "helib_b200", "libhelib_b200.so")
+    deps = [src, os.path.join(ROOT, "include", "helib_b200_doublecrt.hpp"), os.path.join(ROOT, "include", "helib_b200_ctxt.hpp"), libpath]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
-                               "-L" + os.path.join(ROOT, "helib_b200"), "-lhelib_b200", "-Wl,-rpath," + os.path.join(ROOT, "helib_b200")])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, libpath,
+                               "-Wl,-rpath," + os.path.dirname(libpath)])
     return exe
 
 
@@ -49,4 +55,16 @@ def test_ctxt_multiplyBy_decrypts_on_gpu():
     """helib::Ctxt mirror: BGV encrypt -> multiplyBy (noise-driven prime sets, device norms) -> decrypt == product."""
     exe = build_exe("test_ctxt")
     r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ctxt OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_shim_logic_on_simulator():
+    """The DoubleCRT mirror's unit-level properties with the kernels compiled for the CPU simulator."""
+    r = subprocess.run([build_exe("test_shim", sim=True)], capture_output=True, text=True)
+    assert r.returncode == 0 and "shim OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_ctxt_encrypt_multiply_decrypt_on_simulator():
+    """PubKey::Encrypt -> Ctxt::multiplyBy -> SecKey::Decrypt through the mirror, kernels on the CPU simulator."""
+    r = subprocess.run([build_exe("test_ctxt", sim=True)], capture_output=True, text=True)
     assert r.returncode == 0 and "ctxt OK" in r.stdout, r.stdout + r.stderr

@@ -262,3 +262,94 @@ def test_wire_format_matches_reference_layout(lib):
         Q.deserialize(bytes(bad))
     with pytest.raises(HbError):
         Q.deserialize(blob[:-5])
+
+
+# ---- the steps either side of the path (encrypt / decrypt / polynomial -> rows) on the device ----
+
+@pytest.mark.parametrize("cfg", [(64, 257, 1, 120, 2), (4096, 17, 1, 160, 3)])
+def test_polynomial_to_rows_on_device(lib, cfg):
+    """DoubleCRT(zzX) and DoubleCRT(ZZX) constructors (src/DoubleCRT.cpp:68-105): reduce + NTT on the device from one
+    copy of the polynomial; small signed coefficients, full 63-bit ones, and big balanced integers (round trip of
+    toPoly), each against the oracle's rows."""
+    ch, psis, O, E = make(lib, *cfg)
+    n = ch.phim
+    full = ch.ctxt + ch.special
+    rng = np.random.default_rng(5)
+    small = rng.integers(-40, 41, n).astype(np.int64)
+    wide = rng.integers(-(1 << 62), 1 << 62, n).astype(np.int64)
+    wide[:4] = [-(1 << 63) + 1, (1 << 63) - 1, 0, -1]
+    for coeffs in (small, wide):
+        P = E.poly()
+        E.from_i64([P], full, [coeffs])
+        ref = dcrt_of(O, ch, [int(c) for c in coeffs], full)
+        assert rows_equal(P.download(full), ref, full)
+    # big integers: x -> toPoly -> limbs -> rows must reproduce x on every prime of the set, and extend consistently
+    S = ch.ctxt
+    x = O.random(rng, S)
+    X = E.poly(x, S)
+    limbs = E.to_poly(X, S)                      # [N][len(S)+1] two's complement, balanced
+    Y = E.poly()
+    E.from_limbs([Y], full, [limbs])
+    got = Y.download(full)
+    assert rows_equal(got, x, S)
+    ref = x.copy(); O.add_primes(ref, S, ch.special)     # exact base extension of the same integers
+    assert rows_equal(got, ref, ch.special)
+    # batched, and a subset of rows only
+    A, B = E.poly(), E.poly()
+    E.from_i64([A, B], S[:1], [small, wide])
+    assert rows_equal(A.download(S[:1]), dcrt_of(O, ch, [int(c) for c in small], S[:1]), S[:1])
+    assert rows_equal(B.download(S[:1]), dcrt_of(O, ch, [int(c) for c in wide], S[:1]), S[:1])
+    with pytest.raises(HbError):
+        E.from_i64([A], [len(ch.primes)], [small])
+
+
+@pytest.mark.parametrize("cfg", [(128, 257, 1, 150, 2), (64, 2, 1, 120, 2), (256, 3, 2, 150, 2)])
+def test_encrypt_decrypt_on_device_match_restated_reference(lib, cfg):
+    """PubKey::Encrypt (BGV, src/keys.cpp:381-455) and SecKey::Decrypt (src/keys.cpp:1327-1400) with the sampled
+    polynomials given: device rows == oracle rows bit for bit, decrypt(encrypt(m)) == m, and the device's mod-p
+    tail equals PolyRed + MulMod of the oracle's big-integer polynomial."""
+    ch, psis, O, E = make(lib, *cfg)
+    p, n = ch.p ** ch.r, ch.phim
+    S = ch.ctxt
+    rng = np.random.default_rng(23)
+    s = sample_small(rng, n, "ternary")
+    sk = po.PyDCRT.from_poly(ch, psis, s, S)
+    # public encryption key = RLWE1 sample (src/keys.cpp:40-72): pk1 = a, pk0 = p*e - a*s
+    a_rows = {i: [int(x) for x in rng.integers(0, ch.primes[i], n)] for i in S}
+    pk1 = po.PyDCRT(ch, psis, a_rows)
+    pk0 = po.PyDCRT.from_poly(ch, psis, [p * e for e in sample_small(rng, n, "gauss")], S)
+    t = pk1.copy(); t.mul(sk); pk0.sub(t)
+    msg = [int(x) for x in rng.integers(0, p, n)]
+    r = sample_small(rng, n, "ternary")
+    e0, e1 = sample_small(rng, n, "gauss"), sample_small(rng, n, "gauss")
+    want = po.encrypt_bgv(ch, psis, pk0, pk1, r, e0, e1, msg, p, S)
+
+    def up(d):
+        x = O.zeros()
+        for i in S:
+            x[i] = np.array(d.rows[i], dtype=np.uint64)
+        return E.poly(x, S)
+    PK0, PK1, SK = up(pk0), up(pk1), up(sk)
+    # device: three polynomials cross the bus as N int64 each; everything else stays in HBM
+    fixed = po.balanced_mulmod(msg, ch.product(S) % p, p)
+    R, C0, C1 = E.poly(), E.poly(), E.poly()
+    E.from_i64([R, C0, C1], S, [r, [p * a + b for a, b in zip(e0, fixed)], [p * a for a in e1]])
+    E.muladd([C0, C1], [PK0, PK1], [R, R], S)
+    for C, w in ((C0, want[0]), (C1, want[1])):
+        got = C.download(S)
+        for i in S:
+            assert [int(v) for v in got[i]] == w.rows[i]
+    # decrypt on the device
+    ref_pt, ref_f = po.decrypt_bgv(ch, psis, want, [None, sk], p, 1, S)
+    assert ref_pt == msg
+    ACC = E.poly()
+    E.pointwise("copy", [ACC], [C0], S)
+    E.muladd([ACC], [C1], [SK], S)
+    assert orc.limbs_to_ints(E.to_poly(ACC, S)) == ref_f
+    factor = pow(ch.product(S) % p, -1, p) if p > 2 else 1
+    got = E.to_poly_mod_p(ACC, S, p, factor)
+    assert [int(v) for v in got] == msg
+    # factor 1 == plain PolyRed(abs) of the same integers
+    assert [int(v) for v in E.to_poly_mod_p(ACC, S, p, 1)] == [c % p for c in ref_f]
+    with pytest.raises(HbError):
+        E.to_poly_mod_p(ACC, S, 1, 0)
