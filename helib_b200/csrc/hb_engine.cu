@@ -377,24 +377,30 @@ static int check_polys(hb_poly* const* p, int n, hb_ctx** c, const char* who) {
   }
   return HB_OK;
 }
+// rows <-> dense host matrix; runs of consecutive prime indices (the usual case: a prime set is an interval,
+// src/Ctxt.cpp:177-186) travel as ONE copy -- the per-call cost of cudaMemcpyAsync otherwise dominates the host side
+static int copy_rows(hb_ctx* c, u64* dev, u64* host, const int32_t* idx, int n, bool h2d) {
+  for (int j = 0; j < n;) {
+    int k = j + 1;
+    while (k < n && idx[k] == idx[k - 1] + 1) k++;
+    const size_t off = (size_t)idx[j] * c->N, bytes = (size_t)(k - j) * c->N * sizeof(u64);
+    if (h2d) HB_CUDA(cudaMemcpyAsync(dev + off, host + off, bytes, cudaMemcpyHostToDevice, c->stream));
+    else HB_CUDA(cudaMemcpyAsync(host + off, dev + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+    j = k;
+  }
+  return HB_OK;
+}
 extern "C" int hb_poly_upload(hb_poly* p, const int32_t* idx, int n, const uint64_t* host) {
   if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_upload: null");
   hb_ctx* c = p->ctx;
   HB_TRY(check_idx(c, idx, n, "hb_poly_upload"));
-  for (int j = 0; j < n; j++) {
-    size_t off = (size_t)idx[j] * c->N;
-    HB_CUDA(cudaMemcpyAsync(p->d + off, host + off, c->N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-  }
-  return HB_OK;
+  return copy_rows(c, p->d, (u64*)host, idx, n, true);
 }
 extern "C" int hb_poly_download(hb_poly* p, const int32_t* idx, int n, uint64_t* host) {
   if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_download: null");
   hb_ctx* c = p->ctx;
   HB_TRY(check_idx(c, idx, n, "hb_poly_download"));
-  for (int j = 0; j < n; j++) {
-    size_t off = (size_t)idx[j] * c->N;
-    HB_CUDA(cudaMemcpyAsync(host + off, p->d + off, c->N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-  }
+  HB_TRY(copy_rows(c, p->d, (u64*)host, idx, n, false));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return HB_OK;
 }
@@ -402,10 +408,7 @@ extern "C" int hb_poly_download_async(hb_poly* p, const int32_t* idx, int n, uin
   if (!p || !host) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_download_async: null");
   hb_ctx* c = p->ctx;
   HB_TRY(check_idx(c, idx, n, "hb_poly_download_async"));
-  for (int j = 0; j < n; j++) {
-    size_t off = (size_t)idx[j] * c->N;
-    HB_CUDA(cudaMemcpyAsync(host + off, p->d + off, c->N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-  }
+  HB_TRY(copy_rows(c, p->d, (u64*)host, idx, n, false));
   return HB_OK;
 }
 static int prof_collect(hb_ctx* c) {
