@@ -25,6 +25,7 @@
 #include <memory>
 #include <numeric>
 #include <random>
+#include <string>
 
 #include "helib_b200_doublecrt.hpp"
 
@@ -92,6 +93,30 @@ struct KeyInfo {
   const KeySwitch* getKeySWmatrix(const SKHandle& from, long toID) const {
     for (auto& w : keySwitching) if (w.fromKey == from && w.toKeyID == toID) return &w;
     return nullptr;
+  }
+  // PubKey::setKeySwitchMap / getNextKSWmatrix / isReachable (src/keys.cpp:122-172,310-319): BFS from 1 over the
+  // automorphism matrices W[s(X^n) -> s(X)]; map[k] = matrix of the first step towards k
+  std::vector<std::vector<long>> keySwitchMap;
+  void setKeySwitchMap(long keyId = 0) {
+    const long m = context->getM();
+    std::vector<std::pair<long, long>> edges;
+    for (size_t i = 0; i < keySwitching.size(); i++) {
+      const KeySwitch& mat = keySwitching[i];
+      if (mat.toKeyID == keyId && mat.fromKey.powerOfS == 1 && mat.fromKey.secretKeyID == keyId) edges.emplace_back(mat.fromKey.powerOfX, (long)i);
+    }
+    if (keyId >= (long)keySwitchMap.size()) keySwitchMap.resize(keyId + 1);
+    keySwitchMap[keyId].assign((size_t)m, -1);
+    std::vector<long> queue{1};
+    for (size_t h = 0; h < queue.size(); h++)
+      for (auto& e : edges) {
+        long next = (long)(((unsigned __int128)(unsigned long)queue[h] * (unsigned long)e.first) % (unsigned long)m);
+        if (keySwitchMap[keyId][next] == -1) { keySwitchMap[keyId][next] = e.second; queue.push_back(next); }
+      }
+  }
+  bool isReachable(long k, long keyID) const { return keyID < (long)keySwitchMap.size() && keySwitchMap[keyID].at((size_t)k) >= 0; }
+  const KeySwitch* getNextKSWmatrix(long fromXPower, long fromID) const {
+    long i = keySwitchMap.at((size_t)fromID).at((size_t)fromXPower);
+    return i >= 0 ? &keySwitching[(size_t)i] : nullptr;
   }
   double noiseBoundForUniform(double mag, long deg) const { return scale * std::sqrt(double(deg) / 3.0) * mag; }   // include/helib/Context.h:475-478
   double noiseBoundForMod(long modulus, long deg) const {   // include/helib/Context.h:517-524
@@ -327,6 +352,43 @@ class Ctxt {
     tmp.tensorProduct(*this, other);
     *this = tmp;
   }
+  long getKeyID() const { for (auto& part : parts) if (!part.skHandle.isOne()) return part.skHandle.secretKeyID; return 0; }   // src/Ctxt.cpp:2550-2557
+  void cleanUp() {   // src/Ctxt.cpp:788-797
+    reLinearize();
+    if (!primeSet.disjointFrom(context.getSpecialPrimes()) || !primeSet.disjointFrom(context.getSmallPrimes())) dropSmallAndSpecialPrimes();
+  }
+  static long invMod(long a, long m) {
+    long b = m, x0 = 1, x1 = 0; a %= m; if (a < 0) a += m;
+    while (b) { long q = a / b, t = a - q * b; a = b; b = t; t = x0 - q * x1; x0 = x1; x1 = t; }
+    if (a != 1) throw InvalidArgument("InvMod: not invertible");
+    x0 %= m; return x0 < 0 ? x0 + m : x0;
+  }
+  void automorph(long k) {   // src/Ctxt.cpp:2437-2457: F(X) -> F(X^k), no change in the noise bound
+    if (isEmpty()) return;
+    const long m = context.getM();
+    if (k <= 0 || k >= m || std::gcd(k, m) != 1) throw LogicError("k must be in Zm*");
+    for (auto& part : parts) {
+      part.dcrt.automorph(k);
+      if (!part.skHandle.isOne()) part.skHandle.powerOfX = (long)(((unsigned __int128)(unsigned long)part.skHandle.powerOfX * (unsigned long)k) % (unsigned long)m);
+    }
+  }
+  void complexConj() { automorph(context.getM() - 1); }   // src/Ctxt.cpp:2517-2523
+  void smartAutomorph(long k) {   // src/Ctxt.cpp:2462-2515: automorphism then re-linearisation, in the steps the key-switching map allows
+    const long m = context.getM();
+    k %= m; if (k < 0) k += m;
+    if (isEmpty() || k == 1) return;
+    if (std::gcd(k, m) != 1) throw LogicError("k must be in Zm*");
+    const long keyID = getKeyID();
+    if (!pubKey.isReachable(k, keyID)) throw LogicError("no key-switching matrices for k=" + std::to_string(k) + ", keyID=" + std::to_string(keyID));
+    if (!inCanonicalForm(keyID)) { reLinearize(keyID); if (!inCanonicalForm(keyID)) throw LogicError("Re-linearization failed: not in canonical form"); }
+    while (k != 1) {
+      const KeySwitch* matrix = pubKey.getNextKSWmatrix(k, keyID);
+      const long amt = matrix->fromKey.powerOfX;
+      automorph(amt);
+      reLinearize(keyID);
+      k = (long)(((unsigned __int128)(unsigned long)k * (unsigned long)invMod(amt, m)) % (unsigned long)m);
+    }
+  }
   void multiplyBy(const Ctxt& other) {   // src/Ctxt.cpp:1757-1774
     if (isEmpty()) return;
     if (other.isEmpty()) { *this = other; return; }
@@ -336,6 +398,78 @@ class Ctxt {
   // statistics the reference records through HELIB_STATS_UPDATE (src/Ctxt.cpp:537,835)
   double lastModSwitchRatio = 0, lastKSNoiseRatio = 0, lastLo = 0, lastHi = 0;
   IndexSet lastCommonPrimeSet;
+};
+
+// BasicAutomorphPrecon (src/matmul.cpp:60-184): hoisting -- one breakIntoDigits shared by many automorphisms of the
+// same ciphertext.  Each automorph(k) is ONE engine launch for power-of-two m (sigma_k applied in the load stage of
+// the evaluation-key inner product, hb_automorph_keyswitch_digits); general m permutes the digits first.
+class BasicAutomorphPrecon {
+  Ctxt ctxt;
+  XD noise;
+  std::vector<DoubleCRT> polyDigits;
+ public:
+  double lastKSNoiseRatioHoist = 0;   // "KS-noise-ratio-hoist" (src/matmul.cpp:101)
+  explicit BasicAutomorphPrecon(const Ctxt& c) : ctxt(c), noise(1.0) {
+    if (ctxt.parts.size() >= 1 && !ctxt.parts[0].skHandle.isOne()) throw LogicError("Invalid ciphertext (secret key handle for part 0 is not one)");
+    if (ctxt.parts.size() <= 1) return;
+    ctxt.cleanUp();
+    if (!ctxt.inCanonicalForm(ctxt.getKeyID())) throw LogicError("Ciphertext is not in canonical form");
+    ctxt.relin_CKKS_adjust();
+    XD addedNoise(0.0);
+    for (double ln : ctxt.parts[1].dcrt.breakIntoDigitsLogNorms(polyDigits)) addedNoise = addedNoise + XD::exp(ln);
+    XD max_ks_noise(0.0);
+    for (const KeySwitch& ks : ctxt.pubKey.keySwitching) if (max_ks_noise < ks.noiseBound) max_ks_noise = ks.noiseBound;
+    addedNoise = addedNoise * max_ks_noise;
+    noise = ctxt.noiseBound * XD::exp(ctxt.pubKey.logOfProduct(ctxt.context.getSpecialPrimes()));
+    lastKSNoiseRatioHoist = (addedNoise / noise).to_double();
+    noise = noise + addedNoise;
+  }
+  std::shared_ptr<Ctxt> automorph(long k) const {
+    if (k == 1 || ctxt.isEmpty()) return std::make_shared<Ctxt>(ctxt);
+    const Context& context = ctxt.context;
+    const KeyInfo& pubKey = ctxt.pubKey;
+    const long m = context.getM();
+    auto result = std::make_shared<Ctxt>(pubKey, ctxt.ptxtSpace);
+    result->noiseBound = noise;
+    result->intFactor = ctxt.intFactor;
+    result->primeSet = ctxt.primeSet | context.getSpecialPrimes();
+    if (ctxt.isCKKS()) {
+      result->ptxtMag = ctxt.ptxtMag;
+      result->ratFactor = ctxt.ratFactor * XD::exp(pubKey.logOfProduct(context.getSpecialPrimes()));
+    }
+    if (ctxt.parts.size() == 1) {   // only the constant part: no key switch
+      DoubleCRT tmp = ctxt.parts[0].dcrt;
+      tmp.automorph(k);
+      tmp.addPrimesAndScale(context.getSpecialPrimes());
+      result->addPart(tmp, ctxt.parts[0].skHandle);
+      return result;
+    }
+    const long keyID = ctxt.getKeyID();
+    if (!pubKey.isReachable(k, keyID)) throw LogicError("no key-switching matrices for k=" + std::to_string(k) + ", keyID=" + std::to_string(keyID));
+    const KeySwitch& W = *pubKey.getNextKSWmatrix(k, keyID);
+    const long amt = W.fromKey.powerOfX;
+    const bool pow2 = (m & (m - 1)) == 0;
+    if (pow2) {
+      DoubleCRT o0(context, result->primeSet), o1(context, result->primeSet);
+      std::vector<hb_poly*> dg, ea, eb;
+      for (size_t i = 0; i < polyDigits.size(); i++) { dg.push_back(polyDigits[i].handle()); ea.push_back(W.a[i].handle()); eb.push_back(W.b[i].handle()); }
+      hb_poly* c0[1] = {ctxt.parts[0].dcrt.handle()}; hb_poly* p0[1] = {o0.handle()}; hb_poly* p1[1] = {o1.handle()};
+      auto S = ctxt.primeSet.vec();
+      check(hb_automorph_keyswitch_digits(dg.data(), (int)dg.size(), (int)dg.size(), 1, S.data(), (int)S.size(), c0, (uint64_t)amt, ea.data(), eb.data(), p0, p1));
+      result->parts.emplace_back(o0, SKHandle());
+      result->parts.emplace_back(o1, SKHandle(1, 1, W.toKeyID));
+    } else {
+      DoubleCRT tmp = ctxt.parts[0].dcrt;
+      tmp.automorph(amt);
+      tmp.addPrimesAndScale(context.getSpecialPrimes());
+      result->addPart(tmp, ctxt.parts[0].skHandle);
+      std::vector<DoubleCRT> tmpDigits = polyDigits;
+      for (auto& d : tmpDigits) d.automorph(amt);
+      result->keySwitchDigits(W, tmpDigits);
+    }
+    if ((amt - k) % m != 0) result->smartAutomorph((long)(((unsigned __int128)(unsigned long)k * (unsigned long)Ctxt::invMod(amt, m)) % (unsigned long)m));
+    return result;
+  }
 };
 
 // ---- the steps either side of the path ------------------------------------------------------------

@@ -34,20 +34,25 @@ int main() {
     // secret key and the s^2 -> s key-switching matrix (SecKey::GenKeySWmatrix, src/keys.cpp:1159-1256)
     std::vector<long> s = sample_ternary(gen, N);
     DoubleCRT S(s, ctx, allq);
-    DoubleCRT fromKey(S); fromKey *= S;                           // s^2
-    KeySwitch W; W.fromKey = SKHandle(2, 1, 0); W.toKeyID = 0; W.ptxtSpace = p;
-    fromKey.multiplyByPrimes(ctx.getSpecialPrimes());             // P * s^2
-    for (size_t i = 0; i < ctx.getDigits().size(); i++) {
-      W.a.push_back(random_rows(ctx, allq, gen));
-      std::vector<long> e = sample_gauss(gen, N, sigma);
-      DoubleCRT b(e, ctx, allq); b *= p;                           // RLWE1: b = p*e - a*s  (src/keys.cpp:40-72)
-      DoubleCRT t(W.a.back()); t *= S; b -= t;
-      b += fromKey;
-      W.b.push_back(b);
-      fromKey.multiplyByPrimes(ctx.getDigit(i));
-    }
-    W.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)));
-    pk.keySwitching.push_back(W);
+    // GenKeySWmatrix (src/keys.cpp:1159-1256): W[fromKey -> s], b_i = p*e_i - a_i*s + P*(prod_{j<i} Q_j)*fromKey
+    auto genKeySW = [&](DoubleCRT fromKey, const SKHandle& h) {
+      KeySwitch W; W.fromKey = h; W.toKeyID = 0; W.ptxtSpace = p;
+      fromKey.multiplyByPrimes(ctx.getSpecialPrimes());
+      for (size_t i = 0; i < ctx.getDigits().size(); i++) {
+        W.a.push_back(random_rows(ctx, allq, gen));
+        std::vector<long> e = sample_gauss(gen, N, sigma);
+        DoubleCRT b(e, ctx, allq); b *= p;                           // RLWE1: b = p*e - a*s  (src/keys.cpp:40-72)
+        DoubleCRT t(W.a.back()); t *= S; b -= t;
+        b += fromKey;
+        W.b.push_back(b);
+        fromKey.multiplyByPrimes(ctx.getDigit(i));
+      }
+      W.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)));
+      pk.keySwitching.push_back(W);
+    };
+    { DoubleCRT s2(S); s2 *= S; genKeySW(s2, SKHandle(2, 1, 0)); }                 // s^2 -> s
+    for (long amt : {3L, m - 1}) { DoubleCRT sk(S); sk.automorph(amt); genKeySW(sk, SKHandle(1, amt, 0)); }   // s(X^amt) -> s
+    pk.setKeySwitchMap(0);
 
     // public encryption key: an RLWE1 encryption of zero over the ctxt primes (SecKey::GenSecKey, src/keys.cpp:1129-1157)
     Ctxt pubEncrKey(pk, p);
@@ -125,6 +130,34 @@ int main() {
     // drop the special primes again (cleanUp path) and decrypt once more
     ca.dropSmallAndSpecialPrimes();
     if (decrypt(ca, nullptr) != abc) { std::printf("mod-down changed the plaintext\n"); return 1; }
+    // rotations: smartAutomorph in map-driven steps, and the hoisted form sharing one digit decomposition
+    {
+      auto apply = [&](const std::vector<long>& f, long k) {   // f(X^k) mod (X^N + 1, p)
+        std::vector<long> g(N, 0);
+        for (long i = 0; i < N; i++) { long e = (long)(((unsigned __int128)(unsigned long)i * (unsigned long)k) % (unsigned long)m); long v = f[i]; if (e >= N) { e -= N; v = (p - v) % p; } g[e] = (g[e] + v) % p; }
+        return g;
+      };
+      Ctxt cr = encrypt(mb);
+      Ctxt c9 = cr; c9.smartAutomorph(9);                        // two steps of 3
+      if (!c9.inCanonicalForm() || decrypt(c9, nullptr) != apply(mb, 9)) { std::printf("smartAutomorph(9) mismatch\n"); return 1; }
+      Ctxt cc2 = cr; cc2.smartAutomorph(m - 1);                  // complex conjugation matrix
+      if (decrypt(cc2, nullptr) != apply(mb, m - 1)) { std::printf("smartAutomorph(m-1) mismatch\n"); return 1; }
+      hb::BasicAutomorphPrecon pre(cr);
+      for (long k : {3L, 27L, (3 * (m - 1)) % m}) {
+        auto h = pre.automorph(k);
+        double mx = 0;
+        if (decrypt(*h, &mx) != apply(mb, k)) { std::printf("hoisted automorph(%ld) mismatch\n", k); return 1; }
+        if (std::log2(std::max(mx, 1.0)) > h->noiseBound.ln() / ln2) { std::printf("hoisted noise estimate too small\n"); return 1; }
+      }
+      // hoisting must agree with the plain path bit for bit when one step suffices (sigma_k commutes with the digits)
+      Ctxt c3 = cr; c3.smartAutomorph(3);
+      auto h3 = pre.automorph(3);
+      for (size_t i = 0; i < 2; i++)
+        if (c3.parts[i].dcrt.getOneRow(c3.primeSet.first()) != h3->parts[i].dcrt.getOneRow(c3.primeSet.first())) { std::printf("hoisted rows differ from smartAutomorph rows\n"); return 1; }
+      bool threw = false;
+      try { Ctxt bad(pk, p); bad = cr; bad.parts[1].skHandle.secretKeyID = 1; bad.smartAutomorph(3); } catch (const hb::LogicError&) { threw = true; }
+      if (!threw) { std::printf("missing LogicError for unreachable automorphism\n"); return 1; }
+    }
     const long before = ctx.getCtxtPrimes().card(), common = ca.lastCommonPrimeSet.card();
     const double logq_before = logq0, logq_common = logq2;
     ctx.sync();
