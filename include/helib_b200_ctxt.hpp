@@ -352,6 +352,87 @@ class Ctxt {
     tmp.tensorProduct(*this, other);
     *this = tmp;
   }
+  // ---- linear operations (BGV branches; the CKKS branches need equalizeRationalFactors, src/Ctxt.cpp:1196-1394, not mirrored)
+  void negate() { for (auto& part : parts) part.dcrt.Negate(); }   // src/Ctxt.cpp:1190-1194
+  void reducePtxtSpace(long newPtxtSpace) {   // src/Ctxt.cpp:576-584
+    long g = std::gcd(ptxtSpace, newPtxtSpace);
+    if (g <= 1) throw LogicError("New and old plaintext spaces are coprime");
+    ptxtSpace = g; intFactor %= g;
+  }
+  static long balRem(long a, long q) { return a > q / 2 ? a - q : a; }   // include/helib/NumbTh.h:140-146
+  void mulIntFactor(long e) {   // src/Ctxt.cpp:331-340
+    if (e == 1) return;
+    intFactor = (long)(((unsigned __int128)(unsigned long)intFactor * (unsigned long)e) % (unsigned long)ptxtSpace);
+    long bal_e = balRem(e, ptxtSpace);
+    for (auto& part : parts) part.dcrt *= bal_e;
+    noiseBound = noiseBound * XD((double)std::labs(bal_e));
+  }
+  void addCtxt(const Ctxt& other, bool negative = false) {   // src/Ctxt.cpp:1406-1556
+    if (&context != &other.context) throw LogicError("Context mismatch");
+    if (&pubKey != &other.pubKey) throw LogicError("Public key mismatch");
+    if (other.isEmpty()) return;
+    if (isEmpty()) { *this = other; if (negative) negate(); return; }
+    if (isCKKS()) throw LogicError("Ctxt::addCtxt: the CKKS branch (equalizeRationalFactors) is not mirrored");
+    reducePtxtSpace(other.ptxtSpace);
+    Ctxt tmp(pubKey, other.ptxtSpace);
+    const Ctxt* other_pt = &other;
+    if (ptxtSpace != other_pt->ptxtSpace) { tmp = other; tmp.reducePtxtSpace(ptxtSpace); other_pt = &tmp; }
+    IndexSet s = other_pt->primeSet / primeSet;
+    if (!empty(s)) modUpToSet(s);
+    s = primeSet / other_pt->primeSet;
+    if (!empty(s)) { if (other_pt != &tmp) { tmp = other; other_pt = &tmp; } tmp.modUpToSet(s); }
+    long e1 = 1, e2 = 1;
+    if (intFactor != other_pt->intFactor) {   // harmonise: e1*f1 == e2*f2 (mod ptxtSpace) with the least noise growth (:1475-1527)
+      const long f1 = intFactor, f2 = other_pt->intFactor;
+      const long ratio = (long)(((unsigned __int128)(unsigned long)f2 * (unsigned long)invMod(f1, ptxtSpace)) % (unsigned long)ptxtSpace);
+      auto noiseNorm = [&](long a, long b) { return noiseBound * XD((double)std::labs(balRem(a, ptxtSpace))) + other_pt->noiseBound * XD((double)std::labs(balRem(b, ptxtSpace))); };
+      auto mc = [&](long a) { a %= ptxtSpace; return a < 0 ? a + ptxtSpace : a; };
+      long r0 = ptxtSpace, t0 = 0, r1 = ratio, t1 = 1;
+      long e1_best = r1, e2_best = t1;
+      XD noise_best = noiseNorm(e1_best, e2_best);
+      const long pp = context.getP();
+      while (r1 != 0) {
+        long q = r0 / r1, r2 = r0 % r1, t2 = t0 - t1 * q;
+        r0 = r1; r1 = r2; t0 = t1; t1 = t2;
+        long e1_try = mc(r1), e2_try = mc(t1);
+        if (e1_try % pp != 0) { XD n = noiseNorm(e1_try, e2_try); if (n < noise_best) { e1_best = e1_try; e2_best = e2_try; noise_best = n; } }
+      }
+      e1 = e1_best; e2 = e2_best;
+    }
+    if (e2 != 1) { if (other_pt != &tmp) { tmp = other; other_pt = &tmp; } tmp.mulIntFactor(e2); }
+    if (e1 != 1) mulIntFactor(e1);
+    for (const CtxtPart& part : other_pt->parts) {
+      long j = getPartIndexByHandle(part.skHandle);
+      if (j >= 0) { if (negative) parts[j].dcrt -= part.dcrt; else parts[j].dcrt += part.dcrt; }
+      else { parts.push_back(part); if (negative) parts.back().dcrt.Negate(); }
+    }
+    ptxtMag = ptxtMag + other_pt->ptxtMag;
+    noiseBound = noiseBound + other_pt->noiseBound;
+  }
+  Ctxt& operator+=(const Ctxt& o) { addCtxt(o); return *this; }
+  Ctxt& operator-=(const Ctxt& o) { addCtxt(o, true); return *this; }
+  // src/Ctxt.cpp:896-935 (BGV): the constant is scaled by intFactor*Q mod p so that it decrypts unscaled
+  void addConstant(const DoubleCRT& dcrt, double size = -1.0) {
+    if (isCKKS()) throw LogicError("Ctxt::addConstant: addConstantCKKS is not mirrored");
+    if (size < 0.0) size = pubKey.noiseBoundForMod(ptxtSpace, context.getPhiM());
+    long f = 1;
+    if (ptxtSpace > 2) {
+      unsigned long q = 1;
+      for (long i : primeSet) q = (unsigned long)(((unsigned __int128)q * (unsigned long)(context.ithPrime(i) % ptxtSpace)) % (unsigned long)ptxtSpace);
+      f = balRem((long)(((unsigned __int128)(unsigned long)intFactor * q) % (unsigned long)ptxtSpace), ptxtSpace);
+    }
+    noiseBound = noiseBound + XD(size * (double)std::labs(f));
+    if (f == 1) addPart(dcrt, SKHandle(0, 1, 0));
+    else { DoubleCRT tmp = dcrt; tmp *= f; addPart(tmp, SKHandle(0, 1, 0)); }
+  }
+  // src/Ctxt.cpp:1832-1856 (BGV)
+  void multByConstant(const DoubleCRT& dcrt, double size = -1.0) {
+    if (isEmpty()) return;
+    if (isCKKS()) throw LogicError("Ctxt::multByConstant: multByConstantCKKS is not mirrored");
+    if (size < 0.0) size = pubKey.noiseBoundForMod(ptxtSpace, context.getPhiM());
+    for (auto& part : parts) part.dcrt.Mul(dcrt, /*matchIndexSets=*/false);
+    noiseBound = noiseBound * XD(size);
+  }
   long getKeyID() const { for (auto& part : parts) if (!part.skHandle.isOne()) return part.skHandle.secretKeyID; return 0; }   // src/Ctxt.cpp:2550-2557
   void cleanUp() {   // src/Ctxt.cpp:788-797
     reLinearize();

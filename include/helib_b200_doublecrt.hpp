@@ -79,9 +79,9 @@ class Context {
   std::vector<uint64_t> primes_;
   IndexSet small_, ctxt_, special_;
   std::vector<IndexSet> digits_;
-  long m_, phim_;
+  long m_, phim_, p_, r_;
  public:
-  Context(long m, long p, long r, long bits, long c, int device = 0) : m_(m) {
+  Context(long m, long p, long r, long bits, long c, int device = 0) : m_(m), p_(p), r_(r) {
     if (hb_chain_build(&chain_, (uint64_t)m, p, (int)r, (int)bits, (int)c, 0, 3, 0, 3.2) != HB_OK)
       throw InvalidArgument(hb_chain_last_error());
     int np, ns, nc, nsp, nd; int64_t phim;
@@ -104,6 +104,8 @@ class Context {
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   long getM() const { return m_; }
+  long getP() const { return p_; }
+  long getR() const { return r_; }
   long getPhiM() const { return phim_; }
   long numPrimes() const { return (long)primes_.size(); }
   long ithPrime(long i) const { return (long)primes_.at(i); }

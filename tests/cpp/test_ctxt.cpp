@@ -158,6 +158,32 @@ int main() {
       try { Ctxt bad(pk, p); bad = cr; bad.parts[1].skHandle.secretKeyID = 1; bad.smartAutomorph(3); } catch (const hb::LogicError&) { threw = true; }
       if (!threw) { std::printf("missing LogicError for unreachable automorphism\n"); return 1; }
     }
+    // linear operations: addCtxt with unequal prime sets and integer factors, addConstant, multByConstant
+    {
+      Ctxt x = encrypt(ma), y = encrypt(mb), z = encrypt(mc);
+      Ctxt sum = x; sum += y;
+      std::vector<long> d = decrypt(sum, nullptr);
+      for (long k = 0; k < N; k++) if (d[k] != (ma[k] + mb[k]) % p) { std::printf("addCtxt mismatch at %ld\n", k); return 1; }
+      Ctxt xy = x; xy.multiplyBy(y);                 // fewer primes, intFactor != 1 in general
+      Ctxt t = xy; t += z;                           // z is mod-UPped and the factors harmonised
+      Ctxt u = z; u -= xy;
+      std::vector<long> dt = decrypt(t, nullptr), du = decrypt(u, nullptr);
+      for (long i = 0; i < 32; i++) {
+        long k = (i * 131 + 7) % N, prod = negacyclic_at(ma, mb, k);
+        if (dt[k] != (prod + mc[k]) % p) { std::printf("product + fresh mismatch at %ld\n", k); return 1; }
+        if (du[k] != ((mc[k] - prod) % p + p) % p) { std::printf("fresh - product mismatch at %ld\n", k); return 1; }
+      }
+      Ctxt v = xy;
+      DoubleCRT cst(mc, ctx, v.primeSet);
+      v.addConstant(cst);
+      std::vector<long> dv = decrypt(v, nullptr);
+      for (long i = 0; i < 32; i++) { long k = (i * 131 + 7) % N; if (dv[k] != (negacyclic_at(ma, mb, k) + mc[k]) % p) { std::printf("addConstant mismatch at %ld\n", k); return 1; } }
+      Ctxt w = x;
+      DoubleCRT cst2(mb, ctx, w.primeSet);
+      w.multByConstant(cst2);
+      std::vector<long> dw = decrypt(w, nullptr);
+      for (long i = 0; i < 32; i++) { long k = (i * 131 + 7) % N; if (dw[k] != negacyclic_at(ma, mb, k)) { std::printf("multByConstant mismatch at %ld\n", k); return 1; } }
+    }
     const long before = ctx.getCtxtPrimes().card(), common = ca.lastCommonPrimeSet.card();
     const double logq_before = logq0, logq_common = logq2;
     ctx.sync();
