@@ -319,10 +319,13 @@ def main():
         base = top["kernel"].replace("_subscale", "")
         if base in tj:
             t8 = tj[base].get("avg_dram_bytes_per_launch_at_batch8")
-            traffic = t8 * B / 8.0 if t8 else None      # captured at batch 8; DRAM bytes per launch scale with the items per launch
+            if t8:
+                traffic = t8 * B / 8.0                  # older capture at batch 8; DRAM bytes per launch scale with the items per launch
+            elif tj[base].get("avg_dram_bytes_per_launch"):
+                traffic = tj[base]["avg_dram_bytes_per_launch"] * B / float(tj[base].get("batch") or B)
         ach = top["bytes"] / (top["ms"] / 1000.0) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_kind": peak_kind, "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of run r01f)" if traffic else None, "share_of_step": top["ms"] / tot_ms,
+                "peak_kind": peak_kind, "traffic": traffic, "traffic_source": ("profiles/ncu_traffic.json: " + str(tj.get("source", ""))[:160]) if traffic else None, "share_of_step": top["ms"] / tot_ms,
                 "launches_per_step": top["launches"], "avg_launch_ms": top["ms"] / top["launches"],
                 "alg_bytes_per_launch": top["bytes"] / top["launches"]}
     kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot_ms, 4),

@@ -13,11 +13,11 @@ echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --s
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
-   python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu --no-e2e > $OUT/ncu_bench_$TAG.log 2>&1
+   python bench.py --steps 1 --warmup 3 --batch 16 --no-cpu --no-e2e > $OUT/ncu_bench_$TAG.log 2>&1
 tail -2 $OUT/ncu_bench_$TAG.log | cut -c1-300
-echo "== ncu full: k_conv / k_fwd_blk / k_inv_blk"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_conv|k1_fwd_blk|k1_inv_blk|k_ks_inner' -s 30 -c 8 -f -o $OUT/prof_$TAG \
-   python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
+echo "== ncu full: one whole step (16 launches of the transform / conversion / inner-product kernels at batch 16)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_conv|k1_fwd_blk|k1_inv_blk|k_ks_inner' -s 48 -c 16 -f -o $OUT/prof_$TAG \
+   python bench.py --steps 1 --warmup 3 --batch 16 --no-cpu --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log | cut -c1-300
 ls -la $OUT
 fi
