@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="independent ciphertext pairs per step and GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=6, help="multiplies timed for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="multiplies timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-streams", type=int, default=4, help="engine contexts (CUDA streams) the e2e loop spreads the batch over")
