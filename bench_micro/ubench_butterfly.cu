@@ -10,7 +10,7 @@ __device__ __forceinline__ void ct_exact(u64& x, u64& y, u64 w, u64 ws, u64 q, u
   x = xr + t; y = xr - t + q2;
 }
 template <int MODE>
-__global__ void __launch_bounds__(256) kb(u64* out, u64 q, u64 nq, u64 q3, u64 seed, int rounds) {
+__global__ void __launch_bounds__(256) kb(u64* out, u64 q, u64 nq, u64 qb, u64 seed, int rounds) {
   u64 a[16];
   Hb1TwReg tw;
 #pragma unroll
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) kb(u64* out, u64 q, u64 nq, u64 q3, u64 s
 #pragma unroll
   for (int i = 0; i < 15; i++) { u64 w = (seed * (i + 3) + 12345) % q; tw.t[i] = make_ulonglong2(w, (u64)(((unsigned __int128)w << 64) / q)); }
   for (int r = 0; r < rounds; r++) {
-    Hb1Mod M; M.nq = nq; M.q3 = q3; M.qt = (unsigned)((q - 1) >> 52); M.qsh = 20;   // q = 237*2^52 + 1
+    Hb1Mod M; M.nq = nq; M.qb = qb; M.qb2 = qb + qb; M.qt = (unsigned)((q - 1) >> 52); M.qsh = 20;   // q = 237*2^52 + 1
     if (MODE == 0) hb1_r16_fwd<false>(a, tw, M);
     else if (MODE == 1) hb1_r16_inv<false>(a, tw, M);
     else if (MODE == 3) hb1_r16_fwd<true>(a, tw, M);
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) kb(u64* out, u64 q, u64 nq, u64 q3, u64 s
           for (int o = 0; o < d; o++) ct_exact(a[g * 2 * d + o], a[g * 2 * d + o + d], w.x, w.y, q, q + q); } }
     }
 #pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = hb1_csub(hb1_csub(a[i], q3), q3);   // keep bounded between rounds
+    for (int i = 0; i < 16; i++) a[i] = hb1_csub_hi(hb1_csub_hi(a[i], qb), qb);   // keep bounded between rounds
   }
   u64 s = 0;
 #pragma unroll
@@ -64,10 +64,10 @@ int main() {
       int blocks = 148 * bps;
       for (int rep = 0; rep < 2; rep++) {
         cudaEventRecord(e0);
-        if (mode == 0) kb<0><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
-        if (mode == 1) kb<1><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
-        if (mode == 2) kb<2><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
-        if (mode == 3) kb<3><<<blocks, 256>>>(out, q, 0 - q, 3 * q, 7, rounds);
+        if (mode == 0) kb<0><<<blocks, 256>>>(out, q, 0 - q, 4 * q, 7, rounds);
+        if (mode == 1) kb<1><<<blocks, 256>>>(out, q, 0 - q, 4 * q, 7, rounds);
+        if (mode == 2) kb<2><<<blocks, 256>>>(out, q, 0 - q, 4 * q, 7, rounds);
+        if (mode == 3) kb<3><<<blocks, 256>>>(out, q, 0 - q, 4 * q, 7, rounds);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
       }
       float ms; cudaEventElapsedTime(&ms, e0, e1);

@@ -46,7 +46,7 @@ struct HbPrimeDev {
   u64 ninv, ninv_s;        // N^-1 mod q (+ Shoup companion floor(w*2^64/q))
   u64 c64, c64_s;          // 2^64 mod q (+ Shoup)
   u64 one_s;               // floor(2^64 / q)
-  u64 nq, q3;              // 2^64 - q and 3q, kept as opaque table values so ptxas does not re-derive them from q
+  u64 nq, qb;              // 2^64 - q and 4q (the lazy bound B of the register kernels), kept as opaque table values so ptxas does not re-derive them from q
   unsigned qt, qsh;        // HElib primes are q = qt*2^s + 1 with s >= 32 (PrimeGenerator picks k maximal,
                            // src/PrimeGenerator.h:54-124): qsh = s-32, qt = (q-1)>>s.  qt = 0 if s < 32 or qt >= 2^32.
   const ulonglong2* fw;    // fw[k] = (psi^brev(k), shoup), k = 1..N-1   (Cooley-Tukey, merged twist)

@@ -41,61 +41,100 @@ __device__ __forceinline__ void hb1_mac128(u64& hi, u64& lo, u64 a, u64 b) {
 #endif
 }
 
-// ---- lazy arithmetic of the register kernels (requires q < 2^60, so 6q < 2^63) -------------
-// Approximate high word of a 64x64 product: drops the lo*lo partial product, so the result is
-// floor(a*b/2^64) or one less.  3 IMAD.WIDE instead of 4 and a shorter carry chain.
+// ---- lazy arithmetic of the register kernels (requires q < 2^60) ---------------------------
+// The kernels are bound by the ALU pipe (IADD3 / ISETP / SEL / SHF: 16 lanes per sub-partition, ncu
+// sm__inst_executed_pipe_alu pinned at its 50 % ceiling) ahead of the FMA-heavy pipe that runs IMAD, so every
+// helper below is written for the fewest ALU instructions: 21 SASS instructions per butterfly (10 ALU), down from 28 (17).
+//
+// Value ranges (B = 4q, kept as the opaque table value qb):
+//   Shoup product t = y*w - Qe*q with Qe in [Q-3, Q]  =>  t in [0, 4q) for ANY 64-bit y;
+//   forward (CT): x, y in [0, 8q + 2^32)  ->  same;   inverse (GS): x, y in [0, 4q + e), e < 2^48  ->  same
+//   (the conditional subtraction compares high words only, which leaves a slack below 2^32 per use).
+// Everything stays below 13q + 2^49 < 2^64.
+
+// 32x32 -> 64 product that ptxas keeps as one IMAD.WIDE (and folds a following 64-bit add/sub into its addend)
+__device__ __forceinline__ u64 hb1_mulwide(unsigned a, unsigned b) {
+#ifdef HB_SIM
+  return (u64)a * b;
+#else
+  u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+#endif
+}
+// Approximate high word of a 64x64 product: hi*hi plus the HIGH halves of the two cross products (one IMAD.WIDE and
+// two IMAD.HI); the dropped low parts make the result floor(a*b/2^64) - {0,1,2}.
 __device__ __forceinline__ u64 hb1_mulhi_approx(u64 a, u64 b) {
   const unsigned alo = (unsigned)a, ahi = (unsigned)(a >> 32), blo = (unsigned)b, bhi = (unsigned)(b >> 32);
-  const u64 p1 = (u64)alo * bhi;
-  const u64 p2 = (u64)ahi * blo + (unsigned)p1;
-  const u64 p3 = (u64)ahi * bhi + (p1 >> 32);
-  return p3 + (p2 >> 32);
+  return hb1_mulwide(ahi, bhi) + (u64)__umulhi(alo, bhi) + (u64)__umulhi(ahi, blo);
 }
 // Modulus view of the butterfly network.  Generic: nq = 2^64 - q (the subtraction of hi*q is folded into
 // the multiply-add chain).  Special (HElib's q = qt*2^s + 1, s >= 32): hi*q mod 2^64 = hi + ((lo32(hi)*qt) << s),
-// one 32-bit IMAD and a shift instead of a 64-bit multiply -- the FMA-heavy pipe is the bottleneck of these kernels.
+// one 32-bit IMAD and a shift instead of a 64-bit multiply.
 struct Hb1Mod {
-  u64 nq, q3;
+  u64 nq, qb, qb2;     // 2^64 - q, B = 4q, 2B
   unsigned qt, qsh;
 };
-// y*w mod q up to a multiple of q: result in [0,3q) for ANY 64-bit y (Shoup quotient off by <= 2).
+#define HB1_MOD(M, P) Hb1Mod M; M.nq = (P).nq; M.qb = (P).qb; M.qb2 = (P).qb + (P).qb; M.qt = (P).qt; M.qsh = (P).qsh
+// y*w mod q up to a multiple of q: result in [0,4q) for ANY 64-bit y (Shoup quotient off by <= 3).
 template <bool SP>
-__device__ __forceinline__ u64 hb1_shoup3(u64 y, u64 w, u64 ws, const Hb1Mod& M) {
+__device__ __forceinline__ u64 hb1_shoup4(u64 y, u64 w, u64 ws, const Hb1Mod& M) {
   const u64 hi = hb1_mulhi_approx(y, ws);
   if (SP) {
     const unsigned tl = (unsigned)hi * M.qt;
-    const u64 hq = hi + ((u64)(tl << M.qsh) << 32);
-    return y * w - hq;
+    const unsigned ylo = (unsigned)y, yhi = (unsigned)(y >> 32), wlo = (unsigned)w, whi = (unsigned)(w >> 32);
+    const u64 R = hb1_mulwide(ylo, wlo) - hi;                                        // IMAD.WIDE with negated addend
+    const unsigned rhi = (unsigned)(R >> 32) + yhi * wlo + ylo * whi - (tl << M.qsh);   // the rest only touches the high word
+    return ((u64)rhi << 32) | (unsigned)R;
   }
   return y * w + hi * M.nq;
 }
-// x in [0,2m) -> [0,m) by one conditional subtraction decided on the sign of x-m (both < 2^63)
+// x in [0,2m) -> [0,m) by one conditional subtraction decided on the sign of x-m (both < 2^63): exact
 __device__ __forceinline__ u64 hb1_csub(u64 x, u64 m) {
   const u64 d = x - m;
   return (i64)d < 0 ? x : d;
 }
-// Cooley-Tukey butterfly, x,y in [0,6q) -> [0,6q)
+// Lazy conditional subtraction: x -= m when the HIGH word of x exceeds that of m (then x > m).  Otherwise x < m + 2^32.
+// One ISETP and a predicated subtract.
+__device__ __forceinline__ u64 hb1_csub_hi(u64 x, u64 m) {
+#ifdef HB_SIM
+  if ((unsigned)(x >> 32) > (unsigned)(m >> 32)) x -= m;
+  return x;
+#else
+  unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+  asm("{ .reg .pred p; setp.gt.u32 p, %1, %3; @p sub.cc.u32 %0, %0, %2; @p subc.u32 %1, %1, %3; }"
+      : "+r"(xl), "+r"(xh) : "r"((unsigned)m), "r"((unsigned)(m >> 32)));
+  return ((u64)xh << 32) | xl;
+#endif
+}
+// Cooley-Tukey butterfly, x,y in [0, 8q + 2^32) -> same
 template <bool SP>
 __device__ __forceinline__ void hb1_ct(u64& x, u64& y, u64 w, u64 ws, const Hb1Mod& M) {
-  const u64 xr = hb1_csub(x, M.q3);
-  const u64 t = hb1_shoup3<SP>(y, w, ws, M);
+  const u64 xr = hb1_csub_hi(x, M.qb);          // < 4q + 2^32
+  const u64 t = hb1_shoup4<SP>(y, w, ws, M);    // < 4q
   x = xr + t;
-  y = xr - t + M.q3;
+  y = xr - t + M.qb;
 }
-// Gentleman-Sande butterfly, x,y in [0,3q) -> [0,3q)
+// Gentleman-Sande butterfly, x,y in [0, 4q + e) -> [0, 4q + max(2e, 2^32)), [0, 4q)
 template <bool SP>
 __device__ __forceinline__ void hb1_gs(u64& x, u64& y, u64 w, u64 ws, const Hb1Mod& M) {
   const u64 s = x + y;
-  const u64 d = x - y + M.q3;
-  x = hb1_csub(s, M.q3);
-  y = hb1_shoup3<SP>(d, w, ws, M);
+  const u64 d = x - y + M.qb2;                  // > 0 despite the slack of y
+  x = hb1_csub_hi(s, M.qb);
+  y = hb1_shoup4<SP>(d, w, ws, M);
 }
-__device__ __forceinline__ u64 hb1_canon3(u64 x, u64 q) {  // [0,3q) -> [0,q)
+__device__ __forceinline__ u64 hb1_canon4(u64 x, u64 q) {  // exact [0,4q) -> [0,q)
   x = hb1_csub(x, q + q);
   return hb1_csub(x, q);
 }
-__device__ __forceinline__ u64 hb1_canon6(u64 x, u64 q) {  // [0,6q) -> [0,q)
-  return hb1_canon3(hb1_csub(x, 3 * q), q);
+__device__ __forceinline__ u64 hb1_canon_fwd(u64 x, u64 q, u64 qb) {  // forward network output [0, 8q + 2^32) -> [0,q)
+  x = hb1_csub_hi(x, qb);                        // < 4q + 2^32 < 2^63: the exact form is valid from here on
+  x = hb1_csub(x, q + q);                        // < 2q + 2^32
+  x = hb1_csub(x, q);                            // < q + 2^32 < 2q
+  return hb1_csub(x, q);
+}
+__device__ __forceinline__ u64 hb1_canon_inv(u64 x, u64 q) {  // inverse network output [0, 4q + 2^48) -> [0,q)
+  x = hb1_csub(x, q + q);                        // < 2q + 2^48   (4q + 2^48 < 2^63)
+  x = hb1_csub(x, q);                            // < q + 2^48 < 2q
+  return hb1_csub(x, q);
 }
 
 // 4 forward stages on 16 registers; twiddle of stage k (distance 8>>k), group g is tw[(1<<k)-1+g]
@@ -226,13 +265,13 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
   hb1_cp_commit();
   int key = -1, buf = 0;
   u64 q = 0, sc = 0, sc_s = 0;
-  Hb1Mod M; M.nq = 0; M.q3 = 0; M.qt = 0; M.qsh = 0;
+  Hb1Mod M; M.nq = 0; M.qb = 0; M.qb2 = 0; M.qt = 0; M.qsh = 0;
   Hb1TwReg tw2;
   for (long u = ubeg; u < uend; u++, buf ^= 1) {
     if (cur.rowi * G + cur.ug != key) {   // new (row, block group): reload modulus and twiddles
       key = cur.rowi * G + cur.ug;
       const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
-      q = P.q; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+      q = P.q; M.nq = P.nq; M.qb = P.qb; M.qb2 = P.qb + P.qb; M.qt = P.qt; M.qsh = P.qsh;
       sc = J.scal[cur.rowi]; sc_s = J.scal_s[cur.rowi];
       const unsigned b1 = hb_brev((cur.ug << 4) + blk1, n1), b2 = hb_brev((cur.ug << 4) + blk2, n1);
       if (lo < 15) {  // entry e = (1<<k)-1+g of block blk1
@@ -279,8 +318,8 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
     for (int l = 0; l < 16; l++) {
       const size_t o = (size_t)((hb1_brev4(l) << 4) | hrev) << n1;   // brev8(16*hi + l) * N1
       u64 v;
-      if (epi) v = hb1_canon3(hb1_shoup3<SP>(O[l * 256 + tid] - a[l] + 2 * M.q3, sc, sc_s, M), q);   // (old - x) * P^-1, x in [0,6q)
-      else v = hb1_canon6(a[l], q);
+      if (epi) v = hb1_canon4(hb1_shoup4<SP>(O[l * 256 + tid] - a[l] + (M.qb2 + M.qb), sc, sc_s, M), q);   // (old - x) * P^-1, x in [0, 8q + 2^32)
+      else v = hb1_canon_fwd(a[l], q, M.qb);
       dst[o] = v;
     }
     __syncthreads();   // exchange reads of Sb / TW1 done before they are overwritten
@@ -320,14 +359,14 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
   hb1_cp_commit();
   int key = -1, buf = 0;
   u64 q = 0;
-  Hb1Mod M; M.nq = 0; M.q3 = 0; M.qt = 0; M.qsh = 0;
+  Hb1Mod M; M.nq = 0; M.qb = 0; M.qb2 = 0; M.qt = 0; M.qsh = 0;
   unsigned b1 = 0;
   Hb1TwReg tw2;
   for (long u = ubeg; u < uend; u++, buf ^= 1) {
     if (cur.rowi * G + cur.ug != key) {
       key = cur.rowi * G + cur.ug;
       const HbPrimeDev P = primes[J.rows.prime[cur.rowi]];
-      q = P.q; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+      q = P.q; M.nq = P.nq; M.qb = P.qb; M.qb2 = P.qb + P.qb; M.qt = P.qt; M.qsh = P.qsh;
       b1 = hb_brev((cur.ug << 4) + blk1, n1);
       const unsigned b2 = hb_brev((cur.ug << 4) + blk2, n1);
       if (lo < 15) {
@@ -365,7 +404,7 @@ __global__ void __launch_bounds__(256, 2) k1_inv_blk(const HbPrimeDev* __restric
     hb1_r16_inv<SP>(a, tw1, M);
     u64* dst = J.dst[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN) + ((size_t)b1 << 8) + lo;
 #pragma unroll
-    for (int r = 0; r < 16; r++) dst[16 * r] = hb1_canon3(a[r], q);
+    for (int r = 0; r < 16; r++) dst[16 * r] = J.epi == 2 ? a[r] : hb1_canon_inv(a[r], q);   // epi 2: the consumer is a register kernel (lazy values are fine)
     __syncthreads();
     cur = nxt;
   }
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+  const u64 q = P.q; HB1_MOD(M, P);
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = lo in pass 1 (on r), hi in pass 2 (on lo)
@@ -413,7 +452,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
     for (int l = 0; l < 16; l++) a[l] = T[c * HB1_BS + HB1_RS * x + l];
     hb1_r16_fwd<SP>(a, tw2, M);
 #pragma unroll
-    for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = hb1_canon6(a[l], q);
+    for (int l = 0; l < 16; l++) dst[(size_t)(16 * x + l) << 8] = a[l];   // lazy, [0, 8q + 2^32): the consumer is always k1_fwd_blk
     __syncthreads();
   }
 }
@@ -424,7 +463,7 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+  const u64 q = P.q; HB1_MOD(M, P);
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = hi in pass 1 (on lo), lo in pass 2 (on r)
@@ -490,7 +529,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int j = grp; j < n; j += NG) {
     const int pi = cv->src_prime[j];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+    const u64 q = P.q; HB1_MOD(M, P);
     const u64* s = src + ((size_t)pi << J.logN) + c0 + c;
     u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS;
     u64 a[16];
@@ -535,7 +574,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int t = grp; t < nt; t += NG) {
     const int pi = cv->tgt_prime[t];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q; Hb1Mod M; M.nq = P.nq; M.q3 = P.q3; M.qt = P.qt; M.qsh = P.qsh;
+    const u64 q = P.q; HB1_MOD(M, P);
     const u64* ct = cv->c + (size_t)t * n;
     u64 a[16];
     {
@@ -578,6 +617,6 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     }
     u64* d = dst + ((size_t)pi << J.logN) + c0 + c;
 #pragma unroll
-    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = hb1_canon6(a[l], q);
+    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = a[l];   // lazy: k1_fwd_blk finishes the transform
   }
 }

@@ -183,7 +183,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   const size_t N = c->N;
   for (int i = 0; i < nprimes; i++) {
     u64 qi = q[i];
-    // HElib primes are < 2^HELIB_SP_NBITS = 2^60 (src/macro.h:16-23); the lazy butterflies need 6q < 2^63
+    // HElib primes are < 2^HELIB_SP_NBITS = 2^60 (src/macro.h:16-23); the lazy butterflies need 13q + 2^49 < 2^64
     if (qi < 3 || qi >= (1ULL << 60) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^60 with m | q-1", i, (unsigned long long)qi); }
     u64 ps = 0;
     if (pow2) {
@@ -204,7 +204,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
       HbPrimeDev& P = c->h_primes[i];
       memset(&P, 0, sizeof(P));
       P.q = qi; P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi); P.one_s = (u64)(((u128)1 << 64) / qi);
-      P.nq = 0 - qi; P.q3 = 3 * qi;
+      P.nq = 0 - qi; P.qb = 4 * qi;
       { int sh = 0; u64 t = qi - 1; while ((t & 1) == 0) { t >>= 1; sh++; }
         if (sh >= 32 && t < (1ULL << 32)) { P.qt = (unsigned)t; P.qsh = (unsigned)(sh - 32); } }
     }
@@ -246,7 +246,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     P.ninv = h_powmod((u64)N % qi, qi - 2, qi); P.ninv_s = h_shoup(P.ninv, qi);
     P.c64 = (u64)(((u128)1 << 64) % qi); P.c64_s = h_shoup(P.c64, qi);
     P.one_s = (u64)(((u128)1 << 64) / qi);
-    P.nq = 0 - qi; P.q3 = 3 * qi;
+    P.nq = 0 - qi; P.qb = 4 * qi;
     { int sh = 0; u64 t = qi - 1; while ((t & 1) == 0) { t >>= 1; sh++; }
       if (sh >= 32 && t < (1ULL << 32)) { P.qt = (unsigned)t; P.qsh = (unsigned)(sh - 32); } else { P.qt = 0; P.qsh = 0; } }
     P.fw = c->d_tw + ((size_t)i * 2 + 0) * N;
@@ -540,6 +540,7 @@ static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* 
     int nr = std::min(HB_MAXROWS, n - r0);
     Hb1BlkJob J; memset(&J, 0, sizeof(J));
     J.logN = c->logN; J.epi = epi;
+    if (dir < 0) J.epi = v1_cols_ok(c) ? 2 : 0;   // inverse: the next phase is a register kernel (cols or fused conversion) -> lazy values may stay
     fill_rows(J.rows, idx + r0, nr);
     for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
     J.nitems = nitems;

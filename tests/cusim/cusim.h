@@ -42,6 +42,7 @@ void bar_sync(int id, int count);  // named barrier (PTX bar.sync id, count)
 #define __syncthreads() cusim::syncthreads()
 #define __ldg(p) (*(p))
 
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }

@@ -261,6 +261,66 @@ def test_sim_generic_modulus_path(sim_lib, monkeypatch):
     test_sim_full_ring_dimension_small_chain(sim_lib)
 
 
+def _largest_primes(form, count, m):
+    """Largest primes below 2^60 with m | q-1: 'sp' = t*2^32+1 (the shift form of the register kernels), 'gen' = k*m+1."""
+    out = []
+    if form == "sp":
+        t = (1 << 28) - 1
+        while len(out) < count:
+            q = (t << 32) + 1
+            if po.is_prime(q):
+                out.append(q)
+            t -= 1
+    else:
+        k = ((1 << 60) - 2) // m
+        while len(out) < count:
+            q = k * m + 1
+            if q < (1 << 60) and (q - 1) % (1 << 32) != 0 and po.is_prime(q):
+                out.append(q)
+            k -= 1
+    return out
+
+
+@pytest.mark.parametrize("form", ["sp", "gen"])
+def test_lazy_ranges_at_the_largest_primes(lib, form):
+    """The register kernels keep values in [0, 8q + 2^32) (forward) / [0, 4q + 2^48) (inverse) with q < 2^60; the
+    margins are smallest for the largest admissible primes and for inputs at the top of the range.  Rows of q-1, of
+    alternating 0 / q-1 and random rows through the N = 2^16 transforms and a base extension, against the oracle."""
+    from helib_b200.engine import Engine
+    m = 1 << 17
+    primes = _largest_primes(form, 3, m)
+    assert all(q < (1 << 60) and q > (1 << 60) - (1 << 40) for q in primes)
+    psis = [po.find_psi(q, m) for q in primes]
+    N = m // 2
+    O = orc.Oracle(N, m, primes, psis, [[0, 1]], [2], nthreads=8)
+    E = Engine(m, primes, psis, [[0, 1]], [2], lib=lib)
+    rng = np.random.default_rng(3)
+    idx = [0, 1, 2]
+    x = O.random(rng, idx)
+    for i, q in enumerate(primes):
+        x[i][: N // 4] = q - 1
+        x[i][N // 4: N // 2: 2] = 0
+        x[i][N // 4 + 1: N // 2: 2] = q - 1
+    P = E.poly(x, idx)
+    E.ntt_inv([P], idx)
+    ref = x.copy(); O.ntt_inv_rows(ref, idx)
+    assert rows_equal(P.download(idx), ref, idx)
+    E.ntt_fwd([P], idx)
+    assert rows_equal(P.download(idx), x, idx)
+    # forward transform of extreme coefficient vectors
+    E.ntt_fwd([P], idx)
+    ref = x.copy(); O.ntt_fwd_rows(ref, idx)
+    assert rows_equal(P.download(idx), ref, idx)
+    # exact base extension {0,1} -> {2} (fused conversion kernel) and mod-down back
+    Y = E.poly(x, [0, 1])
+    E.add_primes([Y], [0, 1], [2])
+    ref = x.copy(); O.add_primes(ref, [0, 1], [2])
+    assert rows_equal(Y.download(idx), ref, idx)
+    E.scale_down([Y], idx, [0, 1], 1)
+    O.scale_down(ref, idx, [0, 1], 1)
+    assert rows_equal(Y.download([0, 1]), ref, [0, 1])
+
+
 @pytest.mark.parametrize("cfg", [(64, 257, 1, 120, 2), (4096, 257, 1, 60, 2), (8192, -1, 1, 119, 2)])
 def test_hoisted_automorph_keyswitch(lib, cfg):
     """one breakIntoDigits, many (automorph + keySwitchDigits) -- BasicAutomorphPrecon
