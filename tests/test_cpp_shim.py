@@ -68,3 +68,15 @@ def test_ctxt_encrypt_multiply_decrypt_on_simulator():
     """PubKey::Encrypt -> Ctxt::multiplyBy -> SecKey::Decrypt through the mirror, kernels on the CPU simulator."""
     r = subprocess.run([build_exe("test_ctxt", sim=True)], capture_output=True, text=True)
     assert r.returncode == 0 and "ctxt OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_ckks_multiply_through_mirror_on_simulator():
+    """CKKS branches of the Ctxt mirror (scaling factors, CKKS interval for the common prime set, relin_CKKS_adjust)."""
+    r = subprocess.run([build_exe("test_ckks", sim=True)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ckks OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_ckks_multiply_through_mirror_on_gpu():
+    r = subprocess.run([build_exe("test_ckks")], capture_output=True, text=True)
+    assert r.returncode == 0 and "ckks OK" in r.stdout, r.stdout + r.stderr
