@@ -47,6 +47,15 @@ struct XD {
     if (e >= o.e) { long d = e - o.e; return d > 1100 ? *this : make(m + std::ldexp(o.m, (int)-d), e); }
     return o + *this;
   }
+  XD operator-() const { XD r = *this; r.m = -r.m; return r; }
+  XD operator-(const XD& o) const { return *this + (-o); }
+  XD abs() const { XD r = *this; r.m = std::fabs(r.m); return r; }
+  // exact integer value floor(v) of a non-negative XD as mant * 2^shift (mant < 2^63)
+  void floorParts(uint64_t& mant, long& shift) const {
+    if (m <= 0 || e <= 0) { mant = 0; shift = 0; return; }
+    if (e <= 62) { mant = (uint64_t)std::floor(std::ldexp(m, (int)e)); shift = 0; return; }
+    mant = (uint64_t)std::ldexp(m, 53); shift = e - 53;      // 53-bit mantissa: already an integer
+  }
   bool operator<(const XD& o) const { if (m <= 0 || o.m <= 0) return m < o.m; return e != o.e ? e < o.e : m < o.m; }
   bool operator>(const XD& o) const { return o < *this; }
   bool operator<=(const XD& o) const { return !(o < *this); }
@@ -352,7 +361,7 @@ class Ctxt {
     tmp.tensorProduct(*this, other);
     *this = tmp;
   }
-  // ---- linear operations (BGV branches; the CKKS branches need equalizeRationalFactors, src/Ctxt.cpp:1196-1394, not mirrored)
+  // ---- linear operations (addConstant / multByConstant: BGV branches only)
   void negate() { for (auto& part : parts) part.dcrt.Negate(); }   // src/Ctxt.cpp:1190-1194
   void reducePtxtSpace(long newPtxtSpace) {   // src/Ctxt.cpp:576-584
     long g = std::gcd(ptxtSpace, newPtxtSpace);
@@ -372,8 +381,8 @@ class Ctxt {
     if (&pubKey != &other.pubKey) throw LogicError("Public key mismatch");
     if (other.isEmpty()) return;
     if (isEmpty()) { *this = other; if (negative) negate(); return; }
-    if (isCKKS()) throw LogicError("Ctxt::addCtxt: the CKKS branch (equalizeRationalFactors) is not mirrored");
-    reducePtxtSpace(other.ptxtSpace);
+    if (isCKKS()) { if (ptxtSpace != 1 || other.ptxtSpace != 1) throw LogicError("Plaintext spaces incompatible"); }
+    else reducePtxtSpace(other.ptxtSpace);
     Ctxt tmp(pubKey, other.ptxtSpace);
     const Ctxt* other_pt = &other;
     if (ptxtSpace != other_pt->ptxtSpace) { tmp = other; tmp.reducePtxtSpace(ptxtSpace); other_pt = &tmp; }
@@ -381,8 +390,9 @@ class Ctxt {
     if (!empty(s)) modUpToSet(s);
     s = primeSet / other_pt->primeSet;
     if (!empty(s)) { if (other_pt != &tmp) { tmp = other; other_pt = &tmp; } tmp.modUpToSet(s); }
+    if (isCKKS()) { if (other_pt != &tmp) { tmp = other; other_pt = &tmp; } equalizeRationalFactors(*this, tmp, context.getR()); }
     long e1 = 1, e2 = 1;
-    if (intFactor != other_pt->intFactor) {   // harmonise: e1*f1 == e2*f2 (mod ptxtSpace) with the least noise growth (:1475-1527)
+    if (!isCKKS() && intFactor != other_pt->intFactor) {   // harmonise: e1*f1 == e2*f2 (mod ptxtSpace) with the least noise growth (:1475-1527)
       const long f1 = intFactor, f2 = other_pt->intFactor;
       const long ratio = (long)(((unsigned __int128)(unsigned long)f2 * (unsigned long)invMod(f1, ptxtSpace)) % (unsigned long)ptxtSpace);
       auto noiseNorm = [&](long a, long b) { return noiseBound * XD((double)std::labs(balRem(a, ptxtSpace))) + other_pt->noiseBound * XD((double)std::labs(balRem(b, ptxtSpace))); };
@@ -408,6 +418,49 @@ class Ctxt {
     }
     ptxtMag = ptxtMag + other_pt->ptxtMag;
     noiseBound = noiseBound + other_pt->noiseBound;
+  }
+  // src/Ctxt.cpp:1199-1351 ("NEW VERSION"): bring two CKKS ciphertexts to a common scaling factor by multiplying them by
+  // the numerator / denominator of a continued-fraction approximation of the ratio, stopping as soon as the
+  // discretisation error is within sqrt(2) of the unavoidable one.  r = Context::getPrecision().
+  static void equalizeRationalFactors(Ctxt& c1, Ctxt& c2, long r) {
+    Ctxt& big = (c1.ratFactor > c2.ratFactor) ? c1 : c2;
+    Ctxt& small = (c1.ratFactor > c2.ratFactor) ? c2 : c1;
+    const XD x = big.ratFactor / small.ratFactor;
+    const double denomBound = std::ldexp(1.0, (int)r + 1);
+    const double epsilon = 0.125 / denomBound;
+    auto calc_err = [](const XD& f, const XD& m1, const XD& f1, const XD& e1, const XD& m2, const XD& f2, const XD& e2) {
+      return m1 * (f1 / f - XD(1.0)).abs() + m2 * (f2 / f - XD(1.0)).abs() + (e1 + e2) / f;
+    };
+    auto floorXD = [](const XD& v) { uint64_t mant; long sh; v.floorParts(mant, sh); return XD::make((double)mant, sh); };
+    XD xi = x - floorXD(x + XD(epsilon));
+    double prevDenom = 0, denom = 1;
+    XD numer = floorXD(XD(denom) * x + XD(0.5));
+    const XD m1 = big.ptxtMag, of1 = big.ratFactor, oe1 = big.noiseBound;
+    const XD m2 = small.ptxtMag, of2 = small.ratFactor, oe2 = small.noiseBound;
+    const XD target_error = oe1 / of1 + oe2 / of2;
+    XD f, fe1, fe2;
+    for (;;) {
+      const XD xdenom(denom);
+      const XD f1 = of1 * xdenom, e1 = oe1 * xdenom, f2 = of2 * numer, e2 = oe2 * numer;
+      const XD err1 = calc_err(f1, m1, f1, e1, m2, f2, e2), err2 = calc_err(f2, m1, f1, e1, m2, f2, e2);
+      XD err;
+      if (err1 < err2) { f = f1; fe1 = e1; fe2 = e2 + m2 * (f2 - f1).abs(); err = err1; }
+      else { f = f2; fe1 = e1 + m1 * (f2 - f1).abs(); fe2 = e2; err = err2; }
+      if (err < XD(std::sqrt(2.0)) * target_error) break;
+      if (xi.m <= 0) break;
+      xi = XD(1.0) / xi;
+      const XD ai = floorXD(xi + XD(epsilon));
+      xi = xi - ai;
+      const double tmpDenom = denom * ai.to_double() + prevDenom;
+      if (tmpDenom > denomBound) break;
+      prevDenom = denom; denom = tmpDenom;
+      numer = floorXD(XD(denom) * x + XD(0.5));
+    }
+    if (denom != 1) for (auto& part : big.parts) part.dcrt *= (long)denom;
+    big.ratFactor = f; big.noiseBound = fe1;
+    uint64_t nm; long nsh; numer.floorParts(nm, nsh);
+    if (!(nm == 1 && nsh == 0)) for (auto& part : small.parts) part.dcrt.mulByPow2Scaled(nm, nsh);
+    small.ratFactor = f; small.noiseBound = fe2;
   }
   Ctxt& operator+=(const Ctxt& o) { addCtxt(o); return *this; }
   Ctxt& operator-=(const Ctxt& o) { addCtxt(o, true); return *this; }

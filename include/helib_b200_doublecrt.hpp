@@ -197,6 +197,19 @@ class DoubleCRT {
     if (!idx.empty()) { hb_poly* d[1] = {p_}; check(hb_scale_rows(d, 1, idx.data(), (int)idx.size(), sc.data())); }
     return *this;
   }
+  // Op(ZZ, MulFun) for a big non-negative scalar given as mant * 2^shift (the integers NTL converts out of an xdouble)
+  DoubleCRT& mulByPow2Scaled(uint64_t mant, long shift) {
+    auto idx = set_.vec();
+    std::vector<uint64_t> sc;
+    for (int i : idx) {
+      const uint64_t q = (uint64_t)context_->ithPrime(i);
+      unsigned __int128 r = mant % q, b = 2 % q;
+      for (long e = shift; e > 0; e >>= 1) { if (e & 1) r = r * b % q; b = b * b % q; }
+      sc.push_back((uint64_t)r);
+    }
+    if (!idx.empty()) { hb_poly* d[1] = {p_}; check(hb_scale_rows(d, 1, idx.data(), (int)idx.size(), sc.data())); }
+    return *this;
+  }
   // operator/= by the product of a set of chain primes (what the hot path divides by; src/DoubleCRT.cpp:1122-1139)
   DoubleCRT& divideByPrimes(const IndexSet& f) {
     auto idx = set_.vec(), fi = f.vec();

@@ -108,7 +108,25 @@ int main() {
     ca.dropSmallAndSpecialPrimes();
     std::vector<double> prod2 = decode(ca, &nl);
     for (long t = 0; t < 64; t++) { long k = (t * 521 + 3) % N; if (std::fabs(prod2[k] - prod[k]) > std::exp2(nl) + tol) { std::printf("mod-down changed the value at %ld\n", k); return 1; } }
+    // addCtxt across different scaling factors (equalizeRationalFactors, src/Ctxt.cpp:1199-1351): product + fresh
+    std::vector<long> mc(N);
+    for (long k = 0; k < N; k++) mc[k] = (long)(gen() % 7) - 3;
+    Ctxt cc = encrypt(mc);
+    const double rf_before = std::log2((double)ca.ratFactor.m) + (double)ca.ratFactor.e;
+    Ctxt sum = ca; sum += cc;
+    if (std::fabs((sum.ratFactor / cc.ratFactor).to_double() - std::round((sum.ratFactor / cc.ratFactor).to_double())) > 1e-6 && sum.ratFactor.e < 60) { std::printf("common factor is not an integer multiple\n"); return 1; }
+    std::vector<double> ds = decode(sum, &nl);
+    const double tol2 = std::exp2(nl);
+    for (long t = 0; t < 64; t++) {
+      long k = (t * 521 + 3) % N;
+      if (std::fabs(ds[k] - (prod2[k] + (double)mc[k])) > tol2 + tol) { std::printf("CKKS sum mismatch at %ld: %g vs %g (bound %g)\n", k, ds[k], prod2[k] + mc[k], tol2); return 1; }
+    }
+    if (tol2 > 0.05) { std::printf("tracked bound after the sum %.3g is useless\n", tol2); return 1; }
+    Ctxt diff = cc; diff -= ca;
+    std::vector<double> dd = decode(diff, &nl);
+    for (long t = 0; t < 64; t++) { long k = (t * 521 + 3) % N; if (std::fabs(dd[k] - ((double)mc[k] - prod2[k])) > std::exp2(nl) + tol) { std::printf("CKKS difference mismatch at %ld\n", k); return 1; } }
     ctx.sync();
+    std::printf("ckks add OK: log2 ratFactor %.1f + 30.0 -> %.1f, bound %.3g\n", rf_before, std::log2((double)sum.ratFactor.m) + (double)sum.ratFactor.e, tol2);
     std::printf("ckks OK: %.0f -> %.0f bits after multiplyBy, log2 ratFactor %.1f, error %.3g <= bound %.3g, KS-noise-ratio %.3g\n",
                 logq0 / std::log(2.0), pk.logOfProduct(ca.primeSet) / std::log(2.0), std::log2((double)ca.ratFactor.m) + (double)ca.ratFactor.e, worst, tol, ca.lastKSNoiseRatio);
     return 0;
