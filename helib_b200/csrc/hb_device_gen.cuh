@@ -134,3 +134,89 @@ __global__ void __launch_bounds__(HB_THREADS) k_gen_automorph(HbGenAutoJob J) {
     J.dst[blockIdx.z][off + j] = J.src[blockIdx.z][off + J.irep[r]];
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Powerful basis (src/powerful.cpp) and Ctxt::rawModSwitch (src/Ctxt.cpp:2949-3046), SURVEY 8f-4.
+// polyToPowerful is a Z-linear map with coefficients in {0, +-1}: scatter by the CRT index map into the
+// (m_1 x ... x m_k) cube, reduce every hypercolumn of dimension d modulo Phi_{m_d}, read off the
+// (phi(m_1) x ... x phi(m_k)) sub-cube.  Applied to the coefficient rows of every prime, then the exact CRT of the
+// engine gives the balanced integers modulo Q -- PowerfulDCRT::dcrtToPowerful without leaving the device.
+struct HbPwJob2 {
+  u64 m, phim;
+  HbRows rows;
+  const int* cube_to_poly;    // [m]    exponent held by a cube cell
+  const int* short_to_long;   // [phim] cube cell of a powerful coefficient
+  const u64* src;             // coefficient rows [nprimes][phim]
+  u64* cube;                  // scratch [nprimes][m]
+  u64* dst;                   // powerful rows [nprimes][phim]
+  // reduction pass of one dimension (m_d = p^e): stride = cells between consecutive coordinates, b = p^(e-1)
+  u64 stride, md, p, b;
+};
+__global__ void __launch_bounds__(HB_THREADS) k_pw_scatter(const HbPwJob2 J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < J.m; j += (size_t)gridDim.x * blockDim.x) {
+    const int i = J.cube_to_poly[j];
+    J.cube[(size_t)pi * J.m + j] = (u64)i < J.phim ? J.src[(size_t)pi * J.phim + i] : 0;
+  }
+}
+// column mod Phi_{p^e}(X) = sum_{j<p} X^(j*b): c[j*b + t] -= c[(p-1)*b + t] for j < p-1   (the top block is then dead)
+__global__ void __launch_bounds__(HB_THREADS) k_pw_reduce(const HbPrimeDev* __restrict__ primes, const HbPwJob2 J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const u64 q = primes[pi].q;
+  u64* cube = J.cube + (size_t)pi * J.m;
+  const u64 ncol = J.m / J.md, work = ncol * J.b;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += (u64)gridDim.x * blockDim.x) {
+    const u64 col = w / J.b, t = w - col * J.b;
+    const u64 outer = col / J.stride, inner = col - outer * J.stride;    // column = all cells sharing the other coordinates
+    u64* c = cube + outer * J.stride * J.md + inner;
+    const u64 top = c[((J.p - 1) * J.b + t) * J.stride];
+    for (u64 j = 0; j + 1 < J.p; j++) { u64* x = c + (j * J.b + t) * J.stride; *x = hb_submod(*x, top, q); }
+  }
+}
+__global__ void __launch_bounds__(HB_THREADS) k_pw_gather(const HbPwJob2 J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < J.phim; i += (size_t)gridDim.x * blockDim.x)
+    J.dst[(size_t)pi * J.phim + i] = J.cube[(size_t)pi * J.m + J.short_to_long[i]];
+}
+
+// rawModSwitch of one coefficient vector (powerful basis): c balanced mod Q  ->  x = round(c*q/Q) + delta, reduced
+// symmetrically mod q, where delta = bal(Y * Q^-1 mod p^r) and Y = c*q - round(c*q/Q)*Q (src/Ctxt.cpp:2990-3033).
+// With y_j = c_j*(Q/q_j)^-1 mod q_j (so c = sum y_j Q_j - V0*Q) and y'_j = y_j*q mod q_j = y_j*q - k_j*q_j (so
+// Y = sum y'_j Q_j - vY*Q):   round(c*q/Q) = sum_j k_j + vY - q*V0,   and hb_conv_v with the plaintext modulus
+// returns vY + delta with exactly the reference's tie rule.  All quantities are exact integers.
+struct HbRawMsJob {
+  const HbConvDev* cv;
+  const u64* t; const u64* t_s;      // (Q/q_j)^-1 mod q_j
+  u64 N, q;
+  const u64* src;                    // [nprimes][N] coefficient-like rows
+  i64* out;                          // [N]
+  u64* stats;
+};
+__global__ void __launch_bounds__(HB_THREADS) k_raw_mod_switch(const HbPrimeDev* __restrict__ primes, HbRawMsJob J) {
+  const HbConvDev* cv = J.cv;
+  const int n = cv->n;
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= J.N) return;
+  u64 y[HB_MAXROWS];
+  for (int j = 0; j < n; j++) {
+    const int pi = cv->src_prime[j];
+    y[j] = hb_mul_shoup(J.src[(size_t)pi * J.N + k], J.t[j], J.t_s[j], primes[pi].q);
+  }
+  const i64 v0 = hb_conv_v(cv, y, 1, J.stats, nullptr, false);
+  i64 ksum = 0;
+  for (int j = 0; j < n; j++) {
+    const HbPrimeDev P = primes[cv->src_prime[j]];
+    const u64 lo = y[j] * J.q, hi = __umul64hi(y[j], J.q);
+    const u64 r = hb_reduce128(hi, lo, P);
+    u64 inv = P.q;                                        // q_j^-1 mod 2^64 (Newton; q_j odd)
+    for (int it = 0; it < 5; it++) inv *= 2 - P.q * inv;
+    ksum += (i64)((lo - r) * inv);                        // exact quotient (y_j*q - r)/q_j < q
+    y[j] = r;
+  }
+  const i64 v1 = hb_conv_v(cv, y, 1, J.stats, nullptr, true);
+  i64 x = ksum + v1 - (i64)J.q * v0;
+  const i64 qh = (i64)(J.q >> 1);
+  if (x > qh) x -= (i64)J.q;                              // ties of an even q stay (the reference flips a coin there)
+  else if (x < -qh) x += (i64)J.q;
+  J.out[k] = x;
+}

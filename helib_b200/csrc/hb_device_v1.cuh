@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_cols(const HbPrimeDev* __restri
   const int tid = threadIdx.x;
   const int pi = J.rows.prime[blockIdx.y];
   const HbPrimeDev P = primes[pi];
-  const u64 q = P.q; HB1_MOD(M, P);
+  HB1_MOD(M, P);
   const size_t rowoff = (size_t)pi << J.logN;
   const unsigned c0 = blockIdx.x << 4;
   const int c = tid & 15, x = tid >> 4;  // x = lo in pass 1 (on r), hi in pass 2 (on lo)
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   for (int t = grp; t < nt; t += NG) {
     const int pi = cv->tgt_prime[t];
     const HbPrimeDev P = primes[pi];
-    const u64 q = P.q; HB1_MOD(M, P);
+    HB1_MOD(M, P);
     const u64* ct = cv->c + (size_t)t * n;
     u64 a[16];
     {

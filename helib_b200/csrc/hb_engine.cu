@@ -90,6 +90,14 @@ struct hb_ctx {
     u64 *w0 = nullptr, *w1 = nullptr, *wt = nullptr;   // [HB_MAXB][nprimes][L]
     u64 *cA = nullptr, *cB = nullptr;                   // [HB_MAXB][nprimes][phim]
   } gen;
+  struct Pw {   // powerful basis (src/powerful.cpp): built on first use or by hb_ctx_set_powerful
+    bool ready = false, triv = true;
+    std::vector<long> mvec, pvec, bvec, long_prod;     // m_d = p_d^e_d, p_d, p_d^(e_d-1), products of the trailing dimensions
+    std::vector<int> cube_to_poly, short_to_long;      // host copies (the mirror's powerfulToZZX needs them)
+    int* d_cube_to_poly = nullptr; int* d_short_to_long = nullptr;
+    u64* cube = nullptr;                               // [nprimes][m]
+    u64* rows = nullptr;                               // [nprimes][phim] powerful-basis rows
+  } pw;
   // optional per-launch profiling (bench.py): CUDA events around every kernel launch
   bool profiling;
   struct ProfRec { const char* name; cudaEvent_t a, b; u64 bytes; };
@@ -277,6 +285,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
+  cudaFree(c->pw.d_cube_to_poly); cudaFree(c->pw.d_short_to_long); cudaFree(c->pw.cube); cudaFree(c->pw.rows);
   cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max); cudaFree(c->d_bcast);
   cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
@@ -1292,6 +1301,144 @@ extern "C" int hb_muladd(hb_poly* const* dst, hb_poly* const* a, hb_poly* const*
     A.op = HB_PW_MULADD; A.dst = D; A.a = (const u64* const*)A_; A.b = (const u64* const*)B_;
     return launch_pw(c, A, nit, idx, n);
   });
+}
+
+// ------------------------------------------------------------------------------------------
+// powerful basis + rawModSwitch
+static int pw_init(hb_ctx* c, const int64_t* mvec, int k) {
+  hb_ctx::Pw& W = c->pw;
+  std::vector<long> mv;
+  if (mvec && k > 0) mv.assign(mvec, mvec + k);
+  else { long n = (long)c->m; for (long p = 2; p <= n; p++) if (n % p == 0) { long pp = 1; while (n % p == 0) { n /= p; pp *= p; } mv.push_back(pp); } }
+  long prod = 1; for (long f : mv) prod *= f;
+  if (prod != (long)c->m) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: factors do not multiply to m");
+  W.mvec = mv; W.pvec.clear(); W.bvec.clear();
+  for (long f : mv) {
+    long p = 2; while (f % p) p++;
+    long t = f; while (t % p == 0) t /= p;
+    if (f < 2 || t != 1) return hb_fail(HB_ERR_UNSUPPORTED, "hb_ctx_set_powerful: factor %ld is not a prime power", f);
+    W.pvec.push_back(p); W.bvec.push_back(f / p);
+  }
+  const int K = (int)mv.size();
+  W.triv = K == 1;                                            // PowerfulDCRT::triv (src/powerful.cpp:250-254)
+  W.ready = true;
+  if (W.triv) return HB_OK;
+  if (!c->gen.on) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: a power-of-two m has a single factor");
+  const long m = (long)c->m, phim = (long)c->N;
+  std::vector<long> phiv(K), inv(K), sp(K + 1, 1);
+  W.long_prod.assign(K + 1, 1);
+  for (int d = K - 1; d >= 0; d--) { phiv[d] = mv[d] / W.pvec[d] * (W.pvec[d] - 1); W.long_prod[d] = W.long_prod[d + 1] * mv[d]; sp[d] = sp[d + 1] * phiv[d]; }
+  if (sp[0] != phim) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: phi mismatch");
+  for (int d = 0; d < K; d++) { u64 x; if (!h_invmod((u64)((m / mv[d]) % mv[d]), (u64)mv[d], &x)) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: factors are not coprime"); inv[d] = (long)x; }
+  W.cube_to_poly.assign(m, 0); W.short_to_long.assign(phim, 0);
+  for (long i = 0; i < m; i++) {                              // computePowerToCubeMap (src/powerful.cpp:62-84)
+    long j = 0;
+    for (int d = 0; d < K; d++) j += ((i % mv[d]) * inv[d] % mv[d]) * W.long_prod[d + 1];
+    W.cube_to_poly[j] = (int)i;
+  }
+  for (long i = 0; i < phim; i++) {                           // computeShortToLongMap (src/powerful.cpp:92-112)
+    long j = 0;
+    for (int d = 0; d < K; d++) j += ((i / sp[d + 1]) % phiv[d]) * W.long_prod[d + 1];
+    W.short_to_long[i] = (int)j;
+  }
+  HB_TRY(ctx_alloc(c, (void**)&W.d_cube_to_poly, sizeof(int) * m));
+  HB_TRY(ctx_alloc(c, (void**)&W.d_short_to_long, sizeof(int) * phim));
+  HB_CUDA(cudaMemcpy(W.d_cube_to_poly, W.cube_to_poly.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(W.d_short_to_long, W.short_to_long.data(), sizeof(int) * phim, cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&W.cube, sizeof(u64) * c->nprimes * m));
+  HB_TRY(ctx_alloc(c, (void**)&W.rows, sizeof(u64) * c->nprimes * phim));
+  return HB_OK;
+}
+extern "C" int hb_ctx_set_powerful(hb_ctx* c, const int64_t* mvec, int k) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: null");
+  if (c->pw.ready) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_set_powerful: already set");
+  return pw_init(c, mvec, k);
+}
+extern "C" int hb_ctx_powerful_info(hb_ctx* c, int32_t* nfactors, int64_t* mvec, int32_t* to_poly) {
+  if (!c) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_powerful_info: null");
+  if (!c->pw.ready) HB_TRY(pw_init(c, nullptr, 0));
+  if (nfactors) *nfactors = (int32_t)c->pw.mvec.size();
+  if (mvec) for (size_t i = 0; i < c->pw.mvec.size(); i++) mvec[i] = c->pw.mvec[i];
+  if (to_poly) for (size_t i = 0; i < c->N; i++) to_poly[i] = c->pw.triv ? (int32_t)i : c->pw.cube_to_poly[c->pw.short_to_long[i]];
+  return HB_OK;
+}
+// rows idx of p (evaluation form) -> coefficient-like rows in the powerful basis; *out = device rows [nprimes][N]
+static int to_powerful_rows(hb_ctx* c, hb_poly* p, const int32_t* idx, int n, const u64** out) {
+  if (!c->pw.ready) HB_TRY(pw_init(c, nullptr, 0));
+  u64* P[1] = {p->d};
+  const u64* coef;
+  if (c->gen.on) { u64* A[1] = {c->gen.cA}; HB_TRY(gen_inv(c, (const u64* const*)P, A, 1, idx, n)); coef = c->gen.cA; }
+  else {
+    HB_TRY(ctx_scratch(c));
+    u64* tA[1] = {c->tmpA}; u64* tB[1] = {c->tmpB};
+    HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, 1, idx, n, 0, nullptr));
+    HB_TRY(launch_cols(c, -1, (const u64* const*)tA, tB, 1, idx, n));
+    coef = c->tmpB;
+  }
+  if (c->pw.triv) { *out = coef; return HB_OK; }
+  hb_ctx::Pw& W = c->pw;
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    const int nr = std::min(HB_MAXROWS, n - r0);
+    HbPwJob2 J; memset(&J, 0, sizeof(J));
+    J.m = c->m; J.phim = c->N; fill_rows(J.rows, idx + r0, nr);
+    J.cube_to_poly = W.d_cube_to_poly; J.short_to_long = W.d_short_to_long; J.src = coef; J.cube = W.cube; J.dst = W.rows;
+    dim3 grid((unsigned)std::min<size_t>((c->m + HB_THREADS - 1) / HB_THREADS, 256), nr);
+    pre_launch(c);
+    HB_LAUNCH(k_pw_scatter, grid, dim3(HB_THREADS), 0, c->stream, J);
+    HB_TRY(post_launch(c, "k_pw_scatter", (u64)nr * (c->N + c->m) * 8));
+    for (size_t d = 0; d < W.mvec.size(); d++) {
+      J.stride = (u64)W.long_prod[d + 1]; J.md = (u64)W.mvec[d]; J.p = (u64)W.pvec[d]; J.b = (u64)W.bvec[d];
+      pre_launch(c);
+      HB_LAUNCH(k_pw_reduce, grid, dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+      HB_TRY(post_launch(c, "k_pw_reduce", (u64)nr * c->m * 16));
+    }
+    pre_launch(c);
+    HB_LAUNCH(k_pw_gather, grid, dim3(HB_THREADS), 0, c->stream, J);
+    HB_TRY(post_launch(c, "k_pw_gather", (u64)nr * c->N * 16));
+  }
+  *out = W.rows;
+  return HB_OK;
+}
+extern "C" int hb_dcrt_to_powerful(hb_poly* p, const int32_t* idx, int n, uint64_t* out, int Lout) {
+  if (!p || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_dcrt_to_powerful: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_dcrt_to_powerful"));
+  if (Lout < n) return hb_fail(HB_ERR_BAD_ARG, "hb_dcrt_to_powerful: Lout=%d limbs cannot hold a %d-prime product", Lout, n);
+  ConvEntry* E; HB_TRY(get_conv(c, idx, n, nullptr, 0, 1, &E));
+  const u64* rows; HB_TRY(to_powerful_rows(c, p, idx, n, &rows));
+  u64* d_out; size_t bytes = c->N * (size_t)Lout * sizeof(u64);
+  HB_CUDA(cudaMalloc((void**)&d_out, bytes));
+  HbCrtJob J; memset(&J, 0, sizeof(J));
+  J.cv = E->d; J.N = (int)c->N; J.Lout = Lout; J.positive = 0; J.src = rows; J.out = d_out;
+  HbCrtTabs T; T.t = E->d_t; T.t_s = E->d_t_s;
+  pre_launch(c);
+  HB_LAUNCH(k_crt, dim3((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS)), dim3(HB_THREADS), 0, c->stream, c->d_primes, J, T);
+  int r = post_launch(c, "k_crt", (u64)(n + Lout) * c->N * 8);
+  if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_dcrt_to_powerful: copy failed: %s", cudaGetErrorString(e)); }
+  cudaFree(d_out);
+  return r;
+}
+extern "C" int hb_raw_mod_switch(hb_poly* p, const int32_t* idx, int n, uint64_t q, uint64_t p2r, int64_t* out) {
+  if (!p || !out) return hb_fail(HB_ERR_BAD_ARG, "hb_raw_mod_switch: null");
+  hb_ctx* c = p->ctx;
+  HB_TRY(check_idx(c, idx, n, "hb_raw_mod_switch"));
+  if (q <= 1) return hb_fail(HB_ERR_BAD_ARG, "q must be greater than 1");                                  // src/Ctxt.cpp:2953
+  if (p2r <= 1) return hb_fail(HB_ERR_BAD_ARG, "Plaintext space must be greater than 1 for mod switching");   // :2954-2955
+  if (h_gcd((long)q, (long)p2r) != 1) return hb_fail(HB_ERR_BAD_ARG, "New modulus and current plaintext space must be co-prime");   // :2956-2958
+  if (q >= (1ULL << 54)) return hb_fail(HB_ERR_UNSUPPORTED, "hb_raw_mod_switch: q >= 2^54");
+  for (int j = 0; j < n; j++) if (h_gcd((long)(c->q[idx[j]] % q), (long)q) != 1) return hb_fail(HB_ERR_BAD_ARG, "GCD(Q, q) != 1 in Ctxt::rawModSwitch");   // :2970-2971
+  ConvEntry* E; HB_TRY(get_conv(c, idx, n, nullptr, 0, p2r, &E));
+  const u64* rows; HB_TRY(to_powerful_rows(c, p, idx, n, &rows));
+  i64* d_out; size_t bytes = c->N * sizeof(i64);
+  HB_CUDA(cudaMalloc((void**)&d_out, bytes));
+  HbRawMsJob J; memset(&J, 0, sizeof(J));
+  J.cv = E->d; J.t = E->d_t; J.t_s = E->d_t_s; J.N = c->N; J.q = q; J.src = rows; J.out = d_out; J.stats = c->d_stats;
+  pre_launch(c);
+  HB_LAUNCH(k_raw_mod_switch, dim3((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS)), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
+  int r = post_launch(c, "k_raw_mod_switch", (u64)(n + 1) * c->N * 8);
+  if (r == HB_OK) { cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) r = hb_fail(HB_ERR_CUDA, "hb_raw_mod_switch: copy failed: %s", cudaGetErrorString(e)); }
+  cudaFree(d_out);
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------

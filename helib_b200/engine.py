@@ -243,6 +243,31 @@ class Engine:
         self._ck(self.lib.hb_to_poly(poly.h, p, n, int(positive), out.ctypes.data_as(u64p), L))
         return out
 
+    def set_powerful(self, mvec):
+        arr = (C.c_int64 * len(mvec))(*[int(f) for f in mvec])
+        self._ck(self.lib.hb_ctx_set_powerful(self.h, arr, len(mvec)))
+
+    def powerful_info(self):
+        nf = C.c_int32()
+        mv = (C.c_int64 * 32)()
+        to_poly = np.zeros(self.N, dtype=np.int32)
+        self._ck(self.lib.hb_ctx_powerful_info(self.h, C.byref(nf), mv, to_poly.ctypes.data_as(C.POINTER(C.c_int32))))
+        return [int(mv[i]) for i in range(nf.value)], to_poly
+
+    def dcrt_to_powerful(self, poly, idx, L=None):
+        a, p, n = _idx(idx)
+        L = L or (n + 1)
+        out = np.zeros((self.N, L), dtype=np.uint64)
+        self._ck(self.lib.hb_dcrt_to_powerful(poly.h, p, n, out.ctypes.data_as(u64p), L))
+        return out
+
+    def raw_mod_switch(self, poly, idx, q, ptxt_space):
+        a, p, n = _idx(idx)
+        out = np.zeros(self.N, dtype=np.int64)
+        self._ck(self.lib.hb_raw_mod_switch(poly.h, p, n, C.c_uint64(int(q)), C.c_uint64(int(ptxt_space)),
+                                            out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def to_poly_mod_p(self, poly, idx, ptxt_space, factor=1):
         a, p, n = _idx(idx)
         out = np.zeros(self.N, dtype=np.int64)

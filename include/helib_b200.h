@@ -130,6 +130,20 @@ int hb_poly_from_limbs(hb_poly* const* polys, int nitems, const int32_t* idx, in
 /* dst += a * b row-wise: `key *= part; ptxt += key` of SecKey::Decrypt (src/keys.cpp:1373-1374) and
  * `parts[i] *= r; parts[i] += e` of PubKey::Encrypt (src/keys.cpp:416,443) in one pass. */
 int hb_muladd(hb_poly* const* dst, hb_poly* const* a, hb_poly* const* b, int nitems, const int32_t* idx, int n);
+/* ---- powerful basis and the recryption mod-switch ----
+ * hb_ctx_set_powerful: PowerfulDCRT(context, mvec) (src/powerful.cpp:246-318): the factorisation of m into prime powers
+ *   (what Context::buildRecryptData passes); optional -- without it the engine factors m itself on first use.
+ * hb_ctx_powerful_info: number of factors, the factors, and to_poly[i] = cubeToPolyMap[shortToLongMap[i]], the exponent
+ *   of X that powerful coefficient i is written to before the reduction modulo Phi_m (powerfulToPoly, src/powerful.cpp:223-244).
+ * hb_dcrt_to_powerful: PowerfulDCRT::dcrtToPowerful (src/powerful.cpp:393-410): the balanced integers modulo Q of the
+ *   powerful-basis coefficients, out[N][Lout] two's-complement limbs.
+ * hb_raw_mod_switch: the per-part body of Ctxt::rawModSwitch (src/Ctxt.cpp:2976-3037): out[N] = the powerful-basis
+ *   coefficients scaled by q/Q, rounded with the correction that keeps them = c*q*Q^-1 modulo ptxt_space, reduced
+ *   symmetrically mod q (a tie of an even q is left at +-q/2; the reference flips a coin there). */
+int hb_ctx_set_powerful(hb_ctx* ctx, const int64_t* mvec, int k);
+int hb_ctx_powerful_info(hb_ctx* ctx, int32_t* nfactors, int64_t* mvec, int32_t* to_poly);
+int hb_dcrt_to_powerful(hb_poly* p, const int32_t* idx, int n, uint64_t* out_limbs, int Lout);
+int hb_raw_mod_switch(hb_poly* p, const int32_t* idx, int n, uint64_t q, uint64_t ptxt_space, int64_t* out);
 /* DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:479-561).  src rows cur (ctxt primes only);
  * digits[item*maxdig + i] receives digit i over cur | special.  *ndig_out = number of digits. */
 int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, int ncur, hb_poly* const* digits, int maxdig, int* ndig_out);

@@ -523,6 +523,57 @@ class Ctxt {
       k = (long)(((unsigned __int128)(unsigned long)k * (unsigned long)invMod(amt, m)) % (unsigned long)m);
     }
   }
+  // Phi_m(X) over Z (Cyclotomic(m)): Phi_1 = X - 1; Phi_{np}(X) = Phi_n(X^p) / Phi_n(X) for p not dividing n, Phi_n(X^p) otherwise
+  static std::vector<long> cyclotomic(long m) {
+    std::vector<long> phi{-1, 1};
+    long n = 1;
+    for (long p = 2; m > 1; p++) {
+      bool first = true;
+      while (m % p == 0) {
+        m /= p;
+        std::vector<long> up((phi.size() - 1) * p + 1, 0);
+        for (size_t i = 0; i < phi.size(); i++) up[i * p] = phi[i];
+        if (first && n % p != 0) {   // exact division of up by the monic phi
+          std::vector<long> quo(up.size() - phi.size() + 1, 0);
+          for (long i = (long)up.size() - 1; i >= (long)phi.size() - 1; i--) {
+            const long c = up[i]; quo[i - (phi.size() - 1)] = c;
+            if (c) for (size_t j = 0; j < phi.size(); j++) up[i - (phi.size() - 1) + j] -= c * phi[j];
+          }
+          phi = quo;
+        } else phi = up;
+        n *= p; first = false;
+      }
+    }
+    return phi;
+  }
+  // Ctxt::rawModSwitch (src/Ctxt.cpp:2949-3046): mod-switch to an external modulus q for bootstrapping.  The scaling and
+  // rounding run on the device in the powerful basis (hb_raw_mod_switch); the small result is brought back to the
+  // polynomial basis here (PowerfulDCRT::powerfulToZZX, src/powerful.cpp:355-391).  Returns the scaled noise estimate.
+  double rawModSwitch(std::vector<std::vector<long>>& zzParts, long q) const {
+    if (q <= 1) throw InvalidArgument("q must be greater than 1");
+    if (ptxtSpace <= 1) throw LogicError("Plaintext space must be greater than 1 for mod switching");
+    if (std::gcd(q, ptxtSpace) != 1) throw LogicError("New modulus and current plaintext space must be co-prime");
+    const long phim = context.getPhiM(), m = context.getM();
+    int32_t nf = 0; std::vector<int32_t> toPoly((size_t)phim);
+    check(hb_ctx_powerful_info(context.handle(), &nf, nullptr, toPoly.data()));
+    std::vector<long> phimx;
+    if (nf > 1) phimx = cyclotomic(m);
+    zzParts.assign(parts.size(), std::vector<long>());
+    auto idx = primeSet.vec();
+    for (size_t i = 0; i < parts.size(); i++) {
+      std::vector<int64_t> pw((size_t)phim);
+      check(hb_raw_mod_switch(parts[i].dcrt.handle(), idx.data(), (int)idx.size(), (uint64_t)q, (uint64_t)ptxtSpace, pw.data()));
+      if (nf <= 1) { zzParts[i].assign(pw.begin(), pw.end()); continue; }
+      std::vector<long> tmp((size_t)m, 0);
+      for (long k = 0; k < phim; k++) tmp[toPoly[k]] = pw[k];
+      for (long k = m - 1; k >= phim; k--) {   // rem(tmp, Phi_m): Phi_m is monic of degree phi(m)
+        const long c = tmp[k];
+        if (c) for (long j = 0; j <= phim; j++) tmp[k - phim + j] -= c * phimx[j];
+      }
+      zzParts[i].assign(tmp.begin(), tmp.begin() + phim);
+    }
+    return (noiseBound * XD::exp(std::log((double)q) - logOfPrimeSet())).to_double();
+  }
   void multiplyBy(const Ctxt& other) {   // src/Ctxt.cpp:1757-1774
     if (isEmpty()) return;
     if (other.isEmpty()) { *this = other; return; }

@@ -745,3 +745,116 @@ def decrypt_bgv(chain, psis, parts, keys, ptxt_space: int, int_factor: int, idxs
             inv = pow(factor, -1, ptxt_space)
             out = [c * inv % ptxt_space for c in out]
     return out, f
+
+
+# ---------------------------------------------------------------------------------------------
+# Powerful basis and Ctxt::rawModSwitch (the mod-switch that opens recryption)
+
+class PowerfulIndexes:
+    """PowerfulTranslationIndexes (src/powerful.cpp:151-196): m = prod m_d (prime powers), the CRT index map between
+    exponents mod m and the (m_1 x ... x m_k) cube, and the embedding of the (phi(m_1) x ... x phi(m_k)) cube in it."""
+
+    def __init__(self, mvec):
+        self.mvec = list(mvec)
+        self.m = 1
+        for f in self.mvec:
+            self.m *= f
+        self.phivec = [euler_phi(f) for f in self.mvec]
+        self.phim = 1
+        for f in self.phivec:
+            self.phim *= f
+        k = len(self.mvec)
+        div = [self.m // f for f in self.mvec]                                   # computeDivVec (:22-32)
+        inv = [pow(div[d] % self.mvec[d], -1, self.mvec[d]) if self.mvec[d] > 1 else 0 for d in range(k)]   # computeInvVec (:36-49)
+        self.long_prod = [1] * (k + 1)                                           # CubeSignature::getProd(d) = prod of dims d..k-1
+        for d in range(k - 1, -1, -1):
+            self.long_prod[d] = self.long_prod[d + 1] * self.mvec[d]
+        self.short_prod = [1] * (k + 1)
+        for d in range(k - 1, -1, -1):
+            self.short_prod[d] = self.short_prod[d + 1] * self.phivec[d]
+        self.poly_to_cube = [0] * self.m                                         # computePowerToCubeMap (:62-84)
+        self.cube_to_poly = [0] * self.m
+        for i in range(self.m):
+            j = 0
+            for d in range(k):
+                j += ((i % self.mvec[d]) * inv[d] % self.mvec[d]) * self.long_prod[d + 1]
+            self.poly_to_cube[i] = j
+            self.cube_to_poly[j] = i
+        self.short_to_long = [0] * self.phim                                     # computeShortToLongMap (:92-112)
+        for i in range(self.phim):
+            j = 0
+            for d in range(k):
+                j += ((i // self.short_prod[d + 1]) % self.phivec[d]) * self.long_prod[d + 1]
+            self.short_to_long[i] = j
+        self.cyc = [cyclotomic_poly(f) for f in self.mvec]
+        self.phimx = cyclotomic_poly(self.m)
+
+
+def _poly_rem(a, b):
+    """a mod b over Z for monic b (coefficient lists, low -> high)."""
+    a = list(a)
+    db = len(b) - 1
+    for i in range(len(a) - 1, db - 1, -1):
+        c = a[i]
+        if c:
+            for j in range(db + 1):
+                a[i - db + j] -= c * b[j]
+    return a[:db] + [0] * max(0, db - len(a))
+
+
+def poly_to_powerful(ix: PowerfulIndexes, poly):
+    """PowerfulConversion::polyToPowerful over Z (src/powerful.cpp:203-221 with recursiveReduce :113-148): scatter by
+    the CRT map, reduce every hypercolumn of dimension d modulo Phi_{m_d}, read off the short cube."""
+    cube = [0] * ix.m
+    for i, c in enumerate(poly):
+        cube[ix.poly_to_cube[i]] = c
+    k = len(ix.mvec)
+    for d in range(k):
+        stride = ix.long_prod[d + 1]
+        for base in range(ix.m):
+            if (base // stride) % ix.mvec[d] != 0:
+                continue
+            col = [cube[base + t * stride] for t in range(ix.mvec[d])]
+            r = _poly_rem(col, ix.cyc[d])
+            for t in range(ix.mvec[d]):
+                cube[base + t * stride] = r[t] if t < len(r) else 0
+    return [cube[ix.short_to_long[i]] for i in range(ix.phim)]
+
+
+def powerful_to_poly(ix: PowerfulIndexes, pw):
+    """PowerfulConversion::powerfulToPoly over Z (src/powerful.cpp:223-244)."""
+    tmp = [0] * ix.m
+    for i in range(ix.phim):
+        tmp[ix.cube_to_poly[ix.short_to_long[i]]] = pw[i]
+    return _poly_rem(tmp, ix.phimx)[:ix.phim]
+
+
+def raw_mod_switch(ix, parts_coeffs, Q: int, q: int, p2r: int, coin=lambda: 0):
+    """Ctxt::rawModSwitch (src/Ctxt.cpp:2949-3046).  parts_coeffs: per part the balanced coefficients mod Q in the
+    polynomial basis (what DoubleCRT::toPoly returns); ix = None when the powerful basis is the polynomial one
+    (PowerfulDCRT::triv).  Returns the parts as small integer polynomials."""
+    from math import gcd
+    assert q > 1 and p2r > 1 and gcd(q, p2r) == 1 and gcd(Q % q, q) == 1
+    q_half = Q // 2
+    q_inv_p = pow(Q % p2r, -1, p2r)
+    out = []
+    for coeffs in parts_coeffs:
+        pw = [bal(c, Q) for c in poly_to_powerful(ix, coeffs)] if ix is not None else list(coeffs)   # dcrtToPowerful (:393-410)
+        res = []
+        for c in pw:
+            cq = c * q
+            X, Y = divmod(cq, Q)                 # floor division, Y in [0,Q)
+            if Y > q_half:
+                Y -= Q
+                X += 1
+            delta = (Y % p2r) * q_inv_p % p2r
+            if delta > p2r // 2 or (p2r % 2 == 0 and delta == p2r // 2 and (Y < 0 or (Y == 0 and coin()))):
+                delta -= p2r
+            x = X + delta
+            if x > q // 2 or (q % 2 == 0 and x == q // 2 and coin()):
+                x -= q
+            elif x < -(q // 2) or (q % 2 == 0 and x == -(q // 2) and coin()):
+                x += q
+            res.append(x)
+        out.append(powerful_to_poly(ix, res) if ix is not None else res)
+    return out

@@ -80,3 +80,15 @@ def test_ckks_multiply_through_mirror_on_simulator():
 def test_ckks_multiply_through_mirror_on_gpu():
     r = subprocess.run([build_exe("test_ckks")], capture_output=True, text=True)
     assert r.returncode == 0 and "ckks OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_raw_mod_switch_through_mirror_on_simulator():
+    """Ctxt::rawModSwitch (powerful basis, general and power-of-two m): the switched ciphertext decrypts mod q to the same plaintext."""
+    r = subprocess.run([build_exe("test_rawmodswitch", sim=True)], capture_output=True, text=True)
+    assert r.returncode == 0 and "rawmodswitch OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_raw_mod_switch_through_mirror_on_gpu():
+    r = subprocess.run([build_exe("test_rawmodswitch")], capture_output=True, text=True)
+    assert r.returncode == 0 and "rawmodswitch OK" in r.stdout, r.stdout + r.stderr

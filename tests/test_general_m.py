@@ -9,7 +9,7 @@ import pytest
 
 import orc
 import pyoracle as po
-from helib_b200 import Engine
+from helib_b200 import Engine, HbError
 
 
 def backends():
@@ -185,3 +185,54 @@ def test_thinboot_ring_m21845_rows(cuda_lib):
     E.add_primes_and_scale([P], S, ch.special)
     E.scale_down([P], sorted(S + ch.special), S, p)
     assert (P.download(S)[S] == before[S]).all()
+
+
+# ---- powerful basis and the recryption mod-switch ----
+
+@pytest.mark.parametrize("m,mvec,p,bits", [(105, [3, 5, 7], 2, 100), (45, [9, 5], 2, 100), (45, [5, 9], 7, 100), (64, None, 3, 100), (25, None, 2, 80)])
+def test_powerful_basis_and_raw_mod_switch(lib, m, mvec, p, bits):
+    """PowerfulDCRT::dcrtToPowerful (src/powerful.cpp:393-410) and Ctxt::rawModSwitch (src/Ctxt.cpp:2949-3046) against
+    the oracle's big-integer restatement: several prime-power factorisations (both orders), a prime power and a power of
+    two (trivial powerful basis), random rows plus coefficients on the rounding boundaries."""
+    if m & (m - 1):
+        ch, roots, E = setup(lib, (m, p, 1, bits, 2))
+    else:
+        from common import make
+        ch, psis, O, E = make(lib, m, p, 1, bits, 2)
+    S = ch.ctxt
+    Q = ch.product(S)
+    n = ch.phim
+    rng = np.random.default_rng(17)
+    if mvec is not None:
+        E.set_powerful(mvec)
+    factors, to_poly = E.powerful_info()
+    ix = po.PowerfulIndexes(factors) if len(factors) > 1 else None
+    if mvec is not None:
+        assert factors == mvec
+    if ix is not None:
+        assert [int(v) for v in to_poly] == [ix.cube_to_poly[ix.short_to_long[i]] for i in range(n)]
+    # a polynomial with chosen balanced coefficients: random, 0, +-1, +-(Q-1)/2, and values next to multiples of Q/q
+    q = 2 ** 10 + 1 if p % 2 == 0 else p ** 3 + 1
+    p2r = p
+    coeffs = [int(rng.integers(-(1 << 62), 1 << 62)) * int(rng.integers(1, 1 << 30)) % Q for _ in range(n)]
+    coeffs = [po.bal(c, Q) for c in coeffs]
+    special = [0, 1, -1, (Q - 1) // 2, -((Q - 1) // 2), Q // q, Q // q + 1, -(Q // q), (Q // (2 * q)), (Q // (2 * q)) + 1, 3 * Q // (2 * q), 3 * Q // (2 * q) + 1]
+    for i, v in enumerate(special[:n]):
+        coeffs[i] = po.bal(v, Q)
+    X = E.poly()
+    L = len(S) + 1
+    E.from_limbs([X], S, [orc.ints_to_limbs(coeffs, L)])
+    assert orc.limbs_to_ints(E.to_poly(X, S)) == coeffs
+    want_pw = [po.bal(c, Q) for c in (po.poly_to_powerful(ix, coeffs) if ix is not None else coeffs)]
+    assert orc.limbs_to_ints(E.dcrt_to_powerful(X, S)) == want_pw
+    got = [int(v) for v in E.raw_mod_switch(X, S, q, p2r)]
+    # the oracle returns the polynomial-basis result; the ABI the powerful-basis one: convert ours with the engine's map
+    want_poly = po.raw_mod_switch(ix, [coeffs], Q, q, p2r)[0]
+    ours_poly = po.powerful_to_poly(ix, got) if ix is not None else got
+    assert ours_poly == want_poly
+    # defining property of the switch (src/Ctxt.cpp:3011-3016): x = c*q*Q^-1 (mod p^r) and |c*q/Q - x| <= p^r/2 (+ one q wrap)
+    qinv = q * pow(Q, -1, p2r) % p2r
+    for c, x in zip(want_pw, got):
+        assert (x - c * qinv) % p2r == 0 or (x + q - c * qinv) % p2r == 0 or (x - q - c * qinv) % p2r == 0
+    with pytest.raises(HbError):
+        E.raw_mod_switch(X, S, p2r * 5, p2r)     # q not coprime to the plaintext space
