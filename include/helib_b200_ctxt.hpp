@@ -26,6 +26,9 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <ostream>
+#include <istream>
+#include <cstring>
 
 #include "helib_b200_doublecrt.hpp"
 
@@ -573,6 +576,70 @@ class Ctxt {
       zzParts[i].assign(tmp.begin(), tmp.begin() + phim);
     }
     return (noiseBound * XD::exp(std::log((double)q) - logOfPrimeSet())).to_double();
+  }
+  // ---- binary wire format, Ctxt::writeTo / read (src/Ctxt.cpp:2584-2641, src/binio.h:91-137, src/binio.cpp:75-178):
+  //   24-byte SerializeHeader<Ctxt> ("|HE[", format version 0.0.1.0, library version, struct id 20, 7 reserved, "]HE|"),
+  //   "|CX[", ptxtSpace, intFactor, ptxtMag, ratFactor, noiseBound (xdouble = raw double mantissa + int64 exponent),
+  //   primeSet, vector<CtxtPart> (count, then DoubleCRT + SKHandle each), "]CX|".  All integers little-endian int64.
+  // NTL's xdouble is x * (2^114)^e with 2^-57 <= |x| <= 2^57 (NTL 11.4.3 xdouble.h, NTL_XD_BOUND); NTL is not in the
+  // reference tree, so this split is restated from its documentation: parity unpinned for those 16-byte fields.
+  static void writeXD(std::ostream& str, const XD& v) {
+    double x = 0; int64_t e = 0;
+    if (v.m != 0) {
+      long E = v.e;                      // v = m * 2^E, 0.5 <= |m| < 1
+      e = E > 57 ? (E - 57 + 113) / 114 : (E < -56 ? -((-56 - E + 113) / 114) : 0);
+      x = std::ldexp(v.m, (int)(E - 114 * e));
+    }
+    str.write(reinterpret_cast<const char*>(&x), 8); str.write(reinterpret_cast<const char*>(&e), 8);
+  }
+  static XD readXD(std::istream& str) {
+    double x = 0; int64_t e = 0;
+    str.read(reinterpret_cast<char*>(&x), 8); str.read(reinterpret_cast<char*>(&e), 8);
+    return XD::make(x, 114 * (long)e);
+  }
+  static void writeInt(std::ostream& str, int64_t v) { str.write(reinterpret_cast<const char*>(&v), 8); }
+  static int64_t readInt(std::istream& str) { int64_t v = 0; str.read(reinterpret_cast<char*>(&v), 8); return v; }
+  void writeTo(std::ostream& str) const {
+    const char header[24] = {'|', 'H', 'E', '[', 0, 0, 1, 0, 2, 2, 0, 0, 20, 0, 0, 0, 0, 0, 0, 0, ']', 'H', 'E', '|'};
+    str.write(header, 24);
+    str.write("|CX[", 4);
+    writeInt(str, ptxtSpace); writeInt(str, intFactor);
+    writeXD(str, ptxtMag); writeXD(str, ratFactor); writeXD(str, noiseBound);
+    writeInt(str, primeSet.card());
+    for (long i : primeSet) writeInt(str, i);
+    writeInt(str, (int64_t)parts.size());
+    for (const CtxtPart& part : parts) {
+      part.dcrt.writeTo(str);
+      writeInt(str, part.skHandle.powerOfS); writeInt(str, part.skHandle.powerOfX); writeInt(str, part.skHandle.secretKeyID);
+    }
+    str.write("]CX|", 4);
+  }
+  void read(std::istream& str) {
+    char header[24];
+    str.read(header, 24);
+    if (!str || std::memcmp(header, "|HE[", 4) != 0 || std::memcmp(header + 20, "]HE|", 4) != 0) throw RuntimeError("Eye catchers for header mismatch");
+    const char ver[4] = {0, 0, 1, 0};
+    if (std::memcmp(header + 4, ver, 4) != 0) throw RuntimeError("Header: version not supported");
+    char eye[4];
+    str.read(eye, 4);
+    if (std::memcmp(eye, "|CX[", 4) != 0) throw RuntimeError("Could not find pre-ciphertext eye catcher");
+    ptxtSpace = readInt(str); intFactor = readInt(str);
+    ptxtMag = readXD(str); ratFactor = readXD(str); noiseBound = readXD(str);
+    const int64_t card = readInt(str);
+    if (!str || card < 0 || card > context.numPrimes()) throw RuntimeError("Ctxt::read: bad prime set");
+    primeSet = IndexSet();
+    for (int64_t i = 0; i < card; i++) primeSet.insert(readInt(str));
+    const int64_t np = readInt(str);
+    if (!str || np < 0 || np > 64) throw RuntimeError("Ctxt::read: bad part count");
+    parts.clear();
+    for (int64_t i = 0; i < np; i++) {
+      DoubleCRT d(context, IndexSet::emptySet());
+      d.read(str);
+      SKHandle h; h.powerOfS = readInt(str); h.powerOfX = readInt(str); h.secretKeyID = readInt(str);
+      parts.emplace_back(d, h);
+    }
+    str.read(eye, 4);
+    if (!str || std::memcmp(eye, "]CX|", 4) != 0) throw RuntimeError("Could not find post-ciphertext eye catcher");
   }
   void multiplyBy(const Ctxt& other) {   // src/Ctxt.cpp:1757-1774
     if (isEmpty()) return;

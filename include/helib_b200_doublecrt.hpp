@@ -16,6 +16,9 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <ostream>
+#include <istream>
+#include <cstring>
 
 #include "helib_b200.h"
 #include "helib_b200_chain.h"
@@ -337,6 +340,36 @@ class DoubleCRT {
     std::vector<int64_t> out((size_t)context_->getPhiM());
     check(hb_to_poly_mod_p(p_, idx.data(), (int)idx.size(), (uint64_t)ptxtSpace, (uint64_t)factor, out.data()));
     return std::vector<long>(out.begin(), out.end());
+  }
+  // DoubleCRT::writeTo / read (src/DoubleCRT.cpp:1530-1561): IndexSet, then per row int32 length, int32 intSize, LE values
+  void writeTo(std::ostream& str) const {
+    auto idx = set_.vec();
+    uint64_t bytes = 0;
+    check(hb_poly_serialized_size(p_, (int)idx.size(), &bytes));
+    std::vector<char> buf((size_t)bytes);
+    check(hb_poly_serialize(p_, idx.data(), (int)idx.size(), buf.data(), bytes));
+    str.write(buf.data(), (std::streamsize)buf.size());
+  }
+  void read(std::istream& str) {
+    // the record is self-delimiting: read the index set first, then the rows it announces
+    std::vector<char> buf(8);
+    str.read(buf.data(), 8);
+    int64_t card = 0; std::memcpy(&card, buf.data(), 8);
+    if (!str || card < 0 || card > context_->numPrimes()) throw RuntimeError("DoubleCRT::read: bad index set");
+    buf.resize(8 + 8 * (size_t)card);
+    str.read(buf.data() + 8, 8 * card);
+    for (int64_t r = 0; r < card; r++) {
+      size_t off = buf.size(); buf.resize(off + 8);
+      str.read(buf.data() + off, 8);
+      int32_t len = 0, isz = 0; std::memcpy(&len, buf.data() + off, 4); std::memcpy(&isz, buf.data() + off + 4, 4);
+      if (!str || len < 0 || (isz != 4 && isz != 8)) throw RuntimeError("DoubleCRT::read: bad row header");
+      size_t off2 = buf.size(); buf.resize(off2 + (size_t)len * isz);
+      str.read(buf.data() + off2, (std::streamsize)len * isz);
+    }
+    if (!str) throw RuntimeError("DoubleCRT::read: truncated input");
+    std::vector<int32_t> idx((size_t)context_->numPrimes()); int n = 0;
+    check(hb_poly_deserialize(p_, buf.data(), buf.size(), idx.data(), &n));
+    set_ = IndexSet(idx.begin(), idx.begin() + n);
   }
   // getOneRow (DoubleCRT.h:332-336)
   std::vector<long> getOneRow(long i) const {

@@ -5,6 +5,8 @@
 // Exit codes: 0 ok, 3 no CUDA device, 1 failure.
 #include <cstdio>
 #include <random>
+#include <sstream>
+#include <cstring>
 
 #include "helib_b200_ctxt.hpp"
 
@@ -183,6 +185,30 @@ int main() {
       w.multByConstant(cst2);
       std::vector<long> dw = decrypt(w, nullptr);
       for (long i = 0; i < 32; i++) { long k = (i * 131 + 7) % N; if (dw[k] != negacyclic_at(ma, mb, k)) { std::printf("multByConstant mismatch at %ld\n", k); return 1; } }
+    }
+    // binary wire format of Ctxt::writeTo / read (src/Ctxt.cpp:2584-2641): layout, size and round trip
+    {
+      std::stringstream ss;
+      ca.writeTo(ss);
+      const std::string bytes = ss.str();
+      const size_t card = (size_t)ca.primeSet.card(), np = ca.parts.size();
+      const size_t expect = 24 + 4 + 16 + 48 + 8 + 8 * card + 8 + np * ((8 + 8 * card) + card * (8 + 8 * (size_t)N) + 24) + 4;
+      if (bytes.size() != expect) { std::printf("serialized size %zu != %zu\n", bytes.size(), expect); return 1; }
+      if (bytes.compare(0, 4, "|HE[") != 0 || bytes[6] != 1 || bytes[12] != 20 || bytes.compare(20, 8, "]HE||CX[") != 0 || bytes.compare(bytes.size() - 4, 4, "]CX|") != 0) { std::printf("header / eye catchers\n"); return 1; }
+      int64_t ps = 0; std::memcpy(&ps, bytes.data() + 28, 8);
+      if (ps != ca.ptxtSpace) { std::printf("ptxtSpace field\n"); return 1; }
+      Ctxt back(pk, 0);
+      back.read(ss);
+      if (back.ptxtSpace != ca.ptxtSpace || back.intFactor != ca.intFactor || back.primeSet != ca.primeSet || back.parts.size() != np) { std::printf("round trip: metadata\n"); return 1; }
+      if (std::fabs(back.noiseBound.ln() - ca.noiseBound.ln()) > 1e-12) { std::printf("round trip: noiseBound\n"); return 1; }
+      for (size_t i = 0; i < np; i++)
+        if (!(back.parts[i].skHandle == ca.parts[i].skHandle) || back.parts[i].dcrt.getOneRow(ca.primeSet.first()) != ca.parts[i].dcrt.getOneRow(ca.primeSet.first())) { std::printf("round trip: part %zu\n", i); return 1; }
+      if (decrypt(back, nullptr) != decrypt(ca, nullptr)) { std::printf("round trip: decryption differs\n"); return 1; }
+      std::string bad = bytes; bad[25] = 'Q';
+      std::stringstream sb(bad);
+      bool threw = false;
+      try { Ctxt x(pk, 0); x.read(sb); } catch (const hb::RuntimeError&) { threw = true; }
+      if (!threw) { std::printf("missing error for a damaged eye catcher\n"); return 1; }
     }
     const long before = ctx.getCtxtPrimes().card(), common = ca.lastCommonPrimeSet.card();
     const double logq_before = logq0, logq_common = logq2;
