@@ -469,7 +469,7 @@ class Ctxt {
   Ctxt& operator-=(const Ctxt& o) { addCtxt(o, true); return *this; }
   // src/Ctxt.cpp:896-935 (BGV): the constant is scaled by intFactor*Q mod p so that it decrypts unscaled
   void addConstant(const DoubleCRT& dcrt, double size = -1.0) {
-    if (isCKKS()) throw LogicError("Ctxt::addConstant: addConstantCKKS is not mirrored");
+    if (isCKKS()) throw LogicError("Ctxt::addConstant: use addConstantCKKS (explicit size and factor)");
     if (size < 0.0) size = pubKey.noiseBoundForMod(ptxtSpace, context.getPhiM());
     long f = 1;
     if (ptxtSpace > 2) {
@@ -481,10 +481,42 @@ class Ctxt {
     if (f == 1) addPart(dcrt, SKHandle(0, 1, 0));
     else { DoubleCRT tmp = dcrt; tmp *= f; addPart(tmp, SKHandle(0, 1, 0)); }
   }
+  // multByConstantCKKS (src/Ctxt.cpp:1905-1938): dcrt encodes slots of magnitude <= size at scaling factor `factor`;
+  // roundingErr = the encoding's rounding error.  The reference's defaults come from EncryptedArrayCx (the encoding layer,
+  // out of scope here), so the three values are explicit arguments.
+  void multByConstantCKKS(const DoubleCRT& dcrt, const XD& size, const XD& factor, double roundingErr) {
+    if (isEmpty()) return;
+    if (!isCKKS()) throw LogicError("multByConstantCKKS on a BGV ciphertext");
+    noiseBound = noiseBound * factor * size + XD(roundingErr) * ratFactor * ptxtMag + noiseBound * XD(roundingErr);   // must come first
+    ptxtMag = ptxtMag * size;
+    ratFactor = ratFactor * factor;
+    for (auto& part : parts) part.dcrt.Mul(dcrt, /*matchIndexSets=*/false);
+  }
+  // addConstantCKKS (src/Ctxt.cpp:941-1052): the constant (scaling factor `factor`) is multiplied by round(ratFactor/factor)
+  // so that it matches the ciphertext's factor.  The reference adds primes (addSomePrimes) when that rounding alone would
+  // cost more than 2^-precision of accuracy; the mirror reports that case instead.
+  void addConstantCKKS(const DoubleCRT& dcrt, const XD& size_in, const XD& factor) {
+    if (!isCKKS()) throw LogicError("addConstantCKKS on a BGV ciphertext");
+    const XD size = size_in.m <= 0 ? XD(1.0) : size_in;
+    if (factor.m <= 0) throw InvalidArgument("addConstantCKKS: the scaling factor of the constant must be given");
+    XD ratio = ratFactor / factor + XD(0.5);
+    uint64_t mant; long sh; ratio.floorParts(mant, sh);
+    const XD r = XD::make((double)mant, sh);
+    const double inaccuracy = std::fabs((r * factor / ratFactor).to_double() - 1.0);
+    if (inaccuracy * std::ldexp(1.0, (int)context.getR()) > 1.0) throw LogicError("addConstantCKKS: scaling factors too far apart (the reference calls addSomePrimes here)");
+    ptxtMag = ptxtMag + size;
+    noiseBound = noiseBound + XD(0.5);
+    IndexSet delta = primeSet / dcrt.getIndexSet();
+    if (mant == 1 && sh == 0 && empty(delta)) { addPart(dcrt, SKHandle(0, 1, 0)); return; }
+    DoubleCRT tmp = dcrt;
+    if (!empty(delta)) tmp.addPrimes(delta);
+    if (!(mant == 1 && sh == 0)) tmp.mulByPow2Scaled(mant, sh);
+    addPart(tmp, SKHandle(0, 1, 0));
+  }
   // src/Ctxt.cpp:1832-1856 (BGV)
   void multByConstant(const DoubleCRT& dcrt, double size = -1.0) {
     if (isEmpty()) return;
-    if (isCKKS()) throw LogicError("Ctxt::multByConstant: multByConstantCKKS is not mirrored");
+    if (isCKKS()) throw LogicError("Ctxt::multByConstant: use multByConstantCKKS (explicit size, factor and rounding error)");
     if (size < 0.0) size = pubKey.noiseBoundForMod(ptxtSpace, context.getPhiM());
     for (auto& part : parts) part.dcrt.Mul(dcrt, /*matchIndexSets=*/false);
     noiseBound = noiseBound * XD(size);

@@ -125,6 +125,28 @@ int main() {
     Ctxt diff = cc; diff -= ca;
     std::vector<double> dd = decode(diff, &nl);
     for (long t = 0; t < 64; t++) { long k = (t * 521 + 3) % N; if (std::fabs(dd[k] - ((double)mc[k] - prod2[k])) > std::exp2(nl) + tol) { std::printf("CKKS difference mismatch at %ld\n", k); return 1; } }
+    // constants: multByConstantCKKS and addConstantCKKS with an integer-coefficient constant encoded at factor 2^20
+    {
+      const double dc = std::ldexp(1.0, 20);
+      std::vector<long> kc(N, 0), kcs(N, 0);
+      kc[0] = 3; kc[1] = -2;                                   // constant polynomial 3 - 2X
+      for (long k = 0; k < N; k++) kcs[k] = (long)(dc * kc[k]);
+      Ctxt cm = encrypt(mc);
+      DoubleCRT K(kcs, ctx, cm.primeSet);
+      cm.multByConstantCKKS(K, XD(embeddingLargestCoeff(kc, m)), XD(dc), 0.0);
+      std::vector<double> dm = decode(cm, &nl);
+      for (long t = 0; t < 64; t++) {
+        long k = (t * 521 + 3) % N;
+        const long prev = k == 0 ? -mc[N - 1] : mc[k - 1];    // X * f wraps with a sign
+        const double want = 3.0 * mc[k] - 2.0 * prev;
+        if (std::fabs(dm[k] - want) > std::exp2(nl) + 1e-6) { std::printf("multByConstantCKKS mismatch at %ld: %g vs %g\n", k, dm[k], want); return 1; }
+      }
+      Ctxt cadd = encrypt(mc);
+      DoubleCRT K2(kcs, ctx, cadd.primeSet);
+      cadd.addConstantCKKS(K2, XD(embeddingLargestCoeff(kc, m)), XD(dc));   // ratFactor 2^30 / 2^20: the constant is scaled by 1024
+      std::vector<double> da = decode(cadd, &nl);
+      for (long k = 0; k < 4; k++) if (std::fabs(da[k] - (mc[k] + kc[k])) > std::exp2(nl) + 1e-6) { std::printf("addConstantCKKS mismatch at %ld: %g vs %ld\n", k, da[k], mc[k] + kc[k]); return 1; }
+    }
     ctx.sync();
     std::printf("ckks add OK: log2 ratFactor %.1f + 30.0 -> %.1f, bound %.3g\n", rf_before, std::log2((double)sum.ratFactor.m) + (double)sum.ratFactor.e, tol2);
     std::printf("ckks OK: %.0f -> %.0f bits after multiplyBy, log2 ratFactor %.1f, error %.3g <= bound %.3g, KS-noise-ratio %.3g\n",
