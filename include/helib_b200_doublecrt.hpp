@@ -316,6 +316,36 @@ class DoubleCRT {
     check(hb_ctx_sync(ctx.handle()));
     return r;
   }
+  // DoubleCRT::randomize (src/DoubleCRT.cpp:1258-1378): uniform rows by rejection sampling from a byte stream --
+  // get(buf, 2048) stands for NTL::RandomStream::get (the ChaCha20 stream keyed by SetSeed; not restated).  A fresh 2048-byte
+  // buffer per refill and per row, nb = ceil(bits(q-1)/8) little-endian bytes per candidate, masked, accepted when < q.
+  // Runs on the host (once per key-switching matrix) and uploads the rows.
+  template <class GetBytes> void randomize(GetBytes&& get) {
+    const long N = context_->getPhiM(), bufsz = 2048;
+    std::vector<uint64_t> dense((size_t)context_->numPrimes() * N, 0);
+    std::vector<unsigned char> buf((size_t)bufsz);
+    for (long i : set_) {
+      const uint64_t q = (uint64_t)context_->ithPrime(i);
+      long k = 0; for (uint64_t t = q - 1; t; t >>= 1) k++;
+      const long nb = (k + 7) / 8;
+      const uint64_t mask = k >= 64 ? ~0ULL : ((1ULL << k) - 1ULL);
+      uint64_t* row = &dense[(size_t)i * N];
+      long j = 0;
+      while (j < N) {
+        get(buf.data(), bufsz);
+        for (long pos = 0; pos <= bufsz - nb && j < N; pos += nb) {
+          uint64_t u = 0;
+          for (long c = nb - 1; c >= 0; c--) u = (u << 8) | buf[(size_t)(pos + c)];
+          u &= mask;
+          row[j] = u;
+          j += (u < q);
+        }
+      }
+    }
+    auto idx = set_.vec();
+    if (!idx.empty()) check(hb_poly_upload(p_, idx.data(), (int)idx.size(), dense.data()));
+    check(hb_ctx_sync(context_->handle()));
+  }
   // toPoly (src/DoubleCRT.cpp:925-1113): N x L little-endian two's-complement limbs
   std::vector<uint64_t> toPoly(const IndexSet& s, bool positive, int& L) const {
     auto idx = (set_ & s).vec();

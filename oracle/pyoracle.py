@@ -858,3 +858,31 @@ def raw_mod_switch(ix, parts_coeffs, Q: int, q: int, p2r: int, coin=lambda: 0):
             res.append(x)
         out.append(powerful_to_poly(ix, res) if ix is not None else res)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# DoubleCRT::randomize (src/DoubleCRT.cpp:1258-1378): rejection sampling of uniform rows from a byte stream.
+# The stream itself is NTL's RandomStream (ChaCha20 keyed from SetSeed; NTL 11.4.3, not in the reference tree) and is an
+# INPUT here ("parity unpinned" for the bytes; the consumption pattern is the reference's).
+
+def randomize_rows(chain, idxs, get_bytes):
+    """get_bytes(n) -> n fresh bytes.  Per row: a fresh 2048-byte buffer at the start of every refill, nb = ceil(k/8)
+    little-endian bytes per candidate (k = bits of q-1), masked to k bits, accepted when < q (src/DoubleCRT.cpp:1279-1376)."""
+    bufsz = 2048
+    rows = {}
+    for i in sorted(idxs):
+        q = chain.primes[i]
+        k = (q - 1).bit_length()
+        nb = (k + 7) // 8
+        mask = (1 << k) - 1
+        row = []
+        while len(row) < chain.phim:
+            buf = get_bytes(bufsz)
+            pos = 0
+            while pos <= bufsz - nb and len(row) < chain.phim:
+                v = int.from_bytes(buf[pos:pos + nb], "little") & mask
+                if v < q:
+                    row.append(v)
+                pos += nb
+        rows[i] = row
+    return rows

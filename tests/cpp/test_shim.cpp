@@ -65,6 +65,22 @@ int main() {
       std::vector<long> mp = H.toPolyModP(S, 257, 1);
       for (long k : {0L, 1L, N / 2, N - 1}) { long v = coeff_of(hp, L, k) % 257; if (v < 0) v += 257; if (mp[k] != v) { std::printf("toPolyModP mismatch at %ld\n", k); return 1; } }
     }
+    // randomize from a byte stream (splitmix64 bytes; tests/test_cpp_shim.py recomputes the rows with the oracle)
+    {
+      uint64_t st2 = 0x1234567ULL;
+      auto get = [&](unsigned char* b, long n) {
+        for (long i = 0; i < n; i += 8) {
+          st2 += 0x9E3779B97F4A7C15ULL; uint64_t z = st2;
+          z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31;
+          for (int k = 0; k < 8 && i + k < n; k++) b[i + k] = (unsigned char)(z >> (8 * k));
+        }
+      };
+      hb::DoubleCRT R(ctx, S);
+      R.randomize(get);
+      std::printf("randomize:");
+      for (long i : S) { std::vector<long> row = R.getOneRow(i); unsigned long h = 1469598103934665603UL; for (long v : row) h = (h ^ (unsigned long)v) * 1099511628211UL; std::printf(" %ld:%lu", i, h); }
+      std::printf("\n");
+    }
     // error behaviour
     bool threw = false;
     try { hb::DoubleCRT A(ctx, S), B(ctx, hb::IndexSet(S.first())); A += B; } catch (const hb::RuntimeError&) { threw = true; }

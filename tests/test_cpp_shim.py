@@ -41,6 +41,7 @@ def test_shim_runs_on_gpu():
     exe = build_exe()
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "shim OK" in r.stdout, r.stdout + r.stderr
+    _check_randomize_line(r.stdout)
 
 
 def test_ctxt_mirror_compiles_and_refuses_without_gpu():
@@ -58,10 +59,41 @@ def test_ctxt_multiplyBy_decrypts_on_gpu():
     assert r.returncode == 0 and "ctxt OK" in r.stdout, r.stdout + r.stderr
 
 
+def _splitmix_bytes():
+    state = [0x1234567]
+
+    def get(n):
+        out = bytearray()
+        while len(out) < n:
+            state[0] = (state[0] + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+            z = state[0]
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+            z ^= z >> 31
+            out += z.to_bytes(8, "little")
+        return bytes(out[:n])
+    return get
+
+
+def _check_randomize_line(stdout):
+    """DoubleCRT::randomize in the mirror vs the oracle's restatement on the same byte stream (FNV-1a hash per row)."""
+    import pyoracle as po
+    line = [ln for ln in stdout.splitlines() if ln.startswith("randomize:")][0]
+    got = {int(t.split(":")[0]): int(t.split(":")[1]) for t in line.split()[1:]}
+    ch = po.build_mod_chain(4096, 257, 1, 120, 2)
+    rows = po.randomize_rows(ch, ch.ctxt, _splitmix_bytes())
+    for i, row in rows.items():
+        h = 1469598103934665603
+        for v in row:
+            h = ((h ^ v) * 1099511628211) & (2 ** 64 - 1)
+        assert got[i] == h, f"row {i}"
+
+
 def test_shim_logic_on_simulator():
     """The DoubleCRT mirror's unit-level properties with the kernels compiled for the CPU simulator."""
     r = subprocess.run([build_exe("test_shim", sim=True)], capture_output=True, text=True)
     assert r.returncode == 0 and "shim OK" in r.stdout, r.stdout + r.stderr
+    _check_randomize_line(r.stdout)
 
 
 def test_ctxt_encrypt_multiply_decrypt_on_simulator():
