@@ -902,4 +902,39 @@ inline void Decrypt(std::vector<long>& plaintxt, const Ctxt& c, const std::vecto
   plaintxt = ptxt.toPolyModP(P, p, factor);
 }
 
+// RLWE1 (src/keys.cpp:39-72): c0 = p*e - c1*s for a short e; returns the high-probability bound on the canonical
+// embedding of the decryption.  e is drawn by sampleGaussianBounded above (the reference's distribution and rejection bound).
+template <class Gen> double RLWE1(DoubleCRT& c0, const DoubleCRT& c1, const DoubleCRT& s, long p, double stdev, Gen& g) {
+  if (p <= 0) throw InvalidArgument("Cannot generate RLWE instance with nonpositive p");
+  const Context& context = s.getContext();
+  if ((context.getM() & (context.getM() - 1)) != 0) stdev *= std::sqrt((double)context.getM());
+  std::vector<long> e;
+  double bound = sampleGaussianBounded(e, context, stdev, g);
+  c0 = DoubleCRT(e, context, c0.getIndexSet());
+  if (p > 1) { c0 *= p; bound *= p; }
+  DoubleCRT tmp(c1);
+  tmp.Mul(s, /*matchIndexSets=*/false);
+  c0 -= tmp;
+  return bound;
+}
+// SecKey::GenKeySWmatrix (src/keys.cpp:1159-1256): W[fromKey -> toKey] over ctxt | special primes,
+// b_i = p*e_i - a_i*s + P*(prod_{j<i} Q_j)*fromKey.  fromKey = s^r(X^t) is passed in already transformed;
+// drawA(a_i) fills a_i with uniform rows (the reference: a[i].randomize() under SetSeed(prgSeed); DoubleCRT::randomize here).
+template <class Gen, class DrawA>
+KeySwitch genKeySWmatrix(const Context& context, DoubleCRT fromKey, const SKHandle& fromHandle, long toKeyID,
+                         const DoubleCRT& toKey, long p, bool ckks, double stdev, Gen& g, DrawA&& drawA) {
+  KeySwitch W; W.fromKey = fromHandle; W.toKeyID = toKeyID;
+  if (ckks) p = 1;
+  else if (p < 2) throw LogicError("Invalid p value found generating BGV key-switching matrix");
+  W.ptxtSpace = p;
+  const IndexSet all = context.getCtxtPrimes() | context.getSpecialPrimes();
+  const size_t n = context.getDigits().size();
+  for (size_t i = 0; i < n; i++) { W.a.emplace_back(context, all); drawA(W.a.back()); }
+  for (size_t i = 0; i < n; i++) { W.b.emplace_back(context, all); W.noiseBound = XD(RLWE1(W.b[i], W.a[i], toKey, p, stdev, g)); }
+  fromKey.addPrimes(all / fromKey.getIndexSet());
+  fromKey.multiplyByPrimes(context.getSpecialPrimes());
+  for (size_t i = 0; i < n; i++) { W.b[i] += fromKey; fromKey.multiplyByPrimes(context.getDigit((long)i)); }
+  return W;
+}
+
 }  // namespace hb

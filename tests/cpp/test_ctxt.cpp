@@ -36,21 +36,10 @@ int main() {
     // secret key and the s^2 -> s key-switching matrix (SecKey::GenKeySWmatrix, src/keys.cpp:1159-1256)
     std::vector<long> s = sample_ternary(gen, N);
     DoubleCRT S(s, ctx, allq);
-    // GenKeySWmatrix (src/keys.cpp:1159-1256): W[fromKey -> s], b_i = p*e_i - a_i*s + P*(prod_{j<i} Q_j)*fromKey
-    auto genKeySW = [&](DoubleCRT fromKey, const SKHandle& h) {
-      KeySwitch W; W.fromKey = h; W.toKeyID = 0; W.ptxtSpace = p;
-      fromKey.multiplyByPrimes(ctx.getSpecialPrimes());
-      for (size_t i = 0; i < ctx.getDigits().size(); i++) {
-        W.a.push_back(random_rows(ctx, allq, gen));
-        std::vector<long> e = sample_gauss(gen, N, sigma);
-        DoubleCRT b(e, ctx, allq); b *= p;                           // RLWE1: b = p*e - a*s  (src/keys.cpp:40-72)
-        DoubleCRT t(W.a.back()); t *= S; b -= t;
-        b += fromKey;
-        W.b.push_back(b);
-        fromKey.multiplyByPrimes(ctx.getDigit(i));
-      }
-      W.noiseBound = XD(double(p) * pk.scale * sigma * std::sqrt(double(N)));
-      pk.keySwitching.push_back(W);
+    // key-switching matrices through the mirror's GenKeySWmatrix / RLWE1, a_i by DoubleCRT::randomize over a byte stream
+    auto bytes = [&](unsigned char* b, long n) { for (long i = 0; i < n; i++) b[i] = (unsigned char)gen(); };
+    auto genKeySW = [&](const DoubleCRT& fromKey, const SKHandle& h) {
+      pk.keySwitching.push_back(hb::genKeySWmatrix(ctx, fromKey, h, 0, S, p, false, sigma, gen, [&](DoubleCRT& a) { a.randomize(bytes); }));
     };
     { DoubleCRT s2(S); s2 *= S; genKeySW(s2, SKHandle(2, 1, 0)); }                 // s^2 -> s
     for (long amt : {3L, m - 1}) { DoubleCRT sk(S); sk.automorph(amt); genKeySW(sk, SKHandle(1, amt, 0)); }   // s(X^amt) -> s
