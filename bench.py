@@ -140,7 +140,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "ctxt_mults_per_s", "value": v, "unit": "mult/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 (60-bit RNS limbs)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], "N": 1 << 16, "l_in": l_in, "l": l, "K": K, "digits": d, "batch": 1},
         "cpu_baseline": {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} multiplies (1 per step), C++ oracle restating NTL-path HElib, threads across primes/coefficients"},
@@ -325,7 +325,7 @@ def main():
                 traffic = tj[base]["avg_dram_bytes_per_launch"] * B / float(tj[base].get("batch") or B)
         ach = top["bytes"] / (top["ms"] / 1000.0) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_kind": peak_kind, "traffic": traffic, "traffic_source": ("profiles/ncu_traffic.json: " + str(tj.get("source", ""))[:160]) if traffic else None, "share_of_step": top["ms"] / tot_ms,
+                "peak_kind": peak_kind, "binding_unit": "integer pipes (ncu: FMA-heavy 67-72 %, ALU 41 % in k1_conv; DRAM 6 %) -- see profiles/", "traffic": traffic, "traffic_source": ("profiles/ncu_traffic.json: " + str(tj.get("source", ""))[:160]) if traffic else None, "share_of_step": top["ms"] / tot_ms,
                 "launches_per_step": top["launches"], "avg_launch_ms": top["ms"] / top["launches"],
                 "alg_bytes_per_launch": top["bytes"] / top["launches"]}
     kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot_ms, 4),
@@ -344,7 +344,7 @@ def main():
     line = {
         "metric": "ctxt_mults_per_s", "value": value, "unit": "mult/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64 (60-bit RNS limbs)", "data": "synthetic",
+        "dtype": "u64", "data": "synthetic",
         "config": {"workload": w["name"], "N": N, "l_in": l_in, "l": l, "K": K, "digits": d, "batch_per_gpu": B,
                    "sharding": "independent ciphertexts per rank, no data-path collective",
                    "l2": f"inputs larger than L2 ({B * 4 * l_in * ROW_BYTES / 2**20:.0f} MiB of operands per step)",
