@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Extract the DoubleCRT rows of the reference's own I/O fixtures (tests/test_resources/iotest_ascii{LE,BE}.txt:
+a context for m=12, p=7 with five chain primes, the public encryption key and the secret key written by a real
+HElib build) into tests/golden/helib_iotest_m12.json.  Run in the build container only (reads /root/reference);
+the tests read the JSON.  These are the only evaluation-form rows produced by the reference itself in its tree,
+so they pin the oracle's general-m conventions: the root chosen by FindPrimitiveRoot and the row order over Z_m^*."""
+import json
+import os
+import re
+import sys
+
+SRC = "/root/reference/tests/test_resources"
+
+
+def parse_file(path):
+    toks = re.findall(r"\[|\]|-?\d+\.\d+|-?\d+", open(path).read())
+
+    def parse(pos):
+        out = []
+        while pos < len(toks):
+            t = toks[pos]
+            if t == "[":
+                sub, pos = parse(pos + 1)
+                out.append(sub)
+            elif t == "]":
+                return out, pos + 1
+            else:
+                out.append(float(t) if "." in t else int(t))
+                pos += 1
+        return out, pos
+    return parse(0)[0]
+
+
+def rows_of(dcrt):
+    return {str(i): dcrt[1 + k] for k, i in enumerate(dcrt[0])}
+
+
+def main():
+    out = {"source": "reference tests/test_resources/iotest_asciiLE.txt, iotest_asciiBE.txt (legacy ASCII I/O fixtures)", "cases": []}
+    for name in ("iotest_asciiLE.txt", "iotest_asciiBE.txt"):
+        tree = parse_file(os.path.join(SRC, name))
+        m, p, r = tree[0][0], tree[0][1], tree[0][2]
+        ctx = tree[1]
+        nprimes = ctx[2]
+        primes = ctx[3:3 + nprimes]
+        special = ctx[1]
+        enc = tree[2][1]                       # [ptxtSpace, noise, primeSet, nparts, part, part]
+        parts = enc[4:]
+        blocks = []
+
+        def rec(x):
+            if isinstance(x, list):
+                if len(x) == nprimes + 1 and isinstance(x[0], list) and x[0] == list(range(nprimes)) and all(isinstance(v, list) for v in x[1:]):
+                    blocks.append(x)
+                for y in x:
+                    rec(y)
+        rec(tree)
+        out["cases"].append({
+            "file": name, "m": m, "p": p, "r": r, "primes": primes, "special": special,
+            "pk_ptxt_space": enc[0], "pk_prime_set": enc[2],
+            "pk_c0": rows_of(parts[0][0]), "pk_c0_handle": parts[0][1],
+            "pk_c1": rows_of(parts[1][0]), "pk_c1_handle": parts[1][1],
+            "secret_key": rows_of(blocks[-1]),
+        })
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "helib_iotest_m12.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

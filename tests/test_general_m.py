@@ -21,7 +21,7 @@ def lib(request):
     return request.getfixturevalue("sim_lib" if request.param == "sim" else "cuda_lib")
 
 
-CFGS = [(45, 2, 1, 100, 2), (28, 3, 1, 100, 2), (105, 2, 1, 120, 2), (1285, 2, 1, 120, 2)]
+CFGS = [(12, 7, 1, 100, 2), (45, 2, 1, 100, 2), (28, 3, 1, 100, 2), (105, 2, 1, 120, 2), (1285, 2, 1, 120, 2)]
 
 
 def setup(lib, cfg):

@@ -192,3 +192,36 @@ def test_golden_vectors():
         O.scale_down(y, cur, S, G["ptxt_space"])
         for i in S:
             assert list(y[i]) == G["scale_down_rows"][str(i)]
+
+
+def test_oracle_general_m_conventions_pinned_by_reference_fixture():
+    """The reference's own I/O fixtures (tests/test_resources/iotest_ascii*.txt, m=12, p=7) hold evaluation-form rows written
+    by a real HElib build: the secret key over five primes and the public encryption key (c0, c1) over three.  With the
+    oracle's root (FindPrimitiveRoot restatement) and row order over Z_m^*, the secret-key rows must invert to ONE ternary
+    polynomial for every prime, and c0 + c1*s to ONE small multiple of p -- any other root or ordering gives noise."""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "helib_iotest_m12.json")))
+    assert len(G["cases"]) == 2
+    for case in G["cases"]:
+        m, p, primes = case["m"], case["p"], case["primes"]
+        assert all((q - 1) % m == 0 and po.is_prime(q) for q in primes)
+        sk_coef = None
+        for i, q in enumerate(primes):
+            root = po.cmod_root(q, m)
+            coef = [po.bal(c, q) for c in po.gen_ifft(case["secret_key"][str(i)], q, m, root)]
+            assert all(c in (-1, 0, 1) for c in coef), (i, coef)
+            assert sk_coef is None or coef == sk_coef
+            sk_coef = coef
+            # and forward again: the oracle's rows of the recovered polynomial are the fixture's rows
+            assert po.gen_fft([c % q for c in coef], q, m, root) == case["secret_key"][str(i)]
+        assert any(sk_coef)
+        noise = None
+        for i in case["pk_prime_set"]:
+            q = primes[i]
+            root = po.cmod_root(q, m)
+            d = [(a + b * s) % q for a, b, s in zip(case["pk_c0"][str(i)], case["pk_c1"][str(i)], case["secret_key"][str(i)])]
+            coef = [po.bal(c, q) for c in po.gen_ifft(d, q, m, root)]
+            assert all(c % p == 0 and abs(c) < 200 * p for c in coef), (i, coef)      # RLWE1: c0 + c1*s = p*e, e ~ 3.2*sqrt(m)
+            assert noise is None or coef == noise
+            noise = coef
