@@ -17,6 +17,11 @@ rows of a key-switching matrix (NTL PRG, src/Ctxt.cpp:196-206).  Both are
 taken as *inputs* by the engine.  Everything else is a pure function of
 (primes, psi, inputs) and is pinned by this restatement plus the
 psi-independent algebraic invariants in tests/.
+
+Pinned by reference output: the general-m conventions (FindPrimitiveRoot root,
+row order over Z_m^*) reproduce the evaluation-form rows a real HElib build
+wrote into the reference's own fixtures tests/test_resources/iotest_ascii*.txt
+(tests/golden/helib_iotest_m12.json, tests/test_oracle.py).
 """
 from __future__ import annotations
 
