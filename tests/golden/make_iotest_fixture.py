@@ -62,6 +62,22 @@ def main():
             "pk_c1": rows_of(parts[1][0]), "pk_c1_handle": parts[1][1],
             "secret_key": rows_of(blocks[-1]),
         })
+    # the binary twin of the LE file holds the same key; its first ciphertext part is a DoubleCRT::writeTo record
+    # (IndexSet, then per row int32 length, int32 intSize, little-endian int64 values) written by the real library
+    import struct
+    raw = open(os.path.join(SRC, "iotest_binLE.bin"), "rb").read()
+    cx = raw.find(b"|CX[")
+    off = cx + 4 + 8 + 16            # eye catcher, ptxtSpace, noise bound (xdouble = double + int64)
+    card = struct.unpack("<q", raw[off:off + 8])[0]
+    off += 8 + 8 * card + 8          # the ciphertext's prime set, number of parts
+    card = struct.unpack("<q", raw[off:off + 8])[0]
+    end = off + 8 + 8 * card
+    for _ in range(card):
+        ln, isz = struct.unpack("<ii", raw[end:end + 8])
+        end += 8 + ln * isz
+    out["dcrt_record"] = {"file": "iotest_binLE.bin", "offset": off, "hex": raw[off:end].hex(),
+                          "noise_bound_field_hex": raw[cx + 12:cx + 28].hex(),
+                          "note": "same rows as cases[0].pk_c0 (iotest_asciiLE.txt); the 16-byte field is the xdouble noise bound 2007.04 = (double mantissa, int64 exponent 0)"}
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "helib_iotest_m12.json")
     json.dump(out, open(dst, "w"), indent=1)
     print("wrote", dst)

@@ -353,3 +353,27 @@ def test_encrypt_decrypt_on_device_match_restated_reference(lib, cfg):
     assert [int(v) for v in E.to_poly_mod_p(ACC, S, p, 1)] == [c % p for c in ref_f]
     with pytest.raises(HbError):
         E.to_poly_mod_p(ACC, S, 1, 0)
+
+
+def test_wire_format_reads_bytes_written_by_the_reference(lib):
+    """A DoubleCRT::writeTo record written by a real HElib build (the first ciphertext part inside the reference's
+    tests/test_resources/iotest_binLE.bin; tests/golden/make_iotest_fixture.py) deserialises to the rows the ASCII twin
+    of that file lists, and serialising them again reproduces the bytes.  (The fixture's ring is m = 12; the record is
+    loaded into an N = 4 context over the same three primes -- the wire format does not involve the transform.)"""
+    import struct
+    from helib_b200.engine import Engine
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "helib_iotest_m12.json")))
+    case, rec = G["cases"][0], G["dcrt_record"]
+    primes = case["primes"][:3]
+    E = Engine(8, primes, None, [[0, 1]], [2], lib=lib)
+    assert E.N == 4
+    blob = bytes.fromhex(rec["hex"])
+    P = E.poly()
+    assert P.deserialize(blob) == [0, 1, 2]
+    got = P.download([0, 1, 2])
+    for i in range(3):
+        assert [int(v) for v in got[i]] == case["pk_c0"][str(i)]
+    assert P.serialize([0, 1, 2]) == blob
+    # the xdouble field next to it: raw double mantissa + int64 exponent (src/binio.cpp:165-171)
+    mant, expo = struct.unpack("<dq", bytes.fromhex(rec["noise_bound_field_hex"]))
+    assert abs(mant - 2007.04) < 1e-9 and expo == 0
