@@ -172,6 +172,8 @@ def test_golden_vectors():
     assert files
     for fn in files:
         G = json.load(open(os.path.join(gdir, fn)))
+        if "params" not in G:      # other fixtures (e.g. the reference's I/O rows) have their own tests
+            continue
         m, p, r, bits, c = G["params"]
         ch, psis = chain(m, p, r, bits, c)
         assert ch.primes == G["primes"] and psis == G["psis"] and ch.digits == G["digits"]
