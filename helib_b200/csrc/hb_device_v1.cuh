@@ -620,3 +620,98 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = a[l];   // lazy: k1_fwd_blk finishes the transform
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Conversion from ONE source prime (the CKKS rescale / any single-prime mod-down without a plaintext
+// correction): x = balanced(y), y the coefficient modulo q_s, so there is no MAC loop and no fixed-point
+// quotient -- x mod q_t = (y mod q_t) - [y > (q_s-1)/2] * (q_s mod q_t).  CQ quads of 4 columns per CTA keep
+// more groups busy during the (single-row) source phase.  Opt-in (HB_CONV1=1) until measured on the GPU.
+// smem: Y[CQ][HB1_TS] | W[NG][HB1_TS]
+struct Hb1Conv1Job {
+  int logN, ngroups, cq, nitems;
+  int src_prime, nt;
+  int tgt_prime[HB_MAXROWS];
+  u64 qs_mod[HB_MAXROWS];      // q_s mod q_t
+  u64 ninv, ninv_s;            // N^-1 mod q_s (+Shoup): the (Q/q_j)^-1 factor is 1 for a single prime
+  const u64* src[HB_MAXB];
+  u64* dst[HB_MAXB];
+};
+template <bool SP>
+__global__ void __launch_bounds__(640, 1) k1_conv1(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb1Conv1Job J) {
+  HB_SMEM_DECL
+  const int NG = J.ngroups, CQ = J.cq, nt = J.nt;
+  u64* Y = HB_SMEM;                               // [CQ][HB1_TS]
+  u64* W = Y + (size_t)CQ * HB1_TS;               // [NG][HB1_TS]
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6, gt = tid & 63;
+  const int c = gt & 3, x = gt >> 2;
+  const unsigned c0 = blockIdx.x * 4u * (unsigned)CQ;
+  const u64* src = J.src[blockIdx.y];
+  u64* dst = J.dst[blockIdx.y];
+  const HbPrimeDev PS = primes[J.src_prime];
+  // ---- source: inverse cols phase of the quads, canonical coefficients into Y
+  for (int qd = grp; qd < CQ; qd += NG) {
+    HB1_MOD(M, PS);
+    const u64* s = src + ((size_t)J.src_prime << J.logN) + c0 + 4 * qd + c;
+    u64* Yq = Y + (size_t)qd * HB1_TS + c * HB1C_BS;
+    u64 a[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = s[(size_t)(16 * x + l) << 8];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = PS.iw + 16 + x; tw.p[1] = PS.iw + 32 + 2 * x; tw.p[2] = PS.iw + 64 + 4 * x; tw.p[3] = PS.iw + 128 + 8 * x;
+      hb1_r16_inv<SP>(a, tw, M);
+    }
+#pragma unroll
+    for (int l = 0; l < 16; l++) Yq[HB1_RS * x + l] = a[l];
+    hb_group_sync(grp, 64);
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = Yq[HB1_RS * r + x];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = PS.iw + 1; tw.p[1] = PS.iw + 2; tw.p[2] = PS.iw + 4; tw.p[3] = PS.iw + 8;
+      hb1_r16_inv<SP>(a, tw, M);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; r++) Yq[HB1_RS * r + x] = hb_mul_shoup(a[r], J.ninv, J.ninv_s, PS.q);
+  }
+  __syncthreads();
+  // ---- targets
+  const u64 qs_half = (PS.q - 1) >> 1;
+  u64* Wg = W + (size_t)grp * HB1_TS + c * HB1C_BS;
+  for (int w = grp; w < nt * CQ; w += NG) {
+    const int t = w / CQ, qd = w - t * CQ;
+    const int pi = J.tgt_prime[t];
+    const HbPrimeDev P = primes[pi];
+    HB1_MOD(M, P);
+    const u64 adj = P.q - J.qs_mod[t];          // -(q_s mod q_t) mod q_t, in (0, q_t]
+    const u64* Yq = Y + (size_t)qd * HB1_TS + c * HB1C_BS + x;
+    u64 a[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const u64 y = Yq[HB1_RS * r];
+      u64 v = y - __umul64hi(y, P.one_s) * P.q;   // y mod q_t, in [0, 2 q_t)
+      if (y > qs_half) v += adj;                  // balanced representative: subtract q_s   -> [0, 3 q_t]
+      a[r] = v;
+    }
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;
+      hb1_r16_fwd<SP>(a, tw, M);
+    }
+    hb_group_sync(grp, 64);   // the previous item's pass-2 reads of Wg are complete
+#pragma unroll
+    for (int r = 0; r < 16; r++) Wg[HB1_RS * r + x] = a[r];
+    hb_group_sync(grp, 64);
+#pragma unroll
+    for (int l = 0; l < 16; l++) a[l] = Wg[HB1_RS * x + l];
+    {
+      Hb1TwPtr tw;
+      tw.p[0] = P.fw + 16 + x; tw.p[1] = P.fw + 32 + 2 * x; tw.p[2] = P.fw + 64 + 4 * x; tw.p[3] = P.fw + 128 + 8 * x;
+      hb1_r16_fwd<SP>(a, tw, M);
+    }
+    u64* d = dst + ((size_t)pi << J.logN) + c0 + 4 * qd + c;
+#pragma unroll
+    for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = a[l];   // lazy: k1_fwd_blk finishes the transform
+  }
+}

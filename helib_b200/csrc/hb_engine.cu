@@ -77,6 +77,7 @@ struct hb_ctx {
   cudaEvent_t ev0, ev1;
   size_t max_smem;
   bool force_v0;     // HB_FORCE_V0=1: generic radix-2 kernels only (A/B testing)
+  bool conv1;        // HB_CONV1=1: dedicated single-source conversion kernel (opt-in until measured on the GPU)
   int chunk;         // batch items per launch (<= HB_MAXB; HB_CHUNK overrides): keeps the phase scratch L2-sized
   int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
   // general (non power-of-two) m: Bluestein state
@@ -180,6 +181,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
   { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
+  { const char* e = getenv("HB_CONV1"); c->conv1 = e && e[0] == '1'; }
   { const char* e = getenv("HB_CHUNK"); int v = e ? atoi(e) : HB_MAXB; c->chunk = v >= 1 && v <= HB_MAXB ? v : HB_MAXB; }
   c->resident_ctas = 296;
 #ifdef HB_SIM
@@ -269,6 +271,8 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem + 1024));
   HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -787,6 +791,22 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
   tmp_ptrs(c, c->tmpA, nit, tA); tmp_ptrs(c, c->tmpB, nit, tB);
   if (src_is_y) { for (int i = 0; i < nit; i++) tA[i] = polys[i]; }
   else HB_TRY(launch_blk(c, -1, (const u64* const*)polys, tA, nit, src, n, 0, nullptr));
+  if (v1_cols_ok(c) && c->conv1 && n == 1 && p <= 1 && !src_is_y && !want_frac && nt <= HB_MAXROWS) {
+    // single source prime, no plaintext correction: dedicated kernel without the MAC loop / quotient phase
+    Hb1Conv1Job J1; memset(&J1, 0, sizeof(J1));
+    const int cq = 2, ng = 10;
+    J1.logN = c->logN; J1.ngroups = ng; J1.cq = cq; J1.nitems = nit; J1.src_prime = src[0]; J1.nt = nt;
+    const u64 qs = c->q[src[0]];
+    for (int t = 0; t < nt; t++) { J1.tgt_prime[t] = tgt[t]; J1.qs_mod[t] = qs % c->q[tgt[t]]; }
+    u64 ninv; if (!h_invmod(c->N % qs, qs, &ninv)) return hb_fail(HB_ERR_BAD_ARG, "N not invertible");
+    J1.ninv = ninv; J1.ninv_s = h_shoup(ninv, qs);
+    for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
+    const size_t smem1 = (size_t)(cq + ng) * HB1_TS * sizeof(u64);
+    pre_launch(c);
+    if (all_special(c)) HB_LAUNCH(k1_conv1<true>, dim3(64 / cq, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+    else HB_LAUNCH(k1_conv1<false>, dim3(64 / cq, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+    return post_launch(c, "k1_conv1", (u64)(n + nt) * nit * c->N * 8);
+  }
   if (v1_cols_ok(c)) {
     // number of 64-thread row groups: balance of the n source rows / nt target rows, resident warps,
     // and (for small source sets) co-residency of two CTAs so that one CTA's thin source phase

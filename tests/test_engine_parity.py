@@ -350,3 +350,32 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
             O.automorph(rd[i], Sp, k)
         O.keyswitch_digits(rd, Sp, evk_a, evk_b, r0, r1)
         assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
+
+
+def test_single_source_conversion_kernel_opt_in(lib, monkeypatch):
+    """HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
+    kernel k1_conv1; results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
+    prime, and (different bit lengths between source and targets) with rows at the extremes."""
+    monkeypatch.setenv("HB_CONV1", "1")
+    cfg = (1 << 17, -1, 1, 230, 2)
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    rng = np.random.default_rng(21)
+    E.reset_stats() if hasattr(E, "reset_stats") else None
+    cases = [(ch.ctxt, ch.ctxt[:-1]), (ch.ctxt + ch.special[:1], ch.ctxt)]
+    if ch.small:
+        cases.append((sorted(ch.small[:1] + ch.ctxt), ch.ctxt))
+    for cur, keep in cases:
+        x = O.random(rng, cur)
+        drop = [i for i in cur if i not in keep][0]
+        qd = ch.primes[drop]
+        x[drop][:8] = [0, 1, qd - 1, (qd - 1) // 2, (qd + 1) // 2, qd // 2 - 1, 2, qd - 2]
+        P = E.poly(x, cur)
+        E.scale_down([P], cur, keep, 1)
+        ref = x.copy(); O.scale_down(ref, cur, keep, 1)
+        assert rows_equal(P.download(keep), ref, keep), (cur, keep)
+    # batched, two polys at once
+    a, b = O.random(rng, ch.ctxt), O.random(rng, ch.ctxt)
+    A, B = E.poly(a, ch.ctxt), E.poly(b, ch.ctxt)
+    E.scale_down([A, B], ch.ctxt, ch.ctxt[:-1], 1)
+    O.scale_down(a, ch.ctxt, ch.ctxt[:-1], 1); O.scale_down(b, ch.ctxt, ch.ctxt[:-1], 1)
+    assert rows_equal(A.download(ch.ctxt[:-1]), a, ch.ctxt[:-1]) and rows_equal(B.download(ch.ctxt[:-1]), b, ch.ctxt[:-1])
