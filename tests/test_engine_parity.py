@@ -352,13 +352,13 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
         assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
 
 
-def test_single_source_conversion_kernel_opt_in(lib, monkeypatch):
-    """HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
+def test_single_source_conversion_kernel_opt_in(sim_lib, monkeypatch):
+    """(Simulator only while the kernel is opt-in: it has not run on a GPU yet.)  HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
     kernel k1_conv1; results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
     prime, and (different bit lengths between source and targets) with rows at the extremes."""
     monkeypatch.setenv("HB_CONV1", "1")
     cfg = (1 << 17, -1, 1, 230, 2)
-    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    ch, psis, O, E = make(sim_lib, *cfg, nthreads=8)
     rng = np.random.default_rng(21)
     E.reset_stats() if hasattr(E, "reset_stats") else None
     cases = [(ch.ctxt, ch.ctxt[:-1]), (ch.ctxt + ch.special[:1], ch.ctxt)]
