@@ -891,3 +891,70 @@ def randomize_rows(chain, idxs, get_bytes):
                 pos += nb
         rows[i] = row
     return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# ModuliSizes (src/primeChain.cpp:66-319): the table of candidate prime sets and the two getSet4Size searches that
+# Ctxt::multLowLvl / modDownToLevel use to pick the common prime set from noise estimates.
+
+class ModuliSizes:
+    def __init__(self, chain):
+        """ModuliSizes::init (src/primeChain.cpp:66-121): every subset of the small primes, alone and joined with every
+        prefix interval of the ctxt primes; sorted by log-size."""
+        self.ifft_cost = 0 if chain.pow2 else 20
+        sizes = [(0.0, frozenset())]
+        idx = 1
+        for i in chain.small:
+            sz = math.log(chain.primes[i])
+            for j in range(idx, 2 * idx):
+                f, s = sizes[j - idx]
+                sizes.append((f + sz, s | {i}))
+            idx *= 2
+        interval = set()
+        interval_size = 0.0
+        for i in chain.ctxt:
+            interval.add(i)
+            interval_size += math.log(chain.primes[i])
+            for j in range(idx):
+                f, s = sizes[j]
+                sizes.append((f + interval_size, s | interval))
+        self.sizes = sorted(sizes, key=lambda e: (e[0], sorted(e[1])))
+
+    def _cost(self, frm, to):
+        """cost_estimate (src/primeChain.cpp:146-157)."""
+        add = len(to - frm)
+        return 100 * add if self.ifft_cost == 0 else 100 * add + self.ifft_cost * len(frm - to)
+
+    def get_set4size(self, low, high, from1, from2=None, reverse=False):
+        """ModuliSizes::getSet4Size, one- and two-operand forms (src/primeChain.cpp:179-243, 250-319)."""
+        froms = [frozenset(from1)] + ([frozenset(from2)] if from2 is not None else [])
+        n = len(self.sizes)
+        idx = 0
+        while idx < n and self.sizes[idx][0] < low:
+            idx += 1
+        best, best_cost = -1, None
+        ii = idx
+        while ii < n and self.sizes[ii][0] <= high:
+            cost = sum(self._cost(f, self.sizes[ii][1]) for f in froms)
+            if best_cost is None or cost <= best_cost:
+                best, best_cost = ii, cost
+            ii += 1
+        if best == -1:
+            if reverse:
+                if ii < n:
+                    upper = self.sizes[ii][0] + math.log(2.0)
+                    i = ii
+                    while i < n and self.sizes[i][0] <= upper:
+                        cost = sum(self._cost(f, self.sizes[i][1]) for f in froms)
+                        if best_cost is None or cost < best_cost:
+                            best, best_cost = i, cost
+                        i += 1
+            elif idx > 0:
+                lower = self.sizes[idx - 1][0] - math.log(2.0)
+                i = idx - 1
+                while i >= 0 and self.sizes[i][0] >= lower:
+                    cost = sum(self._cost(f, self.sizes[i][1]) for f in froms)
+                    if best_cost is None or cost < best_cost:
+                        best, best_cost = i, cost
+                    i -= 1
+        return sorted(self.sizes[best][1]) if best != -1 else []

@@ -125,3 +125,31 @@ def test_no_device_fails_loudly(lib):
     with pytest.raises(HbError) as ei:
         Engine(64, ch.primes, lib=lib)
     assert ei.value.code == -3   # HB_ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("name", ["cfg1_bgv_m4096", "cfg2_ckks_2^17_1190", "bgv_p17r2", "thinboot_m21845_chain_only"])
+def test_set4size_matches_restated_reference(lib, name):
+    """hb_chain_set4size (product, C++) vs the Python restatement of ModuliSizes::getSet4Size (src/primeChain.cpp:179-319)
+    on random windows: one- and two-operand forms, both search directions, windows that contain candidates and windows
+    that fall between them (the one-bit-of-slack fallback), from-sets that are prefixes with and without small primes."""
+    import random
+    m, p, r, bits, c = CONFIGS[name]
+    ref = po.build_mod_chain(m, p, r, bits, c)
+    ch = Chain(m, p, r, bits, c, lib=lib)
+    MS = po.ModuliSizes(ref)
+    rnd = random.Random(hash(name) & 0xffff)
+    total = sum(math.log(ref.primes[i]) for i in ref.small + ref.ctxt)
+    for trial in range(300):
+        def some_set():
+            k = rnd.randint(1, len(ref.ctxt))
+            s = list(ref.ctxt[:k])
+            s += [i for i in ref.small if rnd.random() < 0.3]
+            return sorted(s)
+        f1 = some_set()
+        f2 = some_set() if rnd.random() < 0.6 else None
+        low = rnd.uniform(0.0, total * 1.05)
+        width = rnd.choice([0.01, 0.5, 2.0, 4 * math.log(2), 40.0])
+        rev = rnd.random() < 0.5
+        want = MS.get_set4size(low, low + width, f1, f2, rev)
+        got = ch.set4size(low, low + width, f1, f2, reverse=rev)
+        assert sorted(got) == want, (trial, low, width, f1, f2, rev)
