@@ -46,7 +46,8 @@ struct XD {
   XD operator*(const XD& o) const { return make(m * o.m, e + o.e); }
   XD operator/(const XD& o) const { return make(m / o.m, e - o.e); }
   XD operator+(const XD& o) const {
-    if (m == 0) return o; if (o.m == 0) return *this;
+    if (m == 0) return o;
+    if (o.m == 0) return *this;
     if (e >= o.e) { long d = e - o.e; return d > 1100 ? *this : make(m + std::ldexp(o.m, (int)-d), e); }
     return o + *this;
   }
