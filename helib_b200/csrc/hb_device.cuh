@@ -254,6 +254,10 @@ struct HbKsJob {            // Ctxt::keySwitchDigits inner product
   //   out0 = scal*sigma_k(c0) + sum_i sigma_k(D_i)*b_i ,  out1 = sum_i sigma_k(D_i)*a_i       (power-of-two m)
   u64 ak, am;
   const u64* c0[HB_MAXB];
+  // fused breakIntoDigits: the rows of digit i's own primes live in own[item] (the part being switched, updated in place
+  // by the mixed-radix steps) instead of dig[item][i];  own_dig[row] = that digit, or -1
+  const u64* own[HB_MAXB];
+  signed char own_dig[HB_MAXROWS];
 };
 
 // ------------------------------------------------------------------------------------------

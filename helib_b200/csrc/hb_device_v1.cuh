@@ -177,13 +177,19 @@ __device__ __forceinline__ unsigned hb1_brev4(unsigned x) {
   return ((x & 1u) << 3) | ((x & 2u) << 1) | ((x & 4u) >> 1) | ((x & 8u) >> 3);
 }
 
+// forward epilogues:  0 store x;  1 dst = (dst - x) * scal[row]  (scaleDownToSet, src/DoubleCRT.cpp:1512-1515);
+//   3 (fused breakIntoDigits, src/DoubleCRT.cpp:540-556): dst = x and, on rows with scal != 0 (the rows of the later digits),
+//     dst2 = (dst2 - x) * scal[row] in the same pass -- the mixed-radix update without a separate pointwise launch.
+// lazy != 0: stored values are only reduced to [0,4q) (epilogue products) / [0, 8q + 2^32) (plain x): every consumer inside the
+//   fused ciphertext paths (tensor product, evk inner product, inverse blk phase) takes such values.
 struct Hb1BlkJob {
-  int logN, epi;
+  int logN, epi, lazy;
   HbRows rows;
   u64 scal[HB_MAXROWS], scal_s[HB_MAXROWS];
   int nitems;
   const u64* src[HB_MAXB];
   u64* dst[HB_MAXB];
+  u64* dst2[HB_MAXB];
 };
 
 // 8-byte asynchronous global->shared copy (LDGSTS) and its group fences
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
   const int blk1 = tid >> 4, lo = tid & 15;
   const int hi = tid >> 4, blk2 = tid & 15;
   const unsigned hrev = hb1_brev4(hi);
-  const bool epi = J.epi == 1;
+  const bool epi1 = J.epi == 1, epi3 = J.epi == 3, lazy = J.lazy != 0;
   const int own = blk1 * HB1_BS + lo;   // + HB1_RS * r
   Hb1TwPtr tw1;
   tw1.p[0] = TW1 + blk1 * 16; tw1.p[1] = tw1.p[0] + 1; tw1.p[2] = tw1.p[0] + 3; tw1.p[3] = tw1.p[0] + 7;
@@ -287,10 +293,13 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
       __syncthreads();  // TW1 visible (the previous unit's trailing barrier ordered its last use)
     }
     u64* Sb = S + buf * HB1_STAGE;
-    u64* dst = J.dst[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN) + (cur.ug << 4) + blk2;
+    const size_t doff = ((size_t)J.rows.prime[cur.rowi] << J.logN) + (cur.ug << 4) + blk2;
+    u64* dst = J.dst[cur.it] + doff;
+    const bool epi = epi1 || (epi3 && sc != 0);           // uniform per unit
+    u64* old = epi3 ? J.dst2[cur.it] + doff : dst;        // where the value to be updated lives
     if (epi) {
 #pragma unroll
-      for (int l = 0; l < 16; l++) hb1_cp8(O + l * 256 + tid, dst + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
+      for (int l = 0; l < 16; l++) hb1_cp8(O + l * 256 + tid, old + ((size_t)((hb1_brev4(l) << 4) | hrev) << n1));
     }
     hb1_cp_commit();
     Hb1Unit nxt = cur;
@@ -317,10 +326,12 @@ __global__ void __launch_bounds__(256, 2) k1_fwd_blk(const HbPrimeDev* __restric
 #pragma unroll
     for (int l = 0; l < 16; l++) {
       const size_t o = (size_t)((hb1_brev4(l) << 4) | hrev) << n1;   // brev8(16*hi + l) * N1
-      u64 v;
-      if (epi) v = hb1_canon4(hb1_shoup4<SP>(O[l * 256 + tid] - a[l] + (M.qb2 + M.qb), sc, sc_s, M), q);   // (old - x) * P^-1, x in [0, 8q + 2^32)
-      else v = hb1_canon_fwd(a[l], q, M.qb);
-      dst[o] = v;
+      if (epi) {
+        u64 v = hb1_shoup4<SP>(O[l * 256 + tid] - a[l] + (M.qb2 + M.qb), sc, sc_s, M);   // (old - x) * P^-1, x in [0, 8q + 2^32), old < 4q
+        if (!lazy) v = hb1_canon4(v, q);
+        old[o] = v;
+      }
+      if (!epi1) dst[o] = lazy ? a[l] : hb1_canon_fwd(a[l], q, M.qb);
     }
     __syncthreads();   // exchange reads of Sb / TW1 done before they are overwritten
     cur = nxt;
@@ -498,6 +509,7 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
 // Row tile layout: Y[c*HB1C_BS + 17*(i1>>4) + (i1&15)], c in [0,4), i1 in [0,256).
 #define HB1C_BS 276           // column stride in k1_conv (2*276 mod 32 = 8: 4 cols x 4 rows conflict-free)
 #define HB1_TS (4 * HB1C_BS)  // u64 per row tile (1104)
+#define HB1_VS 260            // column stride of the quotient tile (260 mod 16 = 4)
 
 struct Hb1ConvJob {
   const HbConvDev* cv;
@@ -516,8 +528,8 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
   const HbConvDev* cv = J.cv;
   const int n = cv->n, nt = cv->nt, NG = J.ngroups;
   u64* Y = HB_SMEM;                               // [n][HB1_TS]
-  i64* Vb = (i64*)(Y + (size_t)n * HB1_TS);       // [1024]  index c*256 + i1
-  u64* W = (u64*)(Vb + 1024);                     // [NG][HB1_TS]
+  i64* Vb = (i64*)(Y + (size_t)n * HB1_TS);       // [4][HB1_VS]  index c*HB1_VS + i1 (padded: the 4 columns of a half-warp hit different banks)
+  u64* W = (u64*)(Vb + 4 * HB1_VS);               // [NG][HB1_TS]
   const int tid = threadIdx.x;
   const int grp = tid >> 6, gt = tid & 63;
   const int c = gt & 3, x = gt >> 2;              // x in [0,16)
@@ -565,7 +577,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
     const int cc = e >> 8, i1 = e & 255;
     double* fr = J.frac[blockIdx.y];
     double f;
-    Vb[e] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
+    Vb[cc * HB1_VS + i1] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
     if (fr) fr[((size_t)i1 << 8) + c0 + cc] = f;
   }
   __syncthreads();
@@ -584,7 +596,7 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
         u64 ahi[8], alo[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-          const i64 v = Vb[c * 256 + 16 * (8 * h + r) + x];
+          const i64 v = Vb[c * HB1_VS + 16 * (8 * h + r) + x];
           const u64 m = v >= 0 ? (u64)v : (u64)(-v);
           const u64 f = v >= 0 ? negq : posq;
           alo[r] = m * f; ahi[r] = __umul64hi(m, f);
@@ -713,5 +725,44 @@ __global__ void __launch_bounds__(640, 1) k1_conv1(const HbPrimeDev* __restrict_
     u64* d = dst + ((size_t)pi << J.logN) + c0 + 4 * qd + c;
 #pragma unroll
     for (int l = 0; l < 16; l++) d[(size_t)(16 * x + l) << 8] = a[l];   // lazy: k1_fwd_blk finishes the transform
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ctxt::keySwitchDigits (src/Ctxt.cpp:191-230), streaming form for power-of-two m: every thread owns two adjacent
+// coefficients of one row (128-bit loads and stores), keeps the 2*ND evaluation-key words of that position in registers
+// and loops over the batch items, so the key rows are fetched once per launch instead of once per item.
+// modes 0 and 1 of HbKsJob (mode 2, the hoisted automorphism, gathers and stays with k_ks_inner).
+// grid = (N / 512, nrows, item groups)
+__device__ __forceinline__ ulonglong2 hb1_ld2(const u64* p) { return *reinterpret_cast<const ulonglong2*>(p); }
+__device__ __forceinline__ void hb1_st2(u64* p, u64 x, u64 y) { ulonglong2 v; v.x = x; v.y = y; *reinterpret_cast<ulonglong2*>(p) = v; }
+template <int ND>
+__global__ void __launch_bounds__(256) k1_ks_inner(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT HbKsJob J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const size_t o = (size_t)pi * (size_t)J.N + 2 * ((size_t)blockIdx.x * 256 + threadIdx.x);
+  ulonglong2 ea[ND], eb[ND];
+#pragma unroll
+  for (int i = 0; i < ND; i++) { ea[i] = hb1_ld2(J.evk_a[i] + o); eb[i] = hb1_ld2(J.evk_b[i] + o); }
+  const int own = J.own_dig[blockIdx.y];
+  const u64 sc = J.scal[blockIdx.y];
+  const bool rd = J.mode == 0 || sc != 0;
+  for (int it = blockIdx.z; it < J.nitems; it += gridDim.z) {
+    ulonglong2 d[ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++) d[i] = hb1_ld2((i == own ? J.own[it] : J.dig[it][i]) + o);
+    u64 h0x = 0, l0x = 0, h0y = 0, l0y = 0, h1x = 0, l1x = 0, h1y = 0, l1y = 0;
+    if (rd) {
+      const ulonglong2 p0 = hb1_ld2(J.out0[it] + o), p1 = hb1_ld2(J.out1[it] + o);
+      if (J.mode == 0) { l0x = p0.x; l0y = p0.y; l1x = p1.x; l1y = p1.y; }
+      else { hb1_mac128(h0x, l0x, p0.x, sc); hb1_mac128(h0y, l0y, p0.y, sc); hb1_mac128(h1x, l1x, p1.x, sc); hb1_mac128(h1y, l1y, p1.y, sc); }
+    }
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+      hb1_mac128(h0x, l0x, d[i].x, eb[i].x); hb1_mac128(h0y, l0y, d[i].y, eb[i].y);
+      hb1_mac128(h1x, l1x, d[i].x, ea[i].x); hb1_mac128(h1y, l1y, d[i].y, ea[i].y);
+    }
+    hb1_st2(J.out0[it] + o, hb_reduce128(h0x, l0x, P), hb_reduce128(h0y, l0y, P));
+    hb1_st2(J.out1[it] + o, hb_reduce128(h1x, l1x, P), hb_reduce128(h1y, l1y, P));
   }
 }

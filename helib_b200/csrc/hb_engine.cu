@@ -546,23 +546,23 @@ static int pick_item_groups(hb_ctx* c, long ctas_per_item_group, int nitems) {
   return best;
 }
 static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
-                         int epi, const u64* scal) {
+                         int epi, const u64* scal, int lazy = 0, u64* const* dst2 = nullptr) {
   const int n1 = c->logN - 8;
   const size_t smem = (2 * HB1_STAGE + (dir > 0 ? 16 * 256 : 0)) * sizeof(u64) + 256 * sizeof(ulonglong2);
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
     int nr = std::min(HB_MAXROWS, n - r0);
     Hb1BlkJob J; memset(&J, 0, sizeof(J));
-    J.logN = c->logN; J.epi = epi;
+    J.logN = c->logN; J.epi = epi; J.lazy = lazy;
     if (dir < 0) J.epi = v1_cols_ok(c) ? 2 : 0;   // inverse: the next phase is a register kernel (cols or fused conversion) -> lazy values may stay
     fill_rows(J.rows, idx + r0, nr);
     for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
     J.nitems = nitems;
-    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; if (dst2) J.dst2[i] = dst2[i]; }
     long units = (long)nr * nitems << (n1 - 4);
     dim3 grid((unsigned)std::min<long>(units, c->resident_ctas));   // persistent CTAs, balanced contiguous chunks
     pre_launch(c);
     const bool sp = all_special(c);
-    if (dir > 0) { if (sp) HB_LAUNCH(k1_fwd_blk<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_fwd_blk<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi ? "k1_fwd_blk_subscale" : "k1_fwd_blk", (u64)(epi ? 3 : 2) * nr * nitems * c->N * 8)); }
+    if (dir > 0) { if (sp) HB_LAUNCH(k1_fwd_blk<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_fwd_blk<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi == 1 ? "k1_fwd_blk_subscale" : (epi == 3 ? "k1_fwd_blk_digits" : "k1_fwd_blk"), (u64)(epi == 1 ? 3 : 2) * nr * nitems * c->N * 8)); }
     else { if (sp) HB_LAUNCH(k1_inv_blk<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_inv_blk<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
@@ -587,8 +587,9 @@ static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const*
 
 // direction: +1 forward blk (src -> dst, optional epilogue), -1 inverse blk
 static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
-                      int epi, const u64* scal) {
-  if (v1_blk_ok(c)) return launch_blk_v1(c, dir, src, dst, nitems, idx, n, epi, scal);
+                      int epi, const u64* scal, int lazy = 0, u64* const* dst2 = nullptr) {
+  if (v1_blk_ok(c)) return launch_blk_v1(c, dir, src, dst, nitems, idx, n, epi, scal, lazy, dst2);
+  if (lazy || dst2 || epi == 3) return hb_fail(HB_ERR_UNSUPPORTED, "lazy / dual-epilogue blk phase needs the register kernels");
   const int lwb = logwb_of(c);
   const int n1 = c->logN - c->log_blk;
   const size_t smem = ((size_t)1 << lwb) * (((size_t)1 << c->log_blk) + 1) * sizeof(u64);
@@ -813,7 +814,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
     // overlaps the other's target phase
     int ng = 0; double best = -1; size_t smem1 = 0;
     for (int g = 10; g >= 4; g--) {
-      size_t sm = ((size_t)(n + g) * HB1_TS + 1024) * sizeof(u64);
+      size_t sm = ((size_t)(n + g) * HB1_TS + 4 * HB1_VS) * sizeof(u64);
       if (sm > 224 * 1024) continue;
       int by_smem = (int)((227 * 1024) / (sm + 1024)), by_regs = 65536 / (96 * 64 * g);
       int ctas = std::max(1, std::min(std::min(by_smem, by_regs), 2));
@@ -1176,7 +1177,8 @@ extern "C" int hb_add_primes_norm(hb_poly* const* polys, int nitems, const int32
   return add_primes_impl(polys, nitems, cur, ncur, add, nadd, log_norms);
 }
 // norms (optional, [nitems]): canonical-embedding norm of delta/P (the "fdelta" of Ctxt::modDownToSet, src/Ctxt.cpp:476-505)
-static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space, double* norms) {
+// lazy: results only reduced to [0,4q) (register kernels only; for consumers inside the fused ciphertext paths)
+static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur, int ncur, const int32_t* keep, int nkeep, uint64_t ptxt_space, double* norms, int lazy = 0) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(polys, nitems, &c, "hb_scale_down"));
   HB_TRY(check_idx(c, cur, ncur, "hb_scale_down")); HB_TRY(check_idx(c, keep, nkeep, "hb_scale_down(keep)", true));
   if (ptxt_space < 1) return hb_fail(HB_ERR_BAD_ARG, "ptxtSpace must be at least 1");  // src/DoubleCRT.cpp:1472
@@ -1202,7 +1204,7 @@ static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* tB[HB_MAXB]; ptrs_of(polys, i0, nit, P); tmp_ptrs(c, c->tmpB, nit, tB);
     HB_TRY(conv_chunk(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space, 0, norms != nullptr));
-    HB_TRY(launch_blk(c, +1, (const u64* const*)tB, P, nit, kept.data(), (int)kept.size(), 1, sc.data()));
+    HB_TRY(launch_blk(c, +1, (const u64* const*)tB, P, nit, kept.data(), (int)kept.size(), 1, sc.data(), lazy && v1_blk_ok(c) ? 1 : 0));
     if (norms) HB_TRY(norm_chunk(c, nit, norms + i0));
     return HB_OK;
   });
@@ -1631,10 +1633,10 @@ static int break_into_digits_impl(hb_poly* const* src, int nitems, const int32_t
 
 static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                                  hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal,
-                                 u64 autok, hb_poly* const* c0);
+                                 u64 autok, hb_poly* const* c0, hb_poly* const* own = nullptr, const int* own_dig = nullptr);
 extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                                    hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1) {
-  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr, 0, nullptr);
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr, 0, nullptr, nullptr, nullptr);
 }
 // Hoisted automorphism + key switch (next row 8f-1): BasicAutomorphPrecon::automorph (src/matmul.cpp:112-184).
 extern "C" int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* S, int nS,
@@ -1654,9 +1656,10 @@ extern "C" int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig,
 }
 // scal (optional, [n]): out = scal[r]*out + sum (0 => out = sum): addPrimesAndScale folded in.
 // autok != 0: digits and c0 are read through the automorphism sigma_autok (hoisting), out0/out1 are pure outputs.
+// own / own_dig (fused breakIntoDigits): rows idx[r] with own_dig[r] = i >= 0 read digit i from own[item] instead of digits[item][i].
 static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                                  hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1, const u64* scal,
-                                 u64 autok = 0, hb_poly* const* c0 = nullptr) {
+                                 u64 autok, hb_poly* const* c0, hb_poly* const* own, const int* own_dig) {
   hb_ctx* c = nullptr;
   HB_TRY(check_polys(out0, nitems, &c, "hb_keyswitch_digits")); HB_TRY(check_polys(out1, nitems, &c, "hb_keyswitch_digits"));
   if (ndig <= 0 || ndig > HB_MAXDIG || ndig > maxdig) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits: ndig=%d out of range", ndig);
@@ -1675,6 +1678,25 @@ static int keyswitch_digits_impl(hb_poly* const* digits, int maxdig, int ndig, i
       for (int it = 0; it < nit; it++) {
         J.out0[it] = out0[i0 + it]->d; J.out1[it] = out1[i0 + it]->d;
         for (int i = 0; i < ndig; i++) J.dig[it][i] = digits[(i0 + it) * maxdig + i]->d;
+      }
+      for (int i = 0; i < nr; i++) J.own_dig[i] = own_dig ? (signed char)own_dig[r0 + i] : (signed char)-1;
+      if (own) for (int it = 0; it < nit; it++) J.own[it] = own[i0 + it]->d;
+      const bool stream_form = !c->gen.on && !autok && ndig <= 4 && c->N % 512 == 0 && !getenv("HB_KS_V0");
+      if (own && !stream_form) return hb_fail(HB_ERR_UNSUPPORTED, "hb_keyswitch_digits: aliased digit rows need the streaming kernel");
+      if (stream_form) {
+        // item groups: enough CTAs for a few waves, as few re-fetches of the key rows as possible
+        const long per = (long)(c->N / 512) * nr;
+        int z = 1; while (z < nit && per * z < 8L * c->resident_ctas) z *= 2;
+        dim3 g((unsigned)(c->N / 512), nr, std::min(z, nit));
+        pre_launch(c);
+        switch (ndig) {
+          case 1: HB_LAUNCH(k1_ks_inner<1>, g, dim3(256), 0, c->stream, c->d_primes, J); break;
+          case 2: HB_LAUNCH(k1_ks_inner<2>, g, dim3(256), 0, c->stream, c->d_primes, J); break;
+          case 3: HB_LAUNCH(k1_ks_inner<3>, g, dim3(256), 0, c->stream, c->d_primes, J); break;
+          default: HB_LAUNCH(k1_ks_inner<4>, g, dim3(256), 0, c->stream, c->d_primes, J); break;
+        }
+        HB_TRY(post_launch(c, "k1_ks_inner", ((u64)(ndig + 4) * nit + 2 * ndig) * nr * c->N * 8));
+        continue;
       }
       unsigned gx = (unsigned)std::max<size_t>(1, c->N / (HB_THREADS * 4));
       pre_launch(c);
@@ -1732,6 +1754,62 @@ extern "C" int hb_automorph(hb_poly* const* dst, hb_poly* const* src, int nitems
 
 // ------------------------------------------------------------------------------------------
 // fused ciphertext-level paths
+
+// reLinearize for the register kernels: breakIntoDigits (src/DoubleCRT.cpp:479-561) without the two copy passes and without the
+// separate mixed-radix pointwise pass.  The switched part c2 is updated in place (the ABI says it is consumed): digit i's own rows
+// ARE c2's rows at the time digit i is reached, the digit polynomials only receive the base-extended rows, and the forward blk phase
+// of digit i's extension applies  c2 <- (c2 - E_i) * Q_i^-1  on the rows of the later digits in its epilogue.  Values handed from
+// kernel to kernel stay lazy; the inner product (src/Ctxt.cpp:191-230, with the addPrimesAndScale of src/Ctxt.cpp:764-768 folded in)
+// reduces exactly.  Everything runs chunk by chunk so that a chunk's scratch is re-read while still in L2.
+static int relin_fused_v1(hb_ctx* c, hb_poly* const* c0, hb_poly* const* c1, hb_poly* const* c2, int nitems, const int32_t* S, int nS,
+                          const std::vector<int32_t>& Sp, hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk, const std::vector<hb_poly*>& dig) {
+  const int maxdig = c->ndigits;
+  for (int i = 0; i < nS; i++) if (c->digit_of[S[i]] < 0) return hb_fail(HB_ERR_INDEX_SET, "breakIntoDigits: index set must be a subset of ctxt primes (prime %d)", S[i]);
+  std::vector<char> rem(c->nprimes, 0); int left = nS, nd = 0;
+  for (int i = 0; i < nS; i++) rem[S[i]] = 1;
+  for (; left > 0; nd++) for (int i = 0; i < c->nprimes; i++) if (rem[i] && c->digit_of[i] == nd) { rem[i] = 0; left--; }
+  if (nd > c->ndigits) return hb_fail(HB_ERR_BAD_ARG, "breakIntoDigits: n cannot be larger than the size of context.digits");
+  if (nd > ndig_evk) return hb_fail(HB_ERR_BAD_ARG, "hb_relinearize: key-switching matrix has %d columns, need %d", ndig_evk, nd);
+  if (nd > 4) return hb_fail(HB_ERR_UNSUPPORTED, "hb_relinearize: more than 4 digits");
+  hb_ctx* c2x = c; HB_TRY(check_polys(evk_a, nd, &c2x, "hb_relinearize(evk_a)")); HB_TRY(check_polys(evk_b, nd, &c2x, "hb_relinearize(evk_b)"));
+  std::vector<std::vector<int32_t>> dset(nd), notin(nd), full(nd);
+  for (int i = 0; i < nd; i++) {
+    for (int j = 0; j < nS; j++) if (c->digit_of[S[j]] == i) dset[i].push_back(S[j]);
+    for (int a : Sp) if (std::find(dset[i].begin(), dset[i].end(), a) == dset[i].end()) notin[i].push_back(a);
+    for (int k = 0; k < c->nprimes; k++) if (c->digit_of[k] == i) full[i].push_back(k);
+  }
+  // per digit: epilogue scalars on the rows of notin[i]: Q_i^-1 mod q_r for rows of later digits, 0 elsewhere
+  std::vector<std::vector<u64>> esc(nd);
+  for (int i = 0; i < nd; i++) {
+    esc[i].assign(notin[i].size(), 0);
+    for (size_t r = 0; r < notin[i].size(); r++) {
+      const int dj = c->digit_of[notin[i][r]];
+      if (dj > i && dj < nd) {
+        u64 inv; if (!h_invmod(prod_mod(c, full[i].data(), (int)full[i].size(), c->q[notin[i][r]]), c->q[notin[i][r]], &inv)) return hb_fail(HB_ERR_BAD_ARG, "digit product not invertible");
+        esc[i][r] = inv;
+      }
+    }
+  }
+  std::vector<u64> sc(Sp.size(), 0);
+  std::vector<int> own_dig(Sp.size(), -1);
+  for (size_t r = 0; r < Sp.size(); r++)
+    if (std::find(S, S + nS, Sp[r]) != S + nS) { sc[r] = prod_mod(c, c->special.data(), (int)c->special.size(), c->q[Sp[r]]); own_dig[r] = c->digit_of[Sp[r]]; }
+  HB_TRY(ctx_scratch(c));
+  return for_items(nitems, [&](int i0, int nit) {
+    u64* R[HB_MAXB]; u64* tB[HB_MAXB]; u64* D[HB_MAXB];
+    ptrs_of(c2, i0, nit, R); tmp_ptrs(c, c->tmpB, nit, tB);
+    for (int i = 0; i < nd; i++) {
+      for (int it = 0; it < nit; it++) D[it] = dig[(size_t)(i0 + it) * maxdig + i]->d;
+      HB_TRY(conv_chunk(c, R, nit, dset[i].data(), (int)dset[i].size(), notin[i].data(), (int)notin[i].size(), 1));
+      HB_TRY(launch_blk(c, +1, (const u64* const*)tB, D, nit, notin[i].data(), (int)notin[i].size(), 3, esc[i].data(), 1, R));
+    }
+    const int saved = g_chunk; g_chunk = HB_MAXB;   // already inside a chunk: one inner-product launch for it
+    int rc = keyswitch_digits_impl(dig.data() + (size_t)i0 * maxdig, maxdig, nd, nit, Sp.data(), (int)Sp.size(), evk_a, evk_b, c0 + i0, c1 + i0, sc.data(), 0, nullptr, c2 + i0, own_dig.data());
+    g_chunk = saved;
+    return rc;
+  });
+}
+
 extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* const* c2, int nitems,
                               const int32_t* S, int nS, hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk) {
   hb_ctx* c = nullptr;
@@ -1741,6 +1819,8 @@ extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* c
   const int maxdig = c->ndigits;
   std::vector<hb_poly*> dig; HB_TRY(pool_get(c, nitems * maxdig, dig));
   std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
+  if (v1_blk_ok(c) && v1_cols_ok(c) && !c->gen.on && !getenv("HB_NO_FUSED_RELIN"))
+    return relin_fused_v1(c, c0, c1, c2, nitems, S, nS, Sp, evk_a, evk_b, ndig_evk, dig);
   // keySwitchPart (src/Ctxt.cpp:805-842)
   int nd = 0;
   HB_TRY(hb_break_into_digits(c2, nitems, S, nS, dig.data(), maxdig, &nd));
@@ -1762,7 +1842,7 @@ extern "C" int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_p
   // bringToSet(common) on both operands: modDownToSet -> scaleDownToSet per part (src/Ctxt.cpp:393-562)
   std::vector<hb_poly*> allp;
   for (int i = 0; i < nitems; i++) { allp.push_back(a0[i]); allp.push_back(a1[i]); allp.push_back(b0[i]); allp.push_back(b1[i]); }
-  HB_TRY(hb_scale_down(allp.data(), (int)allp.size(), S_in, nS_in, S, nS, ptxt_space));
+  HB_TRY(scale_down_impl(allp.data(), (int)allp.size(), S_in, nS_in, S, nS, ptxt_space, nullptr, c->gen.on ? 0 : 1));   // lazy rows: the tensor product reduces exactly
   // tensorProduct in place: (a0,a1,b0) <- (a0*b0, a0*b1+a1*b0, a1*b1)   (src/Ctxt.cpp:1563-1608)
   HB_TRY(hb_tensor(a0, a1, b0, b1, a0, a1, b0, nitems, S, nS));
   // reLinearize (src/Ctxt.cpp:720-786)

@@ -395,6 +395,20 @@ def negacyclic_mul_schoolbook(f, g, mod=None):
 # ---------------------------------------------------------------------------
 
 
+def _row_fwd(chain, psis, poly, i):
+    """Cmodulus::FFT: negacyclic transform for power-of-two m (psis[i] = the 2N-th root), Bluestein rows over Z_m^* for
+    general m (psis[i] = the root of Cmodulus, cmod_root)."""
+    q = chain.primes[i]
+    if chain.pow2:
+        return ntt_fwd(poly, q, psis[i])
+    return gen_fft([int(c) % q for c in poly], q, chain.m, psis[i])
+
+
+def _row_inv(chain, psis, row, i):
+    q = chain.primes[i]
+    return ntt_inv(row, q, psis[i]) if chain.pow2 else gen_ifft(row, q, chain.m, psis[i])
+
+
 class PyDCRT:
     """A DoubleCRT: dict prime-index -> list of N residues (evaluation form)."""
 
@@ -415,7 +429,7 @@ class PyDCRT:
         src/CModulus.cpp:453-457: coefficients reduced into [0,q) first)."""
         n = chain.phim
         poly = list(poly) + [0] * (n - len(poly))
-        return cls(chain, psis, {i: ntt_fwd(poly, chain.primes[i], psis[i]) for i in idxs})
+        return cls(chain, psis, {i: _row_fwd(chain, psis, poly, i) for i in idxs})
 
     def to_poly(self, idxs=None, positive=False):
         """DoubleCRT::toPoly (src/DoubleCRT.cpp:925-1113)."""
@@ -424,7 +438,7 @@ class PyDCRT:
         if not s1:
             return [0] * n
         Q = self.ch.product(s1)
-        coefs = {i: ntt_inv(self.rows[i], self.ch.primes[i], self.psis[i]) for i in s1}
+        coefs = {i: _row_inv(self.ch, self.psis, self.rows[i], i) for i in s1}
         out = []
         for k in range(n):
             acc = 0
@@ -481,7 +495,7 @@ class PyDCRT:
         assert not (set(idxs) & set(self.rows))
         poly = self.to_poly()
         for i in idxs:
-            self.rows[i] = ntt_fwd(poly, self.ch.primes[i], self.psis[i])
+            self.rows[i] = _row_fwd(self.ch, self.psis, poly, i)
         return poly
 
     def add_primes_and_scale(self, idxs):
@@ -548,7 +562,15 @@ class PyDCRT:
         """DoubleCRT::automorph, power-of-two m (src/DoubleCRT.cpp:1160-1202):
         new[j] = old[idx(rep(j)*k mod m)], rep(j) = 2j+1."""
         m = self.ch.m
-        assert self.ch.pow2 and k % 2 == 1
+        if not self.ch.pow2:   # general m: rep(j) = j-th unit of Z_m^* ascending (src/PAlgebra.cpp:535-540)
+            rep = zms_rep(m)
+            pos = {r: j for j, r in enumerate(rep)}
+            assert math.gcd(k, m) == 1
+            for i in self.rows:
+                old = self.rows[i]
+                self.rows[i] = [old[pos[rep[j] * k % m]] for j in range(len(old))]
+            return self
+        assert k % 2 == 1
         for i in self.rows:
             old = self.rows[i]
             self.rows[i] = [old[(((2 * j + 1) * k) % m - 1) // 2] for j in range(len(old))]

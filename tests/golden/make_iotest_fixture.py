@@ -61,6 +61,13 @@ def main():
             "pk_c0": rows_of(parts[0][0]), "pk_c0_handle": parts[0][1],
             "pk_c1": rows_of(parts[1][0]), "pk_c1_handle": parts[1][1],
             "secret_key": rows_of(blocks[-1]),
+            # chain layout of the legacy context record: stdev, special primes, #primes, primes, #digits, digits
+            "digits": [d for d in ctx[3 + nprimes + 1:3 + nprimes + 1 + ctx[3 + nprimes]]],
+            # key-switching matrices W[s^r(X^t) -> s]: [[r, t, fromID], toID, ptxtSpace, n, b_0 .. b_{n-1}, prgSeed]
+            # (KeySwitch::writeTo, src/keySwitching.cpp): the b_i rows as written by real HElib, the 256-bit seed of the a_i as a decimal string
+            "ksw": [{"from": mt[0], "to": mt[1], "ptxt_space": mt[2], "n": mt[3],
+                     "b": [rows_of(mt[4 + d]) for d in range(mt[3])], "prg_seed": str(mt[4 + mt[3]])}
+                    for mt in tree[2][4:4 + tree[2][3]]],
         })
     # the binary twin of the LE file holds the same key; its first ciphertext part is a DoubleCRT::writeTo record
     # (IndexSet, then per row int32 length, int32 intSize, little-endian int64 values) written by the real library

@@ -254,6 +254,33 @@ def test_sim_full_ring_dimension_small_chain(sim_lib):
     assert rows_equal(A0[0].download(S), r0, S) and rows_equal(A1[0].download(S), r1, S)
 
 
+@pytest.mark.parametrize("cfg", [(1 << 17, 257, 1, 230, 3), (1 << 17, -1, 1, 330, 3)])
+def test_fused_relinearize_three_digits(lib, cfg):
+    """hb_relinearize on the register kernels runs breakIntoDigits fused (the switched part is updated in place, the
+    mixed-radix step rides in the forward blk epilogue, the inner product reads a digit's own rows from the part):
+    three digits exercise the chained update c2 <- (c2 - E_i)/Q_i over two steps; two items at once; a lower level
+    (one ctxt prime dropped) changes the digit sets.  Bit-exact vs the oracle's reLinearize + mod-down."""
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    p = ptxt_space(ch)
+    rng = np.random.default_rng(77)
+    full = ch.ctxt + ch.special
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    for S in (ch.ctxt, ch.ctxt[:-1]):
+        Sp = sorted(S + ch.special)
+        cs = [[O.random(rng, S) for _ in range(3)] for _ in range(2)]
+        C0, C1, C2 = ([E.poly(c[k], S) for c in cs] for k in range(3))
+        E.relinearize(C0, C1, C2, S, EA, EB)
+        E.scale_down(C0 + C1, Sp, S, p)
+        for it, c in enumerate(cs):
+            r0, r1 = O.relinearize(c[0], c[1], c[2], S, evk_a, evk_b)
+            O.scale_down(r0, Sp, S, p); O.scale_down(r1, Sp, S, p)
+            assert rows_equal(C0[it].download(S), r0, S) and rows_equal(C1[it].download(S), r1, S), (len(S), it)
+
+
 def test_sim_generic_modulus_path(sim_lib, monkeypatch):
     """The register kernels have two modulus views: HElib's q = t*2^s+1 (s >= 32) shift form and the
     generic 2^64-q form.  Force the generic one (HB_NO_SPECIAL) on the N = 2^16 circuit."""
@@ -352,13 +379,13 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
         assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
 
 
-def test_single_source_conversion_kernel_opt_in(sim_lib, monkeypatch):
-    """(Simulator only while the kernel is opt-in: it has not run on a GPU yet.)  HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
+def test_single_source_conversion_kernel(lib, monkeypatch):
+    """HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
     kernel k1_conv1; results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
     prime, and (different bit lengths between source and targets) with rows at the extremes."""
     monkeypatch.setenv("HB_CONV1", "1")
     cfg = (1 << 17, -1, 1, 230, 2)
-    ch, psis, O, E = make(sim_lib, *cfg, nthreads=8)
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
     rng = np.random.default_rng(21)
     E.reset_stats() if hasattr(E, "reset_stats") else None
     cases = [(ch.ctxt, ch.ctxt[:-1]), (ch.ctxt + ch.special[:1], ch.ctxt)]

@@ -227,3 +227,145 @@ def test_oracle_general_m_conventions_pinned_by_reference_fixture():
             assert all(c % p == 0 and abs(c) < 200 * p for c in coef), (i, coef)      # RLWE1: c0 + c1*s = p*e, e ~ 3.2*sqrt(m)
             assert noise is None or coef == noise
             noise = coef
+
+
+# ---------------------------------------------------------------------------------------------
+# Pinning on key-switching matrices written by a real HElib build (reference fixture, m = 12).
+
+def _iotest_cases():
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "helib_iotest_m12.json")))
+    return G["cases"]
+
+
+def _fixture_chain(case):
+    m, primes = case["m"], case["primes"]
+    special = case["special"]
+    ctxt = [i for i in range(len(primes)) if i not in special]
+    ch = po.Chain(m=m, p=case["p"], r=case["r"], phim=po.euler_phi(m), primes=list(primes), small=[], ctxt=ctxt, special=list(special),
+                  digits=[list(d) for d in case["digits"]])
+    roots = [po.cmod_root(q, m) for q in primes]
+    return ch, roots
+
+
+def _regenerate_a(case, ch, W):
+    """The a_i of a key-switching matrix: SetSeed(prgSeed), then a[i].randomize() for i = 0..n-1 over ctxt|special primes
+    (src/keys.cpp:1199-1204, src/DoubleCRT.cpp:1258-1378) through the restated NTL stream."""
+    import ntl_prg
+    st = ntl_prg.set_seed(int(W["prg_seed"]))
+    full = sorted(ch.ctxt + ch.special)
+    return [po.randomize_rows(ch, full, st.get) for _ in range(W["n"])]
+
+
+def test_ntl_stream_randomize_and_keyswitch_matrix_pinned_by_reference_fixture():
+    """SURVEY 8a rows 14 and 20.  The reference's I/O fixtures store four key-switching matrices W[s^r(X^t) -> s] with the b_i rows
+    a real HElib wrote and the 256-bit prgSeed of their a_i.  Regenerating a_i with the oracle's restatement of NTL's stream
+    (HMAC-SHA256 key derivation + ChaCha20) and of DoubleCRT::randomize, then removing P*prod_{j<i}Q_j*s^r(X^t) and a_i*s,
+    must leave ONE small multiple of p on every prime -- a single wrong byte of the stream, a different consumption pattern, a
+    different automorphism index map or scaling factor leaves uniform noise instead."""
+    for case in _iotest_cases():
+        ch, roots = _fixture_chain(case)
+        m, p = ch.m, ch.p
+        rep = po.zms_rep(m)
+        pos = {r: j for j, r in enumerate(rep)}
+        P = ch.product(ch.special)
+        sk = {int(i): row for i, row in case["secret_key"].items()}
+        assert len(case["ksw"]) == 4
+        for W in case["ksw"]:
+            (spow, xpow, from_id), to_id = W["from"], W["to"]
+            assert (from_id, to_id, W["ptxt_space"], W["n"]) == (0, 0, p, len(ch.digits))
+            a = _regenerate_a(case, ch, W)
+            for d in range(W["n"]):
+                noise = None
+                for i, q in enumerate(ch.primes):
+                    s_from = [sk[i][pos[rep[j] * xpow % m]] for j in range(ch.phim)]          # s(X^t): DoubleCRT::automorph
+                    s_from = [pow(x, spow, q) for x in s_from]                                # s^r(X^t): DoubleCRT::Exp
+                    fac = P * ch.product([k for j in range(d) for k in ch.digits[j]]) % q    # src/keys.cpp:1239-1242
+                    b = W["b"][d][str(i)]
+                    rr = [(bb + aa * s - fac * sf) % q for bb, aa, s, sf in zip(b, a[d][i], sk[i], s_from)]
+                    coef = [po.bal(c, q) for c in po.gen_ifft(rr, q, m, roots[i])]
+                    assert all(c % p == 0 and abs(c) < 200 * p for c in coef), (W["from"], d, i, coef)
+                    assert noise is None or coef == noise
+                    noise = coef
+                assert any(noise)
+
+
+def test_keyswitch_path_semantics_pinned_by_reference_evk():
+    """SURVEY 8a rows 7, 10, 11, 13, 18.  Key-switch with matrices produced by real HElib: a ciphertext of the fixture's key
+    (its public encryption key + a plaintext) is squared (tensorProduct), relinearised with the fixture's W[s^2 -> s] through the
+    oracle's breakIntoDigits / keySwitchDigits / addPrimesAndScale / scaleDownToSet, and rotated with W[s(X^5) -> s]; decrypting
+    with the fixture's secret key (toPoly, balanced) must give mu^2 and mu(X^5).  The oracle's digit decomposition, its factors
+    P*prod Q_j, the mod-down rounding and the balanced CRT must therefore be the ones the reference's matrices encode."""
+    case = _iotest_cases()[0]
+    ch, roots = _fixture_chain(case)
+    m, p, n = ch.m, ch.p, ch.phim
+    S = list(case["pk_prime_set"])
+    assert S == ch.ctxt
+    sk = po.PyDCRT(ch, roots, {int(i): list(r) for i, r in case["secret_key"].items()})
+    phi = po.cyclotomic_poly(m)
+
+    def polymul_mod_phi(f, g):
+        out = [0] * (2 * n)
+        for i, a in enumerate(f):
+            for j, b in enumerate(g):
+                out[i + j] += a * b
+        return [c % p for c in po._poly_rem(out, phi)[:n]] if hasattr(po, "_poly_rem") else None
+
+    def decrypt(c0, c1, idxs):
+        s = po.PyDCRT(ch, roots, {i: sk.rows[i] for i in idxs})
+        t = po.PyDCRT(ch, roots, {i: list(c1.rows[i]) for i in idxs}).mul(s)
+        t.add(po.PyDCRT(ch, roots, {i: list(c0.rows[i]) for i in idxs}))
+        return [c % p for c in t.to_poly()]
+
+    mu = [3, 1, 0, 5]
+    c0 = po.PyDCRT(ch, roots, {int(i): list(r) for i, r in case["pk_c0"].items()})
+    c1 = po.PyDCRT(ch, roots, {int(i): list(r) for i, r in case["pk_c1"].items()})
+    c0.add(po.PyDCRT.from_poly(ch, roots, mu, S))
+    assert decrypt(c0, c1, S) == mu
+
+    def evk(spow, xpow):
+        W = [w for w in case["ksw"] if w["from"][:2] == [spow, xpow]][0]
+        a = _regenerate_a(case, ch, W)
+        A = [po.PyDCRT(ch, roots, a[d]) for d in range(W["n"])]
+        B = [po.PyDCRT(ch, roots, {int(i): list(r) for i, r in W["b"][d].items()}) for d in range(W["n"])]
+        return A, B
+
+    # --- square + relinearise (src/Ctxt.cpp:1563-1608, 720-786) + drop the special primes (src/Ctxt.cpp:589-593)
+    d0 = c0.copy().mul(c0)
+    d1 = c0.copy().mul(c1); d1.add(d1.copy())
+    d2 = c1.copy().mul(c1)
+    A, B = evk(2, 1)
+    digits, _ = d2.break_into_digits()
+    k0, k1 = po.key_switch_digits(digits, A, B)
+    r0 = d0.copy().add_primes_and_scale(ch.special).add(k0)
+    r1 = d1.copy().add_primes_and_scale(ch.special).add(k1)
+    r0.scale_down_to_set(S, p); r1.scale_down_to_set(S, p)
+    mu2 = [0] * (2 * n)
+    for i, a_ in enumerate(mu):
+        for j, b_ in enumerate(mu):
+            mu2[i + j] += a_ * b_
+    for k in range(2 * n - 1, n - 1, -1):      # reduce modulo Phi_12 = X^4 - X^2 + 1
+        ck = mu2[k]
+        for j, pj in enumerate(phi):
+            mu2[k - (len(phi) - 1) + j] -= ck * pj
+    assert decrypt(r0, r1, S) == [c % p for c in mu2[:n]]
+
+    # --- rotate: sigma_5 on both parts, then switch the s(X^5) part back to s (src/Ctxt.cpp:2437-2515)
+    a0, a1 = c0.copy().automorph(5), c1.copy().automorph(5)
+    A, B = evk(1, 5)
+    digits, _ = a1.break_into_digits()
+    k0, k1 = po.key_switch_digits(digits, A, B)
+    r0 = a0.copy().add_primes_and_scale(ch.special).add(k0)
+    r1 = k1
+    r0.scale_down_to_set(S, p); r1.scale_down_to_set(S, p)
+    mu5 = [0] * (5 * n)
+    for i, a_ in enumerate(mu):
+        mu5[5 * i] += a_
+    for k in range(len(mu5) - 1, n - 1, -1):
+        ck = mu5[k]
+        if ck:
+            for j, pj in enumerate(phi):
+                mu5[k - (len(phi) - 1) + j] -= ck * pj
+            mu5[k] = 0
+    assert decrypt(r0, r1, S) == [c % p for c in mu5[:n]]
