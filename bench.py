@@ -84,6 +84,245 @@ class ClockSampler:
         return out
 
 
+def mult_config(B):
+    """The workload both arms are run on (identical dict in `config` of the GPU arm and of --impl reference)."""
+    l_in, l, K, d = 20, 19, 10, 2
+    return {"workload": WORKLOAD["name"], "N": 1 << 16, "l_in": l_in, "l": l, "K": K, "digits": d, "batch_per_gpu": B,
+            "sharding": "independent ciphertexts per rank, no data-path collective",
+            "l2": f"inputs larger than L2 ({B * 4 * l_in * ROW_BYTES / 2**20:.0f} MiB of operands per step)",
+            "operands": "updated in place: from step 2 on a step's inputs are the previous step's outputs (the path is data-oblivious)",
+            "alg_bytes_per_mult": alg_bytes_per_mult(l_in, l, K, d)}
+
+
+def cpu_layout(cores):
+    """Concurrent multiplies x threads per multiply: the reference threads one multiply across primes / coefficients
+    (NTL_EXEC_RANGE, src/DoubleCRT.cpp:79-84), which cannot occupy a many-core host (<= 30 rows); independent
+    ciphertexts on independent thread groups is how a caller fills the box."""
+    per = 8 if cores >= 16 else max(1, cores)
+    workers = max(1, cores // per)
+    return workers, per
+
+
+KS_WORKLOADS = {
+    # BASELINE.json configs[2]: BGV m=2^17 p=257 bits=1500 c=3 -- reLinearize/key-switch batch of 1024 ctxts, 1xB200
+    "cfg3": {"name": "bgv_m2^17_p257_bits1500_c3", "m": 1 << 17, "p": 257, "r": 1, "bits": 1500, "c": 3, "shape": (26, 9, 3)},
+    # BASELINE.json configs[3]: CKKS N=2^16 L=44 -- prime-sharded key-switch at 1/2/4/8 GPUs over NVLink
+    "cfg4": {"name": "ckks_m2^17_bits1700_c2", "m": 1 << 17, "p": -1, "r": 1, "bits": 1700, "c": 2, "shape": (29, 15, 2)},
+}
+
+
+def alg_bytes_per_keyswitch(l, K, d):
+    """B_ks = 8N*[3l + 2d(l+K) + 2l] (3-part in, evk, 2-part out incl. the mod-down)."""
+    return ROW_BYTES * (3 * l + 2 * d * (l + K) + 2 * l)
+
+
+def bench_keyswitch_block(args, np, torch, dist, local, rank, world, peak):
+    """BASELINE config 3: `--ks-count` independent 3-part BGV ciphertexts (p = 257: the ptxtSpace correction of
+    scaleDownToSet is active) resident in HBM; one step = reLinearize + modDownToSet of every one of them
+    (hb_relinearize + hb_scale_down in groups of --ks-group).  Independent ciphertexts per rank, no collective."""
+    from helib_b200 import Chain, Engine
+    wl = KS_WORKLOADS["cfg3"]
+    ch = Chain(wl["m"], wl["p"], wl["r"], wl["bits"], wl["c"])
+    assert (len(ch.ctxt), len(ch.special), len(ch.digits)) == wl["shape"], "chain shape differs from SURVEY section 8"
+    E = Engine(wl["m"], ch.primes, None, ch.digits, ch.special, device=local)
+    N, npr = E.N, E.np
+    S, full, nd, p = ch.ctxt, ch.ctxt + ch.special, len(ch.digits), ch.p ** ch.r
+    Sp = sorted(S + ch.special)
+    rng = np.random.Generator(np.random.Philox(20260922 + 3 + 1000 * rank))
+
+    def rand_dense(idx):
+        out = np.zeros((npr, N), dtype=np.uint64)
+        for i in idx:
+            out[i] = rng.integers(0, ch.primes[i], size=N, dtype=np.uint64)
+        return out
+
+    EA = [E.poly(rand_dense(full), full) for _ in range(nd)]
+    EB = [E.poly(rand_dense(full), full) for _ in range(nd)]
+    count, grp = args.ks_count, min(args.ks_group, args.ks_count)
+    nuniq = min(8, count)
+    C = [[E.poly(rand_dense(S), S) if b < nuniq else E.poly() for _ in range(3)] for b in range(count)]
+    for b0 in range(nuniq, count, nuniq):     # the remaining ciphertexts are device-side copies of the unique ones
+        nb = min(nuniq, count - b0)
+        for k in range(3):
+            E.pointwise("copy", [C[b0 + j][k] for j in range(nb)], [C[j][k] for j in range(nb)], S)
+    groups = [([c[0] for c in C[g:g + grp]], [c[1] for c in C[g:g + grp]], [c[2] for c in C[g:g + grp]]) for g in range(0, count, grp)]
+
+    def step():
+        for c0, c1, c2 in groups:
+            E.relinearize(c0, c1, c2, S, EA, EB)
+            E.scale_down(c0 + c1, Sp, S, p)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, args.ks_steps))
+    for _ in range(3):
+        step()
+    E.reset_stats()
+    barrier()
+    E.mark_begin()
+    for _ in range(steps):
+        step()
+    ms = E.mark_end()
+    barrier()
+    st = E.stats()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    E.profile(True)
+    c0, c1, c2 = groups[0]
+    E.relinearize(c0, c1, c2, S, EA, EB)
+    E.scale_down(c0 + c1, Sp, S, p)
+    E.profile(False)
+    prof = sorted(E.profile_results(), key=lambda r: -r["ms"])
+    tot = sum(r["ms"] for r in prof) or 1.0
+    l, K = len(S), len(ch.special)
+    bks = alg_bytes_per_keyswitch(l, K, nd)
+    v = world * count * steps / (ms / 1000.0)
+    top = prof[0] if prof else None
+    out = {
+        "metric": "key_switches_per_s", "value": v, "unit": "keyswitch/s", "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+        "config": {"workload": wl["name"], "N": N, "l": l, "K": K, "digits": nd, "ptxt_space": p, "ciphertexts_per_gpu": count, "group": grp,
+                   "resident_bytes": count * 3 * l * ROW_BYTES, "alg_bytes_per_keyswitch": bks, "alg_bytes_per_keyswitch_without_evk": bks - 2 * nd * (l + K) * ROW_BYTES,
+                   "sharding": "independent ciphertexts per rank, no data-path collective"},
+        "alg_roofline": {"achieved_GBps": v / world * bks / 1e9, "peak_GBps": peak, "frac": v / world * bks / 1e9 / peak},
+        "roofline": None if top is None else {"bound": "hbm", "kernel": top["kernel"], "achieved": top["bytes"] / (top["ms"] / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": top["bytes"] / (top["ms"] / 1000.0) / 1e9 / peak, "share_of_step": top["ms"] / tot, "traffic": None},
+        "gpu_launches": st["launches"], "exact_crt_fallbacks": st["exact_fallbacks"],
+        "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot, 4)} for r in prof],
+    }
+    del groups, C, EA, EB, c0, c1, c2
+    import gc
+    gc.collect()          # polys are freed by their finalisers (before the context goes away)
+    E.close()
+    return out
+
+
+def bench_sharded_block(args, np, torch, dist, local, rank, world, peak):
+    """BASELINE config 4: ONE stream of ciphertexts, every ciphertext's rows sharded by RNS prime index over the ranks
+    (helib_b200/sharded.py): key-switches/s (strong scaling), exchange bytes, and a bit-exact check of the rows each rank
+    owns against the unsharded engine path run on the same inputs inside this process."""
+    from helib_b200 import Chain, Engine
+    from helib_b200.sharded import ShardedKeySwitch
+    wl = KS_WORKLOADS["cfg4"]
+    ch = Chain(wl["m"], wl["p"], wl["r"], wl["bits"], wl["c"])
+    assert (len(ch.ctxt), len(ch.special), len(ch.digits)) == wl["shape"], "chain shape differs from SURVEY section 8"
+    E = Engine(wl["m"], ch.primes, None, ch.digits, ch.special, device=local)
+    side = torch.cuda.Stream()            # engine kernels, torch index ops and NCCL all run ordered on this stream
+    prev = torch.cuda.current_stream()
+    torch.cuda.set_stream(side)
+    E.set_stream(side.cuda_stream)
+    N, npr, B = E.N, E.np, args.sharded_batch
+    S, full, nd = ch.ctxt, ch.ctxt + ch.special, len(ch.digits)
+    rng = np.random.Generator(np.random.Philox(20260922 + 4))      # the same data on every rank
+
+    def rand_dense(idx):
+        out = np.zeros((npr, N), dtype=np.uint64)
+        for i in idx:
+            out[i] = rng.integers(0, ch.primes[i], size=N, dtype=np.uint64)
+        return out
+
+    evk = [rand_dense(full) for _ in range(2 * nd)]
+    nuniq = min(4, B)
+    cts = [[rand_dense(S) for _ in range(3)] for _ in range(nuniq)]
+    res = {}
+    for mode in (["p2p", "gather"] if world > 1 else ["local"]):
+        KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, rank=rank, world=world, device=f"cuda:{local}", p2p=(mode == "p2p"))
+        own_full, oS = KS.owned(full), KS.owned(S)
+        EA = [E.poly(evk[i], own_full) for i in range(nd)]
+        EB = [E.poly(evk[nd + i], own_full) for i in range(nd)]
+        C = [[E.poly(cts[b % nuniq][k], oS) for k in range(3)] for b in range(B)]
+        digs = [[E.poly() for _ in range(nd)] for _ in range(B)]
+        C0, C1, C2 = ([c[k] for c in C] for k in range(3))
+
+        def step():
+            Sp_ = KS.relinearize(C0, C1, C2, S, EA, EB, digs)
+            KS.mod_down(C0 + C1, Sp_, S, 1)
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- parity inside the run: rows this rank owns == the unsharded engine path on the same inputs
+        step()
+        torch.cuda.synchronize()
+        got = [(C0[b].download(oS), C1[b].download(oS)) for b in range(nuniq)]
+        FA = [E.poly(evk[i], full) for i in range(nd)]
+        FB = [E.poly(evk[nd + i], full) for i in range(nd)]
+        ok = True
+        for b in range(nuniq):
+            f0, f1, f2 = (E.poly(cts[b][k], S) for k in range(3))
+            E.relinearize([f0], [f1], [f2], S, FA, FB)
+            E.scale_down([f0, f1], sorted(S + ch.special), S, 1)
+            r0, r1 = f0.download(oS), f1.download(oS)
+            ok = ok and bool((got[b][0][oS] == r0[oS]).all() and (got[b][1][oS] == r1[oS]).all())
+        del FA, FB
+        if world > 1:
+            t = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(t.item())
+        for _ in range(3):
+            step()
+        E.reset_stats()
+        step()
+        launches_per_step = E.stats()["launches"]
+        barrier()
+        run, graphed = step, False
+        try:     # ~30 launches + the exchange steps per pass: replay them as one CUDA graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                step()
+            run, graphed = g.replay, True
+            for _ in range(2):
+                run()
+        except Exception as ex:
+            if rank == 0:
+                print(f"[bench] sharded key switch: CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+        barrier()
+        steps = max(1, min(args.steps, args.ks_steps * 4))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        E.profile(True)
+        step()
+        E.profile(False)
+        prof = sorted(E.profile_results(), key=lambda r: -r["ms"])
+        l, K = len(S), len(ch.special)
+        bks = alg_bytes_per_keyswitch(l, K, nd)
+        v = B * steps / (ms / 1000.0)
+        res[mode] = {
+            "value": v, "unit": "keyswitch/s", "ms_per_step": ms / steps, "steps": steps, "cuda_graph": graphed, "bit_exact_vs_unsharded": ok,
+            "gpu_launches_per_step": launches_per_step,
+            "exchange_bytes_per_keyswitch": (l + 2 * K) * ROW_BYTES if world > 1 else 0, "exchanges_per_step": (nd + 1) if world > 1 else 0,
+            "alg_roofline_frac": v * bks / 1e9 / (peak * world),
+            "phase_ms": [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4)} for r in prof],
+            "engine_kernel_ms_per_step": round(sum(r["ms"] for r in prof), 4),
+        }
+        del C, digs, EA, EB, KS
+    torch.cuda.set_stream(prev)
+    best = max(res.values(), key=lambda r: r["value"])
+    l, K = len(S), len(ch.special)
+    out = {"metric": "key_switches_per_s", "value": best["value"], "unit": "keyswitch/s", "scaling": "strong", "n_gpus": world,
+           "config": {"workload": wl["name"], "N": N, "l": l, "K": K, "digits": nd, "batch": B, "sharding": "rows by RNS prime index, round-robin within ctxt / special primes; evk sharded identically",
+                      "alg_bytes_per_keyswitch": alg_bytes_per_keyswitch(l, K, nd)},
+           "bit_exact_vs_unsharded": all(r["bit_exact_vs_unsharded"] for r in res.values()), "modes": res}
+    return out
+
+
 def oracle_setup(nthreads):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -117,15 +356,30 @@ def oracle_one_mult(ch, O, evk_a, evk_b, ops):
     return r0, r1
 
 
-def time_oracle(steps, warmup, nthreads):
-    ch, O, evk_a, evk_b, ops = oracle_setup(nthreads)
+def time_oracle(steps, warmup, cores):
+    """`steps` rounds of `workers` concurrent multiplies (one oracle context and thread group each; ctypes releases the GIL).
+    Returns (multiplies/s, seconds, multiplies timed, workers, threads per multiply)."""
+    import threading
+    workers, per = cpu_layout(cores)
+    ch, O, evk_a, evk_b, ops = oracle_setup(per)
+    import orc
+    Os = [O] + [orc.Oracle(ch.phim, ch.m, O.primes, O.psis, ch.digits, ch.special, nthreads=per) for _ in range(workers - 1)]
+
+    def round_():
+        th = [threading.Thread(target=oracle_one_mult, args=(ch, o, evk_a, evk_b, ops)) for o in Os[1:]]
+        for t_ in th:
+            t_.start()
+        oracle_one_mult(ch, Os[0], evk_a, evk_b, ops)
+        for t_ in th:
+            t_.join()
+
     for _ in range(warmup):
-        oracle_one_mult(ch, O, evk_a, evk_b, ops)
+        round_()
     t = time.perf_counter()
     for _ in range(steps):
-        oracle_one_mult(ch, O, evk_a, evk_b, ops)
+        round_()
     dt = time.perf_counter() - t
-    return steps / dt, dt
+    return steps * workers / dt, dt, steps * workers, workers, per
 
 
 def run_reference(args):
@@ -135,15 +389,15 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    v, dt = time_oracle(args.steps, max(1, min(args.warmup, 2)), cores)
-    l_in, l, K, d = 20, 19, 10, 2
+    v, dt, nmul, workers, per = time_oracle(args.steps, min(args.warmup, 1), cores)
     line = {
         "impl": "reference", "metric": "ctxt_mults_per_s", "value": v, "unit": "mult/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"], "N": 1 << 16, "l_in": l_in, "l": l, "K": K, "digits": d, "batch": 1},
-        "cpu_baseline": {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} multiplies (1 per step), C++ oracle restating NTL-path HElib, threads across primes/coefficients"},
+        "config": mult_config(args.batch),
+        "cpu_baseline": {"value": v, "unit": "mult/s", "cores": workers * per, "kind": "port",
+                         "sample": f"each step = {workers} concurrent multiplies of the batch (bounded sample), {per} threads per multiply across primes/coefficients; "
+                                   f"{nmul} multiplies in {dt:.1f}s; C++ oracle restating NTL-path HElib (HElib itself is unbuildable here: NTL/GMP absent)"},
         "e2e": {"value": v, "unit": "mult/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -160,6 +414,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-streams", type=int, default=4, help="engine contexts (CUDA streams) the e2e loop spreads the batch over")
+    ap.add_argument("--no-ks", action="store_true", help="skip the key-switch blocks (BASELINE configs 3 and 4)")
+    ap.add_argument("--ks-count", type=int, default=1024, help="config 3: ciphertexts resident per GPU (one step switches all of them)")
+    ap.add_argument("--ks-group", type=int, default=64, help="config 3: ciphertexts per hb_relinearize / hb_scale_down call")
+    ap.add_argument("--ks-steps", type=int, default=3, help="config 3: timed passes over the resident ciphertexts (at most --steps)")
+    ap.add_argument("--sharded-batch", type=int, default=16, help="config 4: ciphertexts per step of the prime-sharded key switch")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -331,29 +590,50 @@ def main():
     kernels = [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot_ms, 4),
                 "alg_GBps": round(r["bytes"] / (r["ms"] / 1000.0) / 1e9, 1) if r["ms"] > 0 else None} for r in prof]
 
-    if rank != 0:
-        return
     l_in, l, K, d = len(S_in), len(S), len(ch.special), nd
+    st_mult = st
+    # ---- the key-switch blocks (BASELINE configs 3 and 4); every rank takes part.  The multiply block's ~8 GB stay allocated.
+    ks = sharded = None
+    if not args.no_ks:
+        import gc
+        gc.collect()
+        ks = bench_keyswitch_block(args, np, torch, dist if world > 1 else None, local, rank, world, peak)
+        gc.collect()
+        sharded = bench_sharded_block(args, np, torch, dist if world > 1 else None, local, rank, world, peak)
+    if rank != 0:
+        return _leave(world)
+    st = st_mult
     bmul = alg_bytes_per_mult(l_in, l, K, d)
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
-        v, dt = time_oracle(args.cpu_sample, 1, cores)
-        cpu = {"value": v, "unit": "mult/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} multiplies of the same workload (batch 1), C++ oracle restating NTL-path HElib, {cores} threads, {dt:.1f}s"}
+        workers, per = cpu_layout(cores)
+        v, dt, nmul, workers, per = time_oracle(max(1, args.cpu_sample // workers), 1, cores)
+        cpu = {"value": v, "unit": "mult/s", "cores": workers * per, "kind": "port",
+               "sample": f"{nmul} multiplies of the same workload ({workers} concurrent x {per} threads each), C++ oracle restating NTL-path HElib, {dt:.1f}s"}
     line = {
         "metric": "ctxt_mults_per_s", "value": value, "unit": "mult/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": w["name"], "N": N, "l_in": l_in, "l": l, "K": K, "digits": d, "batch_per_gpu": B,
-                   "sharding": "independent ciphertexts per rank, no data-path collective",
-                   "l2": f"inputs larger than L2 ({B * 4 * l_in * ROW_BYTES / 2**20:.0f} MiB of operands per step)",
-                   "alg_bytes_per_mult": bmul},
+        "config": mult_config(B),
         "alg_roofline": {"achieved_GBps": value / world * bmul / 1e9, "peak_GBps": peak, "frac": value / world * bmul / 1e9 / peak, "peak_kind": peak_kind},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
         "exact_crt_fallbacks": st["exact_fallbacks"],
+        "keyswitch": ks, "sharded_keyswitch": sharded,
     }
     print(json.dumps(line))
+    _leave(world)
+
+
+def _leave(world):
+    """Leave without tearing NCCL down: destroy_process_group() after a captured graph that contains collectives can block
+    for minutes; the results are already printed."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -77,7 +77,7 @@ struct hb_ctx {
   cudaEvent_t ev0, ev1;
   size_t max_smem;
   bool force_v0;     // HB_FORCE_V0=1: generic radix-2 kernels only (A/B testing)
-  bool conv1;        // HB_CONV1=1: dedicated single-source conversion kernel (opt-in until measured on the GPU)
+  bool conv1;        // dedicated single-source conversion kernel k1_conv1 (HB_CONV1=0 falls back to the general k1_conv)
   int chunk;         // batch items per launch (<= HB_MAXB; HB_CHUNK overrides): keeps the phase scratch L2-sized
   int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
   // general (non power-of-two) m: Bluestein state
@@ -181,7 +181,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->digit_of.assign(nprimes, -1);
   c->max_smem = 200 * 1024;
   { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
-  { const char* e = getenv("HB_CONV1"); c->conv1 = e && e[0] == '1'; }
+  { const char* e = getenv("HB_CONV1"); c->conv1 = !(e && e[0] == '0'); }
   { const char* e = getenv("HB_CHUNK"); int v = e ? atoi(e) : HB_MAXB; c->chunk = v >= 1 && v <= HB_MAXB ? v : HB_MAXB; }
   c->resident_ctas = 296;
 #ifdef HB_SIM

@@ -26,6 +26,14 @@ def main():
         lib = load_library(build_sim())
         dist.init_process_group("gloo")
         device = "cpu"
+    elif backend == "cuda1":
+        # world_size ranks sharing ONE GPU (the driver's 1-GPU box): real library, gloo for the plumbing
+        # (NCCL refuses two ranks on one device), CUDA-IPC peer mappings for the p2p stores.
+        lib = load_library()
+        local = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+        device = "cuda:0"
     else:
         lib = load_library()
         local = int(os.environ.get("LOCAL_RANK", rank))
@@ -35,7 +43,7 @@ def main():
     ch = po.build_mod_chain(*cfg)
     psis = [po.find_psi(q, ch.m) for q in ch.primes]
     O = orc.Oracle(ch.phim, ch.m, ch.primes, psis, ch.digits, ch.special, nthreads=4)
-    E = Engine(ch.m, ch.primes, psis, ch.digits, ch.special, device=0 if backend == "sim" else int(os.environ.get("LOCAL_RANK", rank)), lib=lib)
+    E = Engine(ch.m, ch.primes, psis, ch.digits, ch.special, device=0 if backend in ("sim", "cuda1") else int(os.environ.get("LOCAL_RANK", rank)), lib=lib)
     if backend != "sim":
         E.set_stream(torch.cuda.current_stream().cuda_stream)
     rng = np.random.default_rng(123)           # same data on every rank

@@ -380,8 +380,8 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
 
 
 def test_single_source_conversion_kernel(lib, monkeypatch):
-    """HB_CONV1=1 routes mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) through the dedicated
-    kernel k1_conv1; results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
+    """Mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) run through the dedicated
+    kernel k1_conv1 (default; HB_CONV1=0 disables it); results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
     prime, and (different bit lengths between source and targets) with rows at the extremes."""
     monkeypatch.setenv("HB_CONV1", "1")
     cfg = (1 << 17, -1, 1, 230, 2)

@@ -37,6 +37,16 @@ def test_owner_map_balances_digits():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode,port", [("gather", 29616), ("p2p", 29617)])
+def test_sharded_keyswitch_two_ranks_one_gpu(cuda_lib, mode, port):
+    """world_size 2 on ONE device with the real library (gloo plumbing; p2p = CUDA-IPC peer stores from the producing
+    kernel): hb_conv_make_y / hb_conv_make_y_bcast / hb_conv_from_y parity without needing a second GPU."""
+    run("cuda1", 2, "8192,257,1,160,2", port, mode)
+    if mode == "p2p":
+        run("cuda1", 2, "131072,257,1,230,2", port + 2, mode)
+
+
+@pytest.mark.gpu
 def test_sharded_keyswitch_nccl(cuda_lib):
     import torch
     if torch.cuda.device_count() < 2:
