@@ -296,6 +296,7 @@ class Ctxt {
     if (isEmpty() || inCanonicalForm(keyID)) return;
     dropSmallAndSpecialPrimes();
     relin_CKKS_adjust();
+    long g = ptxtSpace;
     double logProd = pubKey.logOfProduct(context.getSpecialPrimes());
     Ctxt tmp(pubKey, ptxtSpace);
     tmp.intFactor = intFactor; tmp.ptxtMag = ptxtMag;
@@ -310,6 +311,7 @@ class Ctxt {
       }
       const KeySwitch* W = pubKey.getKeySWmatrix(part.skHandle, keyID);
       if (!W) throw LogicError("No key-switching matrix exists");
+      if (g > 1) { tmp.reducePtxtSpace(W->ptxtSpace); g = tmp.ptxtSpace; }   // g == 1 for CKKS (src/Ctxt.cpp:771-775)
       tmp.keySwitchPart(part, *W);
     }
     *this = tmp;
@@ -350,8 +352,17 @@ class Ctxt {
   void multLowLvl(const Ctxt& other_orig) {   // src/Ctxt.cpp:1681-1753 (non-destructive, distinct operands)
     if (isEmpty()) return;
     if (other_orig.isEmpty()) { *this = other_orig; return; }
+    if (isCKKS() != other_orig.isCKKS()) throw LogicError("Scheme mismatch");
     if (&context != &other_orig.context) throw LogicError("Context mismatch");
+    if (&pubKey != &other_orig.pubKey) throw LogicError("Public key mismatch");
+    if (isCKKS() && (ptxtSpace != 1 || other_orig.ptxtSpace != 1)) throw LogicError("Plaintext spaces incompatible");
     Ctxt other = other_orig;
+    if (!isCKKS()) {   // equalize plaintext spaces (src/Ctxt.cpp:1717-1725); reducePtxtSpace also reduces intFactor
+      long g = std::gcd(ptxtSpace, other.ptxtSpace);
+      if (g <= 1) throw LogicError("Plaintext spaces are co-prime");
+      reducePtxtSpace(g);
+      other.reducePtxtSpace(g);
+    }
     double lo, hi;
     computeIntervalForMul(lo, hi, *this, other);
     auto f1 = primeSet.vec(), f2 = other.primeSet.vec();

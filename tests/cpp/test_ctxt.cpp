@@ -118,6 +118,38 @@ int main() {
     }
     est = ca.noiseBound.ln() / ln2; act = std::log2(std::max(maxabs, 1.0));
     if (act > est) { std::printf("noise estimate too small after 2 products: 2^%.1f < actual 2^%.1f\n", est, act); return 1; }
+    // ---- operands with different plaintext spaces (p^2 x p): multLowLvl must equalise to gcd = p on BOTH operands
+    //      (src/Ctxt.cpp:1717-1725) and reLinearize must reduce to the matrix's space (src/Ctxt.cpp:771-775)
+    {
+      const long p2 = p * p;
+      Ctxt pubEncrKey2(pk, p2);
+      pubEncrKey2.primeSet = ctx.getCtxtPrimes();
+      std::vector<long> e2 = sample_gauss(gen, N, sigma);
+      DoubleCRT k1 = random_rows(ctx, pubEncrKey2.primeSet, gen);
+      DoubleCRT k0(e2, ctx, pubEncrKey2.primeSet); k0 *= p2;
+      { DoubleCRT t(k1); t.Mul(S, false); k0 -= t; }
+      pubEncrKey2.parts.emplace_back(k0, SKHandle());
+      pubEncrKey2.parts.emplace_back(k1, SKHandle(1, 1, 0));
+      pubEncrKey2.noiseBound = XD(double(p2) * pk.noiseBoundForGaussian(sigma, N));
+      std::vector<long> mw(N);
+      for (long k = 0; k < N; k++) mw[k] = (long)(gen() % p2);
+      Ctxt cw(pk, p2);
+      hb::EncryptionSample smp = hb::drawEncryptionSample(ctx, sigma, gen);
+      if (hb::Encrypt(cw, pubEncrKey2, mw, p2, smp) != p2) { std::printf("Encrypt at p^2 changed the plaintext space\n"); return 1; }
+      if (decrypt(cw, nullptr) != mw) { std::printf("p^2 fresh decrypt mismatch\n"); return 1; }
+      Ctxt cn = encrypt(mb);
+      cw.multiplyBy(cn);
+      if (cw.ptxtSpace != p) { std::printf("mixed plaintext spaces: product space %ld, expected %ld\n", cw.ptxtSpace, p); return 1; }
+      std::vector<long> mwp(N); for (long k = 0; k < N; k++) mwp[k] = mw[k] % p;
+      std::vector<long> got = decrypt(cw, nullptr);
+      for (long t = 0; t < 32; t++) {
+        long k = (t * 193 + 7) % N;
+        if (got[k] != negacyclic_at(mwp, mb, k)) { std::printf("mixed plaintext spaces: product mismatch at %ld\n", k); return 1; }
+      }
+      bool threw = false;
+      try { Ctxt bad = encrypt(ma); bad.ptxtSpace = 3; bad.intFactor = 1; Ctxt o = encrypt(mb); bad.multLowLvl(o); } catch (const hb::LogicError&) { threw = true; }
+      if (!threw) { std::printf("co-prime plaintext spaces must throw\n"); return 1; }
+    }
     // drop the special primes again (cleanUp path) and decrypt once more
     ca.dropSmallAndSpecialPrimes();
     if (decrypt(ca, nullptr) != abc) { std::printf("mod-down changed the plaintext\n"); return 1; }
