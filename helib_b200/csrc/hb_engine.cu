@@ -5,6 +5,7 @@
 // in hb_device.cuh.  There is no CPU compute path: without a CUDA device hb_ctx_create fails.
 #include "hb_device.cuh"
 #include "hb_device_v1.cuh"
+#include "hb_device_v2.cuh"
 #include "hb_device_gen.cuh"
 
 #include <algorithm>
@@ -80,6 +81,11 @@ struct hb_ctx {
   bool conv1;        // dedicated single-source conversion kernel k1_conv1 (HB_CONV1=0 falls back to the general k1_conv)
   int chunk;         // batch items per launch (<= HB_MAXB; HB_CHUNK overrides): keeps the phase scratch L2-sized
   int resident_ctas; // CTAs the v1 transform kernels keep resident (2 per SM)
+  // TMA-staged blk kernels (hb_device_v2.cuh): tensor maps of every matrix they touch, built on first use
+  bool blk_v2;       // HB_BLK_V2=0 falls back to the cp.async kernels k1_fwd_blk / k1_inv_blk
+  struct TmapKey { const void* base; int logN; bool operator<(const TmapKey& o) const { return base != o.base ? base < o.base : logN < o.logN; } };
+  std::map<TmapKey, HbTmap*> tmaps;      // -> device pair {BLK view, NAT view}
+  std::vector<HbTmap*> tmap_slabs; size_t tmap_used = 0;
   // general (non power-of-two) m: Bluestein state
   struct Gen {
     bool on = false;
@@ -182,6 +188,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   c->max_smem = 200 * 1024;
   { const char* e = getenv("HB_FORCE_V0"); c->force_v0 = e && e[0] == '1'; }
   { const char* e = getenv("HB_CONV1"); c->conv1 = !(e && e[0] == '0'); }
+  { const char* e = getenv("HB_BLK_V2"); c->blk_v2 = !(e && e[0] == '0'); }
   { const char* e = getenv("HB_CHUNK"); int v = e ? atoi(e) : HB_MAXB; c->chunk = v >= 1 && v <= HB_MAXB ? v : HB_MAXB; }
   c->resident_ctas = 296;
 #ifdef HB_SIM
@@ -229,6 +236,10 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k2_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+    HB_CUDA(cudaFuncSetAttribute(k2_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+    HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+    HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
 #endif
     int r = gen_init(c, psi);
     if (r != HB_OK) return r;
@@ -271,6 +282,10 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   HB_CUDA(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem + 1024));
   HB_CUDA(cudaFuncSetAttribute(k_fwd_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k_inv_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k2_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(k2_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
   HB_CUDA(cudaFuncSetAttribute(k1_conv1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -294,6 +309,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
+  for (HbTmap* sl : c->tmap_slabs) cudaFree(sl);
   cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -567,6 +583,104 @@ static int launch_blk_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* 
   }
   return HB_OK;
 }
+
+// ---- tensor maps for the TMA-staged blk kernels ------------------------------------------------
+// Two tiled views per [nprimes][N] matrix (hb_device_v2.cuh): BLK {256, G, 16, nprimes} box {256,1,16,1} and
+// NAT {N1, 256, nprimes} box {16,256,1} with SWIZZLE_128B.  Encoded on the host once per (buffer, logN), kept in device memory.
+#define HB_TMAP_SLAB 512   // matrices per slab
+#ifndef HB_SIM
+typedef CUresult (*hb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static hb_encode_tiled_fn hb_encode_tiled() {
+  static hb_encode_tiled_fn fn = [] {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+    return (hb_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+#endif
+static bool v2_blk_ok(hb_ctx* c) {
+  if (!c->blk_v2 || c->force_v0 || c->log_blk != 8 || c->logN - 8 < 4) return false;
+#ifndef HB_SIM
+  if (!hb_encode_tiled() || c->max_smem < HB2_SMEM_BYTES) return false;
+#endif
+  return true;
+}
+static int get_tmaps(hb_ctx* c, const u64* base, const HbTmap** out) {
+  hb_ctx::TmapKey key{base, c->logN};
+  auto it = c->tmaps.find(key);
+  if (it != c->tmaps.end()) { *out = it->second; return HB_OK; }
+  if (c->tmap_slabs.empty() || c->tmap_used == HB_TMAP_SLAB) {
+    HbTmap* sl = nullptr;
+    HB_TRY(ctx_alloc(c, (void**)&sl, sizeof(HbTmap) * 2 * HB_TMAP_SLAB));
+    c->tmap_slabs.push_back(sl); c->tmap_used = 0;
+  }
+  HbTmap* d = c->tmap_slabs.back() + 2 * c->tmap_used++;
+  const int n1 = c->logN - 8;
+  const u64 N = (u64)1 << c->logN, N1 = (u64)1 << n1, G = (u64)1 << (n1 - 4);
+  HbTmap h[2];
+#ifdef HB_SIM
+  memset(h, 0, sizeof(h));
+  h[0].base = (u64*)base; h[0].rank = 4; h[0].swz128 = 0;
+  h[0].dim[0] = 256; h[0].dim[1] = G; h[0].dim[2] = 16; h[0].dim[3] = c->nprimes;
+  h[0].stride[0] = 1; h[0].stride[1] = 256; h[0].stride[2] = 256 * G; h[0].stride[3] = N;
+  h[0].box[0] = 256; h[0].box[1] = 1; h[0].box[2] = 16; h[0].box[3] = 1;
+  h[1].base = (u64*)base; h[1].rank = 3; h[1].swz128 = 1;
+  h[1].dim[0] = N1; h[1].dim[1] = 256; h[1].dim[2] = c->nprimes;
+  h[1].stride[0] = 1; h[1].stride[1] = N1; h[1].stride[2] = N;
+  h[1].box[0] = 16; h[1].box[1] = 256; h[1].box[2] = 1;
+#else
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  {
+    const cuuint64_t dim[4] = {256, G, 16, (cuuint64_t)c->nprimes};
+    const cuuint64_t str[3] = {256 * 8, 256 * 8 * G, N * 8};
+    const cuuint32_t box[4] = {256, 1, 16, 1};
+    CUresult r = hb_encode_tiled()(&h[0], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)base, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return hb_fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled(BLK view) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t dim[3] = {N1, 256, (cuuint64_t)c->nprimes};
+    const cuuint64_t str[2] = {N1 * 8, N * 8};
+    const cuuint32_t box[3] = {16, 256, 1};
+    CUresult r = hb_encode_tiled()(&h[1], CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)base, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return hb_fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled(NAT view) failed: %d", (int)r);
+  }
+#endif
+  HB_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));   // once per buffer
+  c->tmaps[key] = d;
+  *out = d;
+  return HB_OK;
+}
+static int launch_blk_v2(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
+                         int epi, const u64* scal, int lazy, u64* const* dst2) {
+  const int n1 = c->logN - 8;
+  for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+    int nr = std::min(HB_MAXROWS, n - r0);
+    Hb2BlkJob J; memset(&J, 0, sizeof(J));
+    J.logN = c->logN; J.epi = epi; J.lazy = lazy;
+    if (dir < 0) J.epi = v1_cols_ok(c) ? 2 : 0;   // inverse: the next phase is a register kernel (cols or fused conversion) -> lazy values may stay
+    fill_rows(J.rows, idx + r0, nr);
+    for (int i = 0; i < nr; i++) if (scal) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); }
+    J.nitems = nitems;
+    for (int i = 0; i < nitems; i++) {
+      const HbTmap *ms, *md, *m2;
+      HB_TRY(get_tmaps(c, src[i], &ms)); HB_TRY(get_tmaps(c, dst[i], &md));
+      J.src[i] = ms + (dir > 0 ? 0 : 1); J.dst[i] = md + (dir > 0 ? 1 : 0);
+      if (dst2) { HB_TRY(get_tmaps(c, dst2[i], &m2)); J.dst2[i] = m2 + 1; }
+    }
+    long units = (long)nr * nitems << (n1 - 4);
+    dim3 grid((unsigned)std::min<long>(units, c->resident_ctas));   // persistent CTAs, balanced contiguous chunks
+    pre_launch(c);
+    const bool sp = all_special(c);
+    if (dir > 0) { if (sp) HB_LAUNCH(k2_fwd_blk<true>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); else HB_LAUNCH(k2_fwd_blk<false>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi == 1 ? "k2_fwd_blk_subscale" : (epi == 3 ? "k2_fwd_blk_digits" : "k2_fwd_blk"), (u64)(epi == 1 ? 3 : 2) * nr * nitems * c->N * 8)); }
+    else { if (sp) HB_LAUNCH(k2_inv_blk<true>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); else HB_LAUNCH(k2_inv_blk<false>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k2_inv_blk", (u64)2 * nr * nitems * c->N * 8)); }
+  }
+  return HB_OK;
+}
 static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n) {
   const size_t smem = (16 * HB1_BS + 8) * sizeof(u64);
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
@@ -588,6 +702,7 @@ static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const*
 // direction: +1 forward blk (src -> dst, optional epilogue), -1 inverse blk
 static int launch_blk(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
                       int epi, const u64* scal, int lazy = 0, u64* const* dst2 = nullptr) {
+  if (v2_blk_ok(c)) return launch_blk_v2(c, dir, src, dst, nitems, idx, n, epi, scal, lazy, dst2);
   if (v1_blk_ok(c)) return launch_blk_v1(c, dir, src, dst, nitems, idx, n, epi, scal, lazy, dst2);
   if (lazy || dst2 || epi == 3) return hb_fail(HB_ERR_UNSUPPORTED, "lazy / dual-epilogue blk phase needs the register kernels");
   const int lwb = logwb_of(c);

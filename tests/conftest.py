@@ -18,7 +18,7 @@ def build_sim() -> str:
     """Build the kernel-logic simulator build of the engine (tests/cusim, CPU fibers).
     TEST INFRASTRUCTURE: never shipped, never loaded by helib_b200 itself."""
     out = os.path.join(ROOT, "tests", "cusim", "libhelib_b200_sim.so")
-    srcs = [os.path.join(ROOT, "helib_b200", "csrc", f) for f in ("hb_engine.cu", "hb_chain.cpp", "hb_device.cuh", "hb_device_v1.cuh", "hb_device_gen.cuh")]
+    srcs = [os.path.join(ROOT, "helib_b200", "csrc", f) for f in ("hb_engine.cu", "hb_chain.cpp", "hb_device.cuh", "hb_device_v1.cuh", "hb_device_v2.cuh", "hb_device_gen.cuh")]
     srcs.append(os.path.join(ROOT, "tests", "cusim", "cusim.h"))
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call([

@@ -28,7 +28,10 @@ extern char* smem_;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void syncthreads();
 void bar_sync(int id, int count);  // named barrier (PTX bar.sync id, count)
+void syncwarp();                   // full-warp __syncwarp()
+void yield();                      // let the other threads of the CTA run (spin waits)
 }  // namespace cusim
+#define __syncwarp() cusim::syncwarp()
 
 #define threadIdx cusim::threadIdx_
 #define blockIdx cusim::blockIdx_
@@ -116,7 +119,7 @@ static void fiber_entry() {
   swapcontext(&fibers[cur_fiber].ctx, &sched_ctx);
 }
 
-static int bar_arrived[16], bar_gen[16];
+static int bar_arrived[80], bar_gen[80];   // 0..15: CTA-level named barriers; 16 + w: __syncwarp of warp w
 static unsigned cur_nthr = 0;
 
 // counter/generation barriers: a fiber arrives, then yields until the generation advances
@@ -127,6 +130,10 @@ void bar_sync(int id, int count) {
   while (bar_gen[id] == gen) swapcontext(&fibers[me].ctx, &sched_ctx);
 }
 void syncthreads() { bar_sync(0, (int)cur_nthr); }
+// warp-level barrier (all 32 lanes; the kernels only use full-warp __syncwarp)
+void syncwarp() { bar_sync(16 + cur_fiber / 32, 32); }
+// give the other fibers of the CTA a turn (spin-wait loops: mbarrier waits)
+void yield() { int me = cur_fiber; swapcontext(&fibers[me].ctx, &sched_ctx); }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   unsigned nthr = block.x * block.y * block.z;
@@ -143,7 +150,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
       for (unsigned bx = 0; bx < grid.x; bx++) {
         smem_ = shared.data();
         cur_nthr = nthr;
-        for (int b = 0; b < 16; b++) { bar_arrived[b] = 0; bar_gen[b] = 0; }
+        for (int b = 0; b < 80; b++) { bar_arrived[b] = 0; bar_gen[b] = 0; }
         for (unsigned t = 0; t < nthr; t++) {
           getcontext(&fibers[t].ctx);
           fibers[t].ctx.uc_stack.ss_sp = fibers[t].stack;
