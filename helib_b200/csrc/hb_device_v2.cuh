@@ -18,7 +18,11 @@
 //   * mod-down epilogue: the old destination tile is TMA-loaded INTO the output buffer; every thread reads and rewrites
 //     its own 16 positions, the same buffer is stored back.
 //
-// smem (per CTA, 1024-byte aligned): IN[2][4096] | OUT[4096] | TW1[16][16] | 7 mbarriers      (~100.1 KB, 2 CTAs / SM)
+//   * a CTA holds TWO independent teams (8 compute warps + 1 I/O warp each, 18 warps = 576 threads, 1 CTA / SM): same
+//     16 resident compute warps per SM as two 9-warp CTAs, but 112 registers per thread instead of 96 (register
+//     allocation rounds a 288-thread CTA up to 320).
+//
+// smem per team (1024-byte aligned): IN[2][4096] | OUT[4096] | TW1[16][16] | 7 mbarriers  (101 KB; 203 KB per CTA)
 #pragma once
 #include "hb_device_v1.cuh"
 
@@ -36,8 +40,9 @@ typedef CUtensorMap HbTmap;
 
 #define HB2_TILE 4096            // u64 per tile (32 KB)
 #define HB2_TILE_BYTES 32768u
-#define HB2_THREADS 288          // 8 compute warps + 1 I/O warp
-#define HB2_SMEM_BYTES ((3 * HB2_TILE) * 8 + 256 * 16 + 64 + 1024)
+#define HB2_THREADS 576          // 2 teams x 8 compute warps, then one I/O warp per team
+#define HB2_TEAM_U64 (101 * 128) // u64 per team region (101 KB: a multiple of 1024 bytes keeps every tile 1024-byte aligned)
+#define HB2_SMEM_BYTES (2 * HB2_TEAM_U64 * 8 + 1024)
 
 // ---- mbarrier / TMA wrappers ---------------------------------------------------------------
 #ifdef HB_SIM
@@ -69,6 +74,7 @@ __device__ __forceinline__ void hb2_tma_load4(u64* dst, const HbTmap* m, u64*, i
 __device__ __forceinline__ void hb2_tma_load3(u64* dst, const HbTmap* m, u64*, int c0, int c1, int c2) { int c[4] = {c0, c1, c2, 0}; hb2_sim_copy(dst, m, c, true); }
 __device__ __forceinline__ void hb2_tma_store4(const HbTmap* m, int c0, int c1, int c2, int c3, u64* src) { int c[4] = {c0, c1, c2, c3}; hb2_sim_copy(src, m, c, false); }
 __device__ __forceinline__ void hb2_tma_store3(const HbTmap* m, int c0, int c1, int c2, u64* src) { int c[4] = {c0, c1, c2, 0}; hb2_sim_copy(src, m, c, false); }
+__device__ __forceinline__ void hb2_bulk_store(u64* gdst, const u64* src, unsigned bytes) { memcpy(gdst, src, bytes); }
 #else
 __device__ __forceinline__ unsigned hb2_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void hb2_mbar_init(u64* bar, unsigned count) {
@@ -112,6 +118,10 @@ __device__ __forceinline__ void hb2_tma_store3(const HbTmap* m, int c0, int c1, 
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(m), "r"(hb2_saddr(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// contiguous shared -> global copy (no tensor map): bytes and both addresses multiples of 16
+__device__ __forceinline__ void hb2_bulk_store(u64* gdst, const u64* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(hb2_saddr(src)), "r"(bytes) : "memory");
+}
 #endif
 
 __device__ __forceinline__ u64* hb2_align1024(u64* p) {
@@ -133,6 +143,7 @@ struct Hb2BlkJob {
   const HbTmap* src[HB_MAXB];    // forward: BLK view of the source;      inverse: NAT view
   const HbTmap* dst[HB_MAXB];    // forward: NAT view of the destination; inverse: BLK view
   const HbTmap* dst2[HB_MAXB];   // forward epilogue 3: NAT view of the matrix updated in place
+  u64* dstp[HB_MAXB];            // inverse: the destination matrices themselves (each warp stores its own two blocks)
 };
 
 // barrier slots
@@ -145,27 +156,29 @@ struct Hb2BlkJob {
 // ------------------------------------------------------------------------------------------
 // Forward "blk" phase: last 8 Cooley-Tukey stages inside 256-blocks + un-bit-reversal.
 template <bool SP>
-__global__ void __launch_bounds__(HB2_THREADS, 2) k2_fwd_blk(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb2BlkJob J) {
+__global__ void __launch_bounds__(HB2_THREADS, 1) k2_fwd_blk(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb2BlkJob J) {
   HB_SMEM_DECL
-  u64* IN = hb2_align1024(HB_SMEM);
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int team = wid >= 16 ? wid - 16 : wid >> 3, warp = wid >= 16 ? 8 : wid & 7;   // warp 8 = the team's I/O warp
+  u64* IN = hb2_align1024(HB_SMEM) + (size_t)team * HB2_TEAM_U64;
   u64* OUT = IN + 2 * HB2_TILE;
   ulonglong2* TW1 = (ulonglong2*)(OUT + HB2_TILE);
   u64* BAR = (u64*)(TW1 + 256);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n1 = J.logN - 8;
   const int G = 1 << (n1 - 4);
   const long U = (long)J.rows.n * G * J.nitems;
-  const long ubeg = U * blockIdx.x / gridDim.x, uend = U * (blockIdx.x + 1) / gridDim.x;
-  if (ubeg >= uend) return;
+  const long vcta = 2L * blockIdx.x + team, vgrid = 2L * gridDim.x;          // every team is a persistent worker of its own
+  const long ubeg = U * vcta / vgrid, uend = U * (vcta + 1) / vgrid;
   const int nu = (int)(uend - ubeg);
   const bool epi1 = J.epi == 1, epi3 = J.epi == 3, lazy = J.lazy != 0;
-  if (tid == 0) {
+  if (warp == 8 && lane == 0) {
     hb2_mbar_init(BAR + HB2_FULL0, 1); hb2_mbar_init(BAR + HB2_FULL0 + 1, 1);
     hb2_mbar_init(BAR + HB2_EMPTY0, 8); hb2_mbar_init(BAR + HB2_EMPTY0 + 1, 8);
     hb2_mbar_init(BAR + HB2_OUTFULL, 8); hb2_mbar_init(BAR + HB2_OUTFREE, 1); hb2_mbar_init(BAR + HB2_OLDFULL, 1);
     hb2_fence_init();
   }
   __syncthreads();
+  if (nu <= 0) return;
 
   if (warp == 8) {
     // ---------------- I/O warp: one thread drives the TMA
@@ -289,47 +302,41 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k2_fwd_blk(const HbPrimeDev* _
 // ------------------------------------------------------------------------------------------
 // Inverse "blk" phase: bit-reversal + first 8 Gentleman-Sande stages.
 template <bool SP>
-__global__ void __launch_bounds__(HB2_THREADS, 2) k2_inv_blk(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb2BlkJob J) {
+__global__ void __launch_bounds__(HB2_THREADS, 1) k2_inv_blk(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb2BlkJob J) {
   HB_SMEM_DECL
-  u64* IN = hb2_align1024(HB_SMEM);
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int team = wid >= 16 ? wid - 16 : wid >> 3, warp = wid >= 16 ? 8 : wid & 7;
+  u64* IN = hb2_align1024(HB_SMEM) + (size_t)team * HB2_TEAM_U64;
   u64* OUT = IN + 2 * HB2_TILE;
   ulonglong2* TW1 = (ulonglong2*)(OUT + HB2_TILE);
   u64* BAR = (u64*)(TW1 + 256);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n1 = J.logN - 8;
   const int G = 1 << (n1 - 4);
   const long U = (long)J.rows.n * G * J.nitems;
-  const long ubeg = U * blockIdx.x / gridDim.x, uend = U * (blockIdx.x + 1) / gridDim.x;
-  if (ubeg >= uend) return;
+  const long vcta = 2L * blockIdx.x + team, vgrid = 2L * gridDim.x;
+  const long ubeg = U * vcta / vgrid, uend = U * (vcta + 1) / vgrid;
   const int nu = (int)(uend - ubeg);
-  if (tid == 0) {
+  if (warp == 8 && lane == 0) {
     hb2_mbar_init(BAR + HB2_FULL0, 1); hb2_mbar_init(BAR + HB2_FULL0 + 1, 1);
     hb2_mbar_init(BAR + HB2_EMPTY0, 8); hb2_mbar_init(BAR + HB2_EMPTY0 + 1, 8);
-    hb2_mbar_init(BAR + HB2_OUTFULL, 8); hb2_mbar_init(BAR + HB2_OUTFREE, 1);
     hb2_fence_init();
   }
   __syncthreads();
+  if (nu <= 0) return;
 
   if (warp == 8) {
     if (lane != 0) return;
-    Hb1Unit cur = hb1_unit(ubeg, G, J.nitems), ahead = cur;
+    Hb1Unit ahead = hb1_unit(ubeg, G, J.nitems);
     auto load_in = [&](const Hb1Unit& x, int slot) {
       hb2_mbar_expect(BAR + HB2_FULL0 + slot, HB2_TILE_BYTES);
       hb2_tma_load3(IN + slot * HB2_TILE, J.src[x.it], BAR + HB2_FULL0 + slot, x.ug << 4, 0, J.rows.prime[x.rowi]);
     };
     load_in(ahead, 0);
     if (nu > 1) { ahead = hb1_unit_next(ahead, G, J.nitems); load_in(ahead, 1); }
-    unsigned pf = 0;
-    for (int k = 0; k < nu; k++) {
+    for (int k = 0; k + 2 < nu; k++) {   // loads only: every compute warp stores its own two blocks
       hb2_mbar_wait(BAR + HB2_EMPTY0 + (k & 1), (unsigned)(k >> 1) & 1u);
-      if (k + 2 < nu) { ahead = hb1_unit_next(ahead, G, J.nitems); load_in(ahead, k & 1); }
-      hb2_mbar_wait(BAR + HB2_OUTFULL, pf); pf ^= 1u;
-      hb2_tma_store4(J.dst[cur.it], 0, (int)hb_brev((unsigned)cur.ug, n1 - 4), 0, J.rows.prime[cur.rowi], OUT);
-      hb2_store_commit(); hb2_store_wait_read();
-      hb2_mbar_arrive(BAR + HB2_OUTFREE);
-      cur = hb1_unit_next(cur, G, J.nitems);
+      ahead = hb1_unit_next(ahead, G, J.nitems); load_in(ahead, k & 1);
     }
-    hb2_store_wait_all();
     return;
   }
 
@@ -348,7 +355,6 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k2_inv_blk(const HbPrimeDev* _
   u64 q = 0;
   Hb1Mod M; M.nq = 0; M.qb = 0; M.qb2 = 0; M.qt = 0; M.qsh = 0;
   Hb1TwReg tw2;
-  unsigned pfree = 1;
   for (int k = 0; k < nu; k++) {
     if (cur.rowi * G + cur.ug != key) {
       key = cur.rowi * G + cur.ug;
@@ -377,7 +383,10 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k2_inv_blk(const HbPrimeDev* _
     __syncwarp();
     if (lane == 0) hb2_mbar_arrive(BAR + HB2_EMPTY0 + (k & 1));
     hb1_r16_inv<SP>(a, tw2, M);
-    hb2_mbar_wait(BAR + HB2_OUTFREE, pfree); pfree ^= 1u;   // the exchange happens in the output tile (block-contiguous, warp-private)
+    // the exchange happens in the output tile (block-contiguous, so each warp's two blocks are private to it): only this
+    // warp's own previous store has to be done reading them
+    if (lane == 0) hb2_store_wait_read();
+    __syncwarp();
 #pragma unroll
     for (int l = 0; l < 16; l++) OUT[p2 + (x2 ^ l)] = a[l];
     __syncwarp();
@@ -389,7 +398,15 @@ __global__ void __launch_bounds__(HB2_THREADS, 2) k2_inv_blk(const HbPrimeDev* _
     for (int r = 0; r < 16; r++) OUT[p1 + 16 * r + lo] = J.epi == 2 ? a[r] : hb1_canon_inv(a[r], q);
     hb2_fence_async();
     __syncwarp();
-    if (lane == 0) hb2_mbar_arrive(BAR + HB2_OUTFULL);
+    if (lane == 0) {   // block b = slot*G + brev(ug) of the row, 2 KB contiguous each
+      const unsigned ugr = hb_brev((unsigned)cur.ug, n1 - 4);
+      u64* d = J.dstp[cur.it] + ((size_t)J.rows.prime[cur.rowi] << J.logN);
+      const int s0 = (int)hb1_brev4((unsigned)(2 * warp)), s1 = (int)hb1_brev4((unsigned)(2 * warp + 1));
+      hb2_bulk_store(d + (((size_t)s0 * G + ugr) << 8), OUT + s0 * 256, 2048);
+      hb2_bulk_store(d + (((size_t)s1 * G + ugr) << 8), OUT + s1 * 256, 2048);
+      hb2_store_commit();
+    }
     cur = hb1_unit_next(cur, G, J.nitems);
   }
+  if (lane == 0) hb2_store_wait_all();
 }

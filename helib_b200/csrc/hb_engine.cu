@@ -604,7 +604,7 @@ static hb_encode_tiled_fn hb_encode_tiled() {
 static bool v2_blk_ok(hb_ctx* c) {
   if (!c->blk_v2 || c->force_v0 || c->log_blk != 8 || c->logN - 8 < 4) return false;
 #ifndef HB_SIM
-  if (!hb_encode_tiled() || c->max_smem < HB2_SMEM_BYTES) return false;
+  if (!hb_encode_tiled()) return false;
 #endif
   return true;
 }
@@ -671,9 +671,10 @@ static int launch_blk_v2(hb_ctx* c, int dir, const u64* const* src, u64* const* 
       HB_TRY(get_tmaps(c, src[i], &ms)); HB_TRY(get_tmaps(c, dst[i], &md));
       J.src[i] = ms + (dir > 0 ? 0 : 1); J.dst[i] = md + (dir > 0 ? 1 : 0);
       if (dst2) { HB_TRY(get_tmaps(c, dst2[i], &m2)); J.dst2[i] = m2 + 1; }
+      J.dstp[i] = dst[i];
     }
     long units = (long)nr * nitems << (n1 - 4);
-    dim3 grid((unsigned)std::min<long>(units, c->resident_ctas));   // persistent CTAs, balanced contiguous chunks
+    dim3 grid((unsigned)std::min<long>((units + 1) / 2, std::max(1, c->resident_ctas / 2)));   // one persistent CTA (two teams) per SM
     pre_launch(c);
     const bool sp = all_special(c);
     if (dir > 0) { if (sp) HB_LAUNCH(k2_fwd_blk<true>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); else HB_LAUNCH(k2_fwd_blk<false>, grid, dim3(HB2_THREADS), HB2_SMEM_BYTES, c->stream, c->d_primes, J); HB_TRY(post_launch(c, epi == 1 ? "k2_fwd_blk_subscale" : (epi == 3 ? "k2_fwd_blk_digits" : "k2_fwd_blk"), (u64)(epi == 1 ? 3 : 2) * nr * nitems * c->N * 8)); }
