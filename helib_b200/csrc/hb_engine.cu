@@ -170,6 +170,7 @@ static u64 find_psi(u64 q, u64 two_n) {
 }
 
 static int gen_init(hb_ctx* c, const uint64_t* psi);
+static int ctx_build(hb_ctx* c, hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi, bool pow2);
 extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi) {
   if (!out || !q || nprimes <= 0) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: null argument or nprimes <= 0");
   if (m < 3 || m > (1ULL << 20)) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: m=%llu out of range [3, 2^20]", (unsigned long long)m);
@@ -178,7 +179,12 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   if (ndev <= 0) return hb_fail(HB_ERR_NO_DEVICE, "hb_ctx_create: no CUDA device (the engine has no CPU path)");
   if (device < 0 || device >= ndev) return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: device %d out of range [0,%d)", device, ndev);
   HB_CUDA(cudaSetDevice(device));
-  hb_ctx* c = new hb_ctx();
+  hb_ctx* c = new hb_ctx();   // value-initialised: every pointer null, so hb_ctx_destroy can unwind a partial construction
+  const int rc = ctx_build(c, out, device, m, nprimes, q, psi, pow2);
+  if (rc != HB_OK) hb_ctx_destroy(c);
+  return rc;
+}
+static int ctx_build(hb_ctx* c, hb_ctx** out, int device, uint64_t m, int nprimes, const uint64_t* q, const uint64_t* psi, bool pow2) {
   c->device = device; c->m = m; c->N = pow2 ? m / 2 : 0; c->nprimes = nprimes;
   c->logN = 0; while (((size_t)1 << c->logN) < c->N) c->logN++;
   c->log_blk = c->logN >= 11 ? 8 : 0;
@@ -201,11 +207,11 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
   for (int i = 0; i < nprimes; i++) {
     u64 qi = q[i];
     // HElib primes are < 2^HELIB_SP_NBITS = 2^60 (src/macro.h:16-23); the lazy butterflies need 13q + 2^49 < 2^64
-    if (qi < 3 || qi >= (1ULL << 60) || (qi - 1) % m != 0) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^60 with m | q-1", i, (unsigned long long)qi); }
+    if (qi < 3 || qi >= (1ULL << 60) || (qi - 1) % m != 0) { return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: q[%d]=%llu is not < 2^60 with m | q-1", i, (unsigned long long)qi); }
     u64 ps = 0;
     if (pow2) {
       ps = psi ? psi[i] : find_psi(qi, m);
-      if (h_powmod(ps, N, qi) != qi - 1) { delete c; return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
+      if (h_powmod(ps, N, qi) != qi - 1) { return hb_fail(HB_ERR_BAD_ARG, "hb_ctx_create: psi[%d] is not a primitive %llu-th root of unity mod q", i, (unsigned long long)m); }
     }
     c->q.push_back(qi); c->psi.push_back(ps);
   }
@@ -241,8 +247,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
     HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
     HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
 #endif
-    int r = gen_init(c, psi);
-    if (r != HB_OK) return r;
+    HB_TRY(gen_init(c, psi));
     *out = c;
     return HB_OK;
   }
@@ -301,7 +306,7 @@ extern "C" int hb_ctx_create(hb_ctx** out, int device, uint64_t m, int nprimes, 
 
 extern "C" void hb_ctx_destroy(hb_ctx* c) {
   if (!c) return;
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& kv : c->convs) { cudaFree(kv.second.blob); cudaFree(kv.second.d); }
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
   cudaFree(c->pw.d_cube_to_poly); cudaFree(c->pw.d_short_to_long); cudaFree(c->pw.cube); cudaFree(c->pw.rows);
@@ -310,7 +315,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
   for (HbTmap* sl : c->tmap_slabs) cudaFree(sl);
-  cudaStreamDestroy(c->own_stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
 
@@ -376,7 +381,8 @@ extern "C" int hb_poly_create(hb_ctx* c, hb_poly** out) {
   size_t sz = (size_t)c->nprimes * c->N * sizeof(u64);
   int r = ctx_alloc(c, (void**)&p->d, sz);
   if (r != HB_OK) { delete p; return r; }
-  HB_CUDA(cudaMemsetAsync(p->d, 0, sz, c->stream));
+  cudaError_t e = cudaMemsetAsync(p->d, 0, sz, c->stream);
+  if (e != cudaSuccess) { cudaFree(p->d); c->bytes -= sz; delete p; return hb_fail(HB_ERR_CUDA, "hb_poly_create: memset failed: %s", cudaGetErrorString(e)); }
   *out = p;
   return HB_OK;
 }
@@ -511,6 +517,9 @@ extern "C" int hb_poly_deserialize(hb_poly* p, const void* buf, uint64_t buflen,
   for (int64_t i = 0; i < card; i++) {
     int64_t v; memcpy(&v, o, 8); o += 8;
     if (v < 0 || v >= c->nprimes) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: prime index %lld out of range", (long long)v);
+    // IndexSet::writeTo emits the members in ascending order and the rows follow in that order (src/IndexSet.cpp, src/DoubleCRT.cpp:1530-1561):
+    // anything else is not a DoubleCRT record
+    if (i > 0 && (int32_t)v <= idx_out[i - 1]) return hb_fail(HB_ERR_BAD_ARG, "hb_poly_deserialize: prime indices must be strictly ascending");
     idx_out[i] = (int32_t)v;
   }
   for (int64_t i = 0; i < card; i++) {
@@ -528,7 +537,8 @@ extern "C" int hb_poly_deserialize(hb_poly* p, const void* buf, uint64_t buflen,
       row[k] = (u64)v;
     }
     o += (size_t)len * isz;
-    HB_CUDA(cudaMemcpy(p->d + (size_t)idx_out[i] * c->N, row.data(), c->N * 8, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpyAsync(p->d + (size_t)idx_out[i] * c->N, row.data(), c->N * 8, cudaMemcpyHostToDevice, c->stream));   // ordered with the context's stream
+    HB_CUDA(cudaStreamSynchronize(c->stream));   // `row` is reused
   }
   *n_out = (int)card;
   return HB_OK;

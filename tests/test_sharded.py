@@ -46,19 +46,19 @@ def test_sharded_keyswitch_two_ranks_one_gpu(cuda_lib, mode, port):
         run("cuda1", 2, "131072,257,1,230,2", port + 2, mode)
 
 
+def _backend():
+    """NCCL over two devices when the box has them, otherwise the same two ranks on one device (gloo plumbing)."""
+    import torch
+    return "cuda" if torch.cuda.device_count() >= 2 else "cuda1"
+
+
 @pytest.mark.gpu
 def test_sharded_keyswitch_nccl(cuda_lib):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    run("cuda", 2, "8192,257,1,160,2", 29613)
+    run(_backend(), 2, "8192,257,1,160,2", 29613)
 
 
 @pytest.mark.gpu
 def test_sharded_keyswitch_p2p_stores(cuda_lib):
-    """Same circuit with the fused make-y + peer-store kernel (CUDA IPC over NVLink) instead of all_gather."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    run("cuda", 2, "8192,257,1,160,2", 29614, "p2p")
-    run("cuda", 2, "131072,257,1,230,2", 29615, "p2p")
+    """Same circuit with the fused make-y + peer-store kernel (CUDA IPC; NVLink between two GPUs) instead of all_gather."""
+    run(_backend(), 2, "8192,257,1,160,2", 29614, "p2p")
+    run(_backend(), 2, "131072,257,1,230,2", 29615, "p2p")
