@@ -1764,6 +1764,22 @@ extern "C" int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig,
                                    hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1) {
   return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, nullptr, 0, nullptr, nullptr, nullptr);
 }
+extern "C" int hb_keyswitch_digits_fused(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                                         hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1,
+                                         const uint64_t* scal, hb_poly* const* own, const int32_t* own_dig) {
+  if (!scal) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits_fused: scal is required");
+  if ((own == nullptr) != (own_dig == nullptr)) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits_fused: own and own_dig go together");
+  std::vector<int> od;
+  if (own_dig) { od.assign(own_dig, own_dig + n); for (int r = 0; r < n; r++) if (od[r] >= ndig || od[r] < -1) return hb_fail(HB_ERR_BAD_ARG, "hb_keyswitch_digits_fused: own_dig[%d] out of range", r); }
+  if (own) { hb_ctx* c = nullptr; HB_TRY(check_polys(own, nitems, &c, "hb_keyswitch_digits_fused(own)")); }
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, idx, n, evk_a, evk_b, out0, out1, (const u64*)scal, 0, nullptr, own, own_dig ? od.data() : nullptr);
+}
+extern "C" int hb_sub_div_by_primes(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, const int32_t* fidx, int nf) {
+  hb_ctx* c = nullptr; HB_TRY(check_polys(dst, nitems, &c, "hb_sub_div_by_primes")); HB_TRY(check_polys(src, nitems, &c, "hb_sub_div_by_primes"));
+  HB_TRY(check_idx(c, idx, n, "hb_sub_div_by_primes")); HB_TRY(check_idx(c, fidx, nf, "hb_sub_div_by_primes(factor)"));
+  std::vector<u64> sc; HB_TRY(scalars_by_primes(c, idx, n, fidx, nf, 1, sc));
+  return pw_simple(HB_PW_SUBSCALE, dst, src, nitems, idx, n, sc.data(), c);
+}
 // Hoisted automorphism + key switch (next row 8f-1): BasicAutomorphPrecon::automorph (src/matmul.cpp:112-184).
 extern "C" int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* S, int nS,
                                              hb_poly* const* c0, uint64_t k, hb_poly* const* evk_a, hb_poly* const* evk_b,

@@ -310,6 +310,24 @@ class Engine:
         flat = [d for item in digits for d in item]
         self._ck(self.lib.hb_keyswitch_digits(_arr(flat), nd, nd, len(digits), p, n, _arr(evk_a), _arr(evk_b), _arr(out0), _arr(out1)))
 
+    def keyswitch_digits_fused(self, digits, idx, evk_a, evk_b, out0, out1, scal, own=None, own_dig=None):
+        """out = scal[r]*out + sum_i D_i*evk_i on rows idx (scal 0 => pure output); rows with own_dig[r] = i take digit i
+        from own[item] (hb_keyswitch_digits_fused)."""
+        a, p, n = _idx(idx)
+        nd = len(digits[0])
+        flat = [d for item in digits for d in item]
+        sc = np.array([int(x) for x in scal], dtype=np.uint64)
+        od = np.ascontiguousarray(np.array(own_dig, dtype=np.int32)) if own_dig is not None else None
+        self._ck(self.lib.hb_keyswitch_digits_fused(_arr(flat), nd, nd, len(digits), p, n, _arr(evk_a), _arr(evk_b), _arr(out0), _arr(out1),
+                                                    sc.ctypes.data_as(u64p), _arr(own) if own is not None else None,
+                                                    od.ctypes.data_as(i32p) if od is not None else None))
+
+    def sub_div_by_primes(self, dst, src, idx, fidx):
+        """dst = (dst - src) / prod(q_f) on rows idx (hb_sub_div_by_primes)."""
+        a, p, n = _idx(idx)
+        b, pf, nf = _idx(fidx)
+        self._ck(self.lib.hb_sub_div_by_primes(_arr(dst), _arr(src), len(dst), p, n, pf, nf))
+
     def tensor(self, a0, a1, b0, b1, o0, o1, o2, idx):
         a, p, n = _idx(idx)
         self._ck(self.lib.hb_tensor(_arr(a0), _arr(a1), _arr(b0), _arr(b1), _arr(o0), _arr(o1), _arr(o2), len(a0), p, n))

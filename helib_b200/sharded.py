@@ -108,18 +108,11 @@ class ShardedKeySwitch:
 
     def relinearize(self, c0, c1, c2, S, evk_a, evk_b, dig_polys=None):
         """3-part (1, s, s^2) ciphertexts over ctxt primes S -> 2-part over S | special (rows owned by this
-        rank only).  c0,c1,c2: lists of Poly (batch items) holding at least the owned rows."""
+        rank only).  c0,c1,c2: lists of Poly (batch items) holding at least the owned rows; c2 is consumed."""
         E = self.E
         Sp = sorted(set(S) | set(self.special))
         oS, oSp, oSpec = self.owned(S), self.owned(Sp), self.owned(self.special)
         nit = len(c0)
-        # parts with handle 1 / base s: addPrimesAndScale(special) on the owned rows (src/Ctxt.cpp:764-768)
-        if oS:
-            E.scale_by_primes(c0, oS, self.special)
-            E.scale_by_primes(c1, oS, self.special)
-        if oSpec:
-            E.zero_rows(c0, oSpec)
-            E.zero_rows(c1, oSpec)
         # digits (src/DoubleCRT.cpp:479-561)
         remaining, nd = set(S), 0
         while remaining:
@@ -128,25 +121,43 @@ class ShardedKeySwitch:
         dsets = [[i for i in S if i in self.digits[d]] for d in range(nd)]
         if dig_polys is None:
             dig_polys = [[E.poly() for _ in range(nd)] for _ in range(nit)]
-        for d in range(nd):
-            od = self.owned(dsets[d])
-            if od:
-                E.pointwise("copy", [dp[d] for dp in dig_polys], c2, od)
+        fused = E.N % 512 == 0 and nd <= 4       # streaming inner-product kernel: aliased own rows, folded scale / zero
+        if not fused:
+            # parts with handle 1 / base s: addPrimesAndScale(special) on the owned rows (src/Ctxt.cpp:764-768)
+            if oS:
+                E.scale_by_primes(c0, oS, self.special)
+                E.scale_by_primes(c1, oS, self.special)
+            if oSpec:
+                E.zero_rows(c0, oSpec)
+                E.zero_rows(c1, oSpec)
+            for d in range(nd):
+                od = self.owned(dsets[d])
+                if od:
+                    E.pointwise("copy", [dp[d] for dp in dig_polys], c2, od)
         for d in range(nd):
             col = [dp[d] for dp in dig_polys]
             ys = [self._ybuf(("dig", it)) for it in range(nit)]
-            self._exchange(col, dsets[d], ys)
+            # fused: digit d's own rows ARE c2's rows by now (the mixed-radix steps update c2 in place)
+            self._exchange(c2 if fused else col, dsets[d], ys)
             tgt = self.owned([i for i in Sp if i not in dsets[d]])
             E.conv_from_y([y[1] for y in ys], dsets[d], tgt, 1, col, 0)
             for j in range(d + 1, nd):   # digits[j] -= digits[d]; digits[j] /= prod(full digit d)
                 oj = self.owned(dsets[j])
                 if oj:
-                    colj = [dp[j] for dp in dig_polys]
-                    E.pointwise("sub", colj, col, oj)
-                    E.scale_by_primes(colj, oj, self.digits[d], inv=True)
+                    E.sub_div_by_primes(c2 if fused else [dp[j] for dp in dig_polys], col, oj, self.digits[d])
         # evk inner product on the owned rows (src/Ctxt.cpp:191-230)
         if oSp:
-            E.keyswitch_digits([dp[:nd] for dp in dig_polys], oSp, evk_a[:nd], evk_b[:nd], c0, c1)
+            digs = [dp[:nd] for dp in dig_polys]
+            if fused:
+                P = 1
+                for i in self.special:
+                    P *= E.primes[i]
+                inS = set(S)
+                scal = [P % E.primes[r] if r in inS else 0 for r in oSp]
+                own_dig = [next(d for d in range(nd) if r in dsets[d]) if r in inS else -1 for r in oSp]
+                E.keyswitch_digits_fused(digs, oSp, evk_a[:nd], evk_b[:nd], c0, c1, scal, own=c2, own_dig=own_dig)
+            else:
+                E.keyswitch_digits(digs, oSp, evk_a[:nd], evk_b[:nd], c0, c1)
         return Sp
 
     def mod_down(self, parts, cur, keep, ptxt_space=1):

@@ -152,6 +152,19 @@ int hb_break_into_digits(hb_poly* const* src, int nitems, const int32_t* cur, in
  * every call, src/Ctxt.cpp:196-206; here they are expanded once by the host and cached). */
 int hb_keyswitch_digits(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
                         hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1);
+/* The same inner product with the two passes around it folded in (what Ctxt::keySwitchPart + reLinearize do per part,
+ * src/Ctxt.cpp:764-768,805-842):
+ *   out0[r] = scal[r]*out0[r] + sum_i D_i[r]*b_i[r]   (same for out1 / a_i);  scal[r] == 0 => the row is a pure output
+ *   (addPrimesAndScale: scal[r] = prod(special) mod q_r on the rows the part already has, 0 on the special rows);
+ *   own / own_dig (optional): rows with own_dig[r] = i >= 0 take digit i from own[item] (the part being switched, whose rows
+ *   ARE digit i's own rows) instead of digits[item*maxdig + i] -- no copies of the part into the digit polynomials.
+ * Power-of-two m, at most 4 digits. */
+int hb_keyswitch_digits_fused(hb_poly* const* digits, int maxdig, int ndig, int nitems, const int32_t* idx, int n,
+                              hb_poly* const* evk_a, hb_poly* const* evk_b, hb_poly* const* out0, hb_poly* const* out1,
+                              const uint64_t* scal, hb_poly* const* own, const int32_t* own_dig);
+/* The mixed-radix step of DoubleCRT::breakIntoDigits (src/DoubleCRT.cpp:551-556) in one pass:
+ * dst = (dst - src) / prod(q_f, f in fidx) on rows idx. */
+int hb_sub_div_by_primes(hb_poly* const* dst, hb_poly* const* src, int nitems, const int32_t* idx, int n, const int32_t* fidx, int nf);
 /* Hoisted automorphism + key switch: BasicAutomorphPrecon::automorph (src/matmul.cpp:112-184),
  * the rotation path of Ctxt::smartAutomorph (src/Ctxt.cpp:2462-2515).  The digits of the s-part are computed once
  * with hb_break_into_digits; for each amount k (odd, < m) one launch applies sigma_k in the load stage:
