@@ -84,7 +84,10 @@ class Context {
   std::vector<IndexSet> digits_;
   long m_, phim_, p_, r_;
  public:
-  Context(long m, long p, long r, long bits, long c, int device = 0) : m_(m), p_(p), r_(r) {
+  // psi (optional, one per chain prime): the primitive m-th root every row is evaluated at.  A build of the reference derives its
+  // roots from NTL's zz_pContext tables (src/CModulus.cpp:93-119): hand them over (Cmodulus::FFT of the monomial X yields psi in
+  // y[0]) to make rows and the writeTo/read bytes interchangeable with that build; without it the engine picks its own root.
+  Context(long m, long p, long r, long bits, long c, int device = 0, const std::vector<uint64_t>* psi = nullptr) : m_(m), p_(p), r_(r) {
     if (hb_chain_build(&chain_, (uint64_t)m, p, (int)r, (int)bits, (int)c, 0, 3, 0, 3.2) != HB_OK)
       throw InvalidArgument(hb_chain_last_error());
     int np, ns, nc, nsp, nd; int64_t phim;
@@ -100,7 +103,8 @@ class Context {
       else if (kind[i] == 1) { ctxt_.insert(i); if (dig[i] >= 0) digits_[dig[i]].insert(i); }
       else { special_.insert(i); sp.push_back(i); }
     }
-    check(hb_ctx_create(&ctx_, device, (uint64_t)m, np, primes_.data(), nullptr));
+    if (psi && (int)psi->size() != np) throw InvalidArgument("Context: one root per chain prime expected");
+    check(hb_ctx_create(&ctx_, device, (uint64_t)m, np, primes_.data(), psi ? psi->data() : nullptr));
     check(hb_ctx_set_chain(ctx_, dig.data(), nd, sp.data(), (int)sp.size()));
   }
   ~Context() { if (ctx_) hb_ctx_destroy(ctx_); if (chain_) hb_chain_destroy(chain_); }
@@ -409,6 +413,50 @@ class DoubleCRT {
     int32_t idx[1] = {(int32_t)i};
     check(hb_poly_download(p_, idx, 1, dense.data()));
     return std::vector<long>(dense.begin() + (size_t)i * N, dense.begin() + (size_t)(i + 1) * N);
+  }
+};
+
+// helib::Cmodulus (include/helib/CModulus.h:104-157): the transform of ONE chain prime -- the row-level view of the engine.
+// FFT / iFFT run on the device through the same kernels as DoubleCRT (a one-row DoubleCRT per call); this is the surface the
+// reference's own per-row seams use (src/CModulus.cpp:358-578), kept for callers that hold a Cmodulus (tests, PAlgebraMod).
+class Cmodulus {
+  const Context* context_ = nullptr;
+  long idx_ = -1;
+ public:
+  Cmodulus() = default;
+  Cmodulus(const Context& ctx, long primeIdx) : context_(&ctx), idx_(primeIdx) {
+    if (primeIdx < 0 || primeIdx >= ctx.numPrimes()) throw InvalidArgument("Cmodulus: prime index out of range");
+  }
+  unsigned long getM() const { return (unsigned long)context_->getM(); }
+  unsigned long getPhiM() const { return (unsigned long)context_->getPhiM(); }
+  long getQ() const { return context_->ithPrime(idx_); }
+  // the primitive m-th root the rows are evaluated at (Cmodulus::getRoot)
+  long getRoot() const {
+    std::vector<uint64_t> psi((size_t)context_->numPrimes());
+    check(hb_ctx_get_psi(context_->handle(), psi.data()));
+    return (long)psi[(size_t)idx_];
+  }
+  // y = FFT(x): x a polynomial with small signed coefficients (zzX), y[j] = x(psi^(rep(j)))   (src/CModulus.cpp:358-443)
+  void FFT(std::vector<long>& y, const std::vector<long>& x) const {
+    IndexSet s; s.insert(idx_);
+    DoubleCRT d(x, *context_, s);
+    y = d.getOneRow(idx_);
+  }
+  // x = FFT^-1(y): coefficients in [0, q)   (src/CModulus.cpp:486-577)
+  void iFFT(std::vector<long>& x, const std::vector<long>& y) const {
+    const long N = context_->getPhiM();
+    if ((long)y.size() != N) throw InvalidArgument("iFFT: row length must be phi(m)");
+    hb_poly* p = nullptr;
+    check(hb_poly_create(context_->handle(), &p));
+    std::vector<uint64_t> dense((size_t)context_->numPrimes() * N, 0);
+    for (long k = 0; k < N; k++) dense[(size_t)idx_ * N + k] = (uint64_t)y[k];
+    int32_t idx[1] = {(int32_t)idx_};
+    int rc = hb_poly_upload(p, idx, 1, dense.data());
+    if (rc == HB_OK) rc = hb_ntt_inv(&p, 1, idx, 1);
+    if (rc == HB_OK) rc = hb_poly_download(p, idx, 1, dense.data());
+    hb_poly_destroy(p);
+    check(rc);
+    x.assign(dense.begin() + (size_t)idx_ * N, dense.begin() + (size_t)(idx_ + 1) * N);
   }
 };
 

@@ -36,6 +36,22 @@ int main() {
       for (long i = 0; i < N; i++) { long j = k - i; if (j >= 0) acc += f[i] * g[j]; else acc -= f[i] * g[j + N]; }
       if (coeff_of(hp, L, k) != acc) { std::printf("product mismatch at %ld\n", k); return 1; }
     }
+    // Cmodulus surface (include/helib/CModulus.h:104-157): the monomial X evaluates to the root itself in y[0] (the calibration
+    // SURVEY 8c describes), y[j] = psi^(2j+1), and iFFT inverts FFT
+    {
+      hb::Cmodulus cm(ctx, S.first());
+      const long q = cm.getQ(), psi = cm.getRoot();
+      if ((long)cm.getM() != 4096 || (long)cm.getPhiM() != N) { std::printf("Cmodulus: m / phi(m)\n"); return 1; }
+      std::vector<long> mono(2, 0), y, back; mono[1] = 1;
+      cm.FFT(y, mono);
+      if (y[0] != psi) { std::printf("Cmodulus::FFT(X)[0] = %ld, root = %ld\n", y[0], psi); return 1; }
+      unsigned __int128 w = (unsigned __int128)psi * psi % q, cur = psi;
+      for (long j = 0; j < 8; j++) { if ((long)cur != y[j]) { std::printf("Cmodulus::FFT(X)[%ld] != psi^(2j+1)\n", j); return 1; } cur = cur * w % q; }
+      cm.FFT(y, f);
+      cm.iFFT(back, y);
+      for (long k = 0; k < N; k++) { long want = f[k] < 0 ? f[k] + q : f[k]; if (back[k] != want) { std::printf("Cmodulus: iFFT(FFT(f)) != f at %ld\n", k); return 1; } }
+      if (y != F.getOneRow(S.first())) { std::printf("Cmodulus::FFT row differs from the DoubleCRT row\n"); return 1; }
+    }
     // addPrimes to the special primes and back
     hb::DoubleCRT E(F);
     E.addPrimes(ctx.getSpecialPrimes());
