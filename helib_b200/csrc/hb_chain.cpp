@@ -117,9 +117,53 @@ struct hb_chain {
   std::vector<int> of_kind(int k) const { std::vector<int> v; for (size_t i = 0; i < kind.size(); i++) if (kind[i] == k) v.push_back((int)i); return v; }
   double log_of_product(const std::vector<int>& s) const { double x = 0; for (int i : s) x += std::log((double)primes[i]); return x; }
 
-  void build(long bits, long nDgts, long skHwt, long resolution, long bitsInSpecial, double stdev) {
+  long e_param = 0, ePrime_param = 0, hwt_param = 0;   // Context::e_param / ePrime_param / hwt_param
+
+  // compute_fudge (src/recryption.cpp:154-197): the v-coefficients of the recryption are not quite uniform
+  static double compute_fudge(long p2ePrime, long p2e) {
+    double eps = 0;
+    if (p2ePrime > 1) {
+      if (p2ePrime % 2 == 0) eps = 1.0 / ((double)p2ePrime * (double)p2ePrime);
+      else eps = 1.0 / (double)p2e;
+    }
+    return 1 + eps;
+  }
+  static long ipow(long b, long e) { long r = 1; while (e-- > 0) r *= b; return r; }
+  // RecryptData::setAE (src/recryption.cpp:200-256) with Context::boundForRecryption (include/helib/Context.h:616-638)
+  void set_ae(long& e, long& ePrime, long skHwt, double scale) const {
+    long k = 0; { long mm = m; for (long f = 2; f * f <= mm; f++) if (mm % f == 0) { k++; while (mm % f == 0) mm /= f; } if (mm > 1) k++; }
+    const double mrat = (double)phim / (double)m;
+    const double stddev = std::sqrt(mrat * (double)skHwt * (double)(1L << k) / 3.0) * 0.5;
+    const double coeff_bound = 0.5 + scale * stddev;
+    long p2r = ipow(p, r);
+    const long frstTerm = 2 * p2r + 2;
+    long e_bnd = 0, p2e_bnd = 1;
+    while (p2e_bnd <= ((1L << 30) - 2) / p) { e_bnd++; p2e_bnd *= p; }   // largest e with p^e + 1 < 2^30
+    ePrime = 0;
+    e = r + 1;
+    while (e <= e_bnd && (double)ipow(p, e) < frstTerm * coeff_bound * 2) e++;
+    if (e > e_bnd) throw std::runtime_error("setAE: cannot find suitable e");
+    long ePrimeTry = 1;
+    while (ePrimeTry <= e_bnd) {
+      const long p2ePrimeTry = ipow(p, ePrimeTry);
+      long eTry = std::max(r + 1, ePrimeTry + 1);
+      while (eTry <= e_bnd && eTry - ePrimeTry < e - ePrime) {
+        const long p2eTry = ipow(p, eTry);
+        const double fudge = compute_fudge(p2ePrimeTry, p2eTry);
+        if ((double)p2eTry >= ((double)p2ePrimeTry * fudge + frstTerm) * coeff_bound * 2) break;
+        eTry++;
+      }
+      if (eTry <= e_bnd && eTry - ePrimeTry < e - ePrime) { e = eTry; ePrime = ePrimeTry; }
+      ePrimeTry++;
+    }
+  }
+
+  void build(long bits, long nDgts, long skHwt, long resolution, long bitsInSpecial, double stdev, bool bootstrappable = false, double scale = 10.0) {
     if (bits <= 0) throw std::invalid_argument("Cannot initialise modulus chain with nBits < 1");
     if (skHwt < 0) throw std::invalid_argument("invalid skHwt parameter");
+    if (ckks) bootstrappable = false;                       // src/Context.cpp:1051-1052
+    if (skHwt == 0 && bootstrappable) skHwt = 120;          // BOOT_DFLT_SK_HWT = MIN_SK_HWT (include/helib/Context.h:34-35)
+    hwt_param = skHwt;
     // ---- addSmallPrimes
     long cp = ctxt_prime_size(bits);
     if (m <= 0 || m > (1 << 20)) throw std::runtime_error("addSmallPrimes: m undefined or larger than 2^20");
@@ -151,6 +195,12 @@ struct hb_chain {
     long p2r = 1;
     if (!ckks) for (long i = 0; i < r; i++) p2r *= pabs;
     long p2e = p2r;
+    if (bootstrappable && !ckks) {   // bigger p^e for bootstrapping (src/Context.cpp:885-897)
+      long e, ePrime;
+      set_ae(e, ePrime, skHwt, scale);
+      p2e *= ipow(pabs, e - ePrime);
+      e_param = e; ePrime_param = ePrime;
+    }
     std::vector<int> ctxt = of_kind(1);
     long nCtxt = (long)ctxt.size();
     if (nDgts > nCtxt) nDgts = nCtxt;
@@ -250,6 +300,17 @@ extern "C" const char* hb_chain_last_error(void) { return g_chain_err.c_str(); }
 
 extern "C" int hb_chain_build(hb_chain** out, uint64_t m, int64_t p, int r, int bits, int c, int sk_hwt, int resolution,
                               int bits_in_special, double stdev) {
+  return hb_chain_build_ex(out, m, p, r, bits, c, sk_hwt, resolution, bits_in_special, stdev, 0, 10.0);
+}
+extern "C" int hb_chain_recrypt_params(const hb_chain* ch, int64_t* e, int64_t* e_prime, int64_t* sk_hwt) {
+  if (!ch) return HB_ERR_BAD_ARG;
+  if (e) *e = ch->e_param;
+  if (e_prime) *e_prime = ch->ePrime_param;
+  if (sk_hwt) *sk_hwt = ch->hwt_param;
+  return HB_OK;
+}
+extern "C" int hb_chain_build_ex(hb_chain** out, uint64_t m, int64_t p, int r, int bits, int c, int sk_hwt, int resolution,
+                                 int bits_in_special, double stdev, int will_be_bootstrappable, double scale) {
   if (!out) return HB_ERR_BAD_ARG;
   std::unique_ptr<hb_chain> ch(new hb_chain());
   try {
@@ -259,7 +320,7 @@ extern "C" int hb_chain_build(hb_chain** out, uint64_t m, int64_t p, int r, int 
     if (!ch->ckks && (p < 2 || m % (uint64_t)p == 0)) throw std::invalid_argument("Modulus pp divides mm");  // src/PAlgebra.cpp:458
     if (ch->ckks && !ch->pow2) throw std::invalid_argument("CKKS requires m to be a power of two");
     ch->phim = euler_phi((long)m);
-    ch->build(bits, c, sk_hwt, resolution, bits_in_special, stdev > 0 ? stdev : 3.2);
+    ch->build(bits, c, sk_hwt, resolution, bits_in_special, stdev > 0 ? stdev : 3.2, will_be_bootstrappable != 0, scale > 0 ? scale : 10.0);
   } catch (const std::exception& e) {
     g_chain_err = e.what();
     return HB_ERR_BAD_ARG;

@@ -350,14 +350,15 @@ class Engine:
 class Chain:
     """Host-side prime chain (hb_chain): helib::Context::buildModChain reproduced in C++."""
 
-    def __init__(self, m, p, r, bits, c, sk_hwt=0, resolution=3, bits_in_special=0, stdev=3.2, lib=None):
+    def __init__(self, m, p, r, bits, c, sk_hwt=0, resolution=3, bits_in_special=0, stdev=3.2, lib=None, bootstrappable=False, scale=10.0):
         self.lib = lib if lib is not None else load_library()
         self.lib.hb_chain_last_error.restype = C.c_char_p
         self.lib.hb_chain_destroy.restype = None
         self.lib.hb_chain_destroy.argtypes = [C.c_void_p]
         self.h = C.c_void_p()
-        rc = self.lib.hb_chain_build(C.byref(self.h), C.c_uint64(m), C.c_int64(p), int(r), int(bits), int(c),
-                                     int(sk_hwt), int(resolution), int(bits_in_special), C.c_double(stdev))
+        rc = self.lib.hb_chain_build_ex(C.byref(self.h), C.c_uint64(m), C.c_int64(p), int(r), int(bits), int(c),
+                                        int(sk_hwt), int(resolution), int(bits_in_special), C.c_double(stdev),
+                                        int(bool(bootstrappable)), C.c_double(scale))
         if rc != 0:
             raise HbError(rc, self.lib.hb_chain_last_error().decode())
         n = [C.c_int() for _ in range(5)]
@@ -374,6 +375,9 @@ class Chain:
         self.ctxt = [i for i in range(npr) if kind[i] == 1]
         self.special = [i for i in range(npr) if kind[i] == 2]
         self.digits = [[i for i in range(npr) if dig[i] == d] for d in range(n[4].value)]
+        e, ep, hw = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.hb_chain_recrypt_params(self.h, C.byref(e), C.byref(ep), C.byref(hw))
+        self.e_param, self.e_prime_param, self.sk_hwt = e.value, ep.value, hw.value
 
     def __del__(self):
         try:

@@ -18,6 +18,13 @@ typedef struct hb_chain hb_chain;
  * include/helib/Context.h:1067-1087).  Bootstrappable chains are not supported. */
 int hb_chain_build(hb_chain** out, uint64_t m, int64_t p, int r, int bits, int c, int sk_hwt, int resolution,
                    int bits_in_special, double stdev);
+/* The same with ContextBuilder::bootstrappable(): will_be_bootstrappable != 0 (ignored for CKKS) sets the default secret-key
+ * weight to BOOT_DFLT_SK_HWT = 120 when sk_hwt == 0 and sizes the special primes for p^(r + e - e') with (e, e') from
+ * RecryptData::setAE (src/Context.cpp:885-897, src/recryption.cpp:200-256); scale = Context::scale (10 by default). */
+int hb_chain_build_ex(hb_chain** out, uint64_t m, int64_t p, int r, int bits, int c, int sk_hwt, int resolution,
+                      int bits_in_special, double stdev, int will_be_bootstrappable, double scale);
+/* Context::e_param / ePrime_param (0 unless bootstrappable) and hwt_param. */
+int hb_chain_recrypt_params(const hb_chain* ch, int64_t* e, int64_t* e_prime, int64_t* sk_hwt);
 void hb_chain_destroy(hb_chain* ch);
 const char* hb_chain_last_error(void);
 int hb_chain_info(const hb_chain* ch, int* nprimes, int* nsmall, int* nctxt, int* nspecial, int* ndigits, int64_t* phim);

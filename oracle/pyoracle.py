@@ -158,6 +158,8 @@ class Chain:
     ctxt: list = field(default_factory=list)
     special: list = field(default_factory=list)
     digits: list = field(default_factory=list)     # list of lists of indices
+    e_param: int = 0                               # Context::e_param / ePrime_param (bootstrappable chains)
+    e_prime_param: int = 0
 
     @property
     def ckks(self) -> bool:
@@ -181,16 +183,65 @@ class Chain:
         return s
 
 
+def compute_fudge(p2e_prime: int, p2e: int) -> float:
+    """compute_fudge (src/recryption.cpp:154-197)."""
+    eps = 0.0
+    if p2e_prime > 1:
+        eps = 1.0 / (float(p2e_prime) * float(p2e_prime)) if p2e_prime % 2 == 0 else 1.0 / float(p2e)
+    return 1 + eps
+
+
+def set_ae(m: int, p: int, r: int, sk_hwt: int, scale: float = 10.0):
+    """RecryptData::setAE (src/recryption.cpp:200-256) -> (e, e'); the bound is Context::boundForRecryption
+    (include/helib/Context.h:616-638): 0.5 + scale * sqrt(phi(m)/m * hwt * 2^k / 3) / 2, k = #prime factors of m."""
+    phim = euler_phi(m)
+    k, mm, f = 0, m, 2
+    while f * f <= mm:
+        if mm % f == 0:
+            k += 1
+            while mm % f == 0:
+                mm //= f
+        f += 1
+    if mm > 1:
+        k += 1
+    coeff_bound = 0.5 + scale * (math.sqrt((phim / m) * sk_hwt * (1 << k) / 3.0) * 0.5)
+    p2r = p ** r
+    frst = 2 * p2r + 2
+    e_bnd, p2e_bnd = 0, 1
+    while p2e_bnd <= ((1 << 30) - 2) // p:
+        e_bnd += 1
+        p2e_bnd *= p
+    e_prime, e = 0, r + 1
+    while e <= e_bnd and p ** e < frst * coeff_bound * 2:
+        e += 1
+    if e > e_bnd:
+        raise RuntimeError("setAE: cannot find suitable e")
+    t = 1
+    while t <= e_bnd:
+        p2t = p ** t
+        e_try = max(r + 1, t + 1)
+        while e_try <= e_bnd and e_try - t < e - e_prime:
+            if p ** e_try >= (p2t * compute_fudge(p2t, p ** e_try) + frst) * coeff_bound * 2:
+                break
+            e_try += 1
+        if e_try <= e_bnd and e_try - t < e - e_prime:
+            e, e_prime = e_try, t
+        t += 1
+    return e, e_prime
+
+
 def build_mod_chain(m: int, p: int, r: int, bits: int, c: int, *, sk_hwt: int = 0,
                     resolution: int = 3, bits_in_special: int = 0,
-                    bootstrappable: bool = False, stdev: float = 3.2) -> Chain:
+                    bootstrappable: bool = False, stdev: float = 3.2, scale: float = 10.0) -> Chain:
     """Context::buildModChain (src/Context.cpp:1037-1070) =
     addSmallPrimes (:728-790) + addCtxtPrimes (:845-872) + addSpecialPrimes (:874-1035).
     p = -1 selects CKKS (m must then be a power of two)."""
     if bits <= 0:
         raise ValueError("Cannot initialise modulus chain with nBits < 1")
-    if bootstrappable and p != -1:
-        raise NotImplementedError("bootstrappable chains (RecryptData::setAE) are out of scope")
+    if p == -1:
+        bootstrappable = False                  # src/Context.cpp:1051-1052
+    if sk_hwt == 0 and bootstrappable:
+        sk_hwt = 120                            # BOOT_DFLT_SK_HWT (include/helib/Context.h:34-35)
     ch = Chain(m=m, p=p, r=r, phim=euler_phi(m))
     ckks = p == -1
 
@@ -247,6 +298,10 @@ def build_mod_chain(m: int, p: int, r: int, bits: int, c: int, *, sk_hwt: int = 
     phim = ch.phim
     p2r = 1 if ckks else pabs ** r
     p2e = p2r
+    if bootstrappable and not ckks:             # bigger p^e for bootstrapping (src/Context.cpp:885-897)
+        e, e_prime = set_ae(m, pabs, r, sk_hwt, scale)
+        p2e *= pabs ** (e - e_prime)
+        ch.e_param, ch.e_prime_param = e, e_prime
     ndg = c
     if ndg > len(ch.ctxt):
         ndg = len(ch.ctxt)

@@ -38,6 +38,47 @@ def test_chain_matches_python_restatement(lib, name):
     assert ch.phim == ref.phim
 
 
+BOOT = {
+    "thinboot_m21845": (21845, 2, 1, 580, 2),     # tests/GTestThinBootstrapping.cpp:102 (BASELINE config 5)
+    "boot_m4369": (4369, 2, 1, 400, 3),
+    "boot_p17_m105": (105, 17, 1, 300, 2),
+    "boot_p17r2_m45": (45, 17, 2, 200, 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BOOT))
+def test_bootstrappable_chain_matches_python_restatement(lib, name):
+    """ContextBuilder::bootstrappable(): default key weight 120, (e, e') from RecryptData::setAE, special primes sized for
+    p^(r+e-e') (src/Context.cpp:885-897, src/recryption.cpp:200-256): product C++ == Python restatement, and the branch
+    actually changes the chain."""
+    m, p, r, bits, c = BOOT[name]
+    ref = po.build_mod_chain(m, p, r, bits, c, bootstrappable=True)
+    ch = Chain(m, p, r, bits, c, lib=lib, bootstrappable=True)
+    assert ch.primes == ref.primes and ch.special == ref.special and ch.digits == ref.digits
+    assert (ch.e_param, ch.e_prime_param, ch.sk_hwt) == (ref.e_param, ref.e_prime_param, 120)
+    plain = Chain(m, p, r, bits, c, lib=lib)
+    assert [ch.primes[i] for i in ch.ctxt] == [plain.primes[i] for i in plain.ctxt]
+    logp = lambda chn: sum(math.log2(chn.primes[i]) for i in chn.special)
+    assert logp(ch) > logp(plain) + (ch.e_param - ch.e_prime_param) * math.log2(p) - 6   # the special primes absorb p^(e-e')
+
+
+def test_set_ae_satisfies_the_recryption_inequality():
+    """Appendix A of ia.cr/2014/873 as the reference states it (src/recryption.cpp:139-150):
+    (f*p^e' + 2*p^r + 2)*B <= p^e/2, with e - e' as small as the search allows."""
+    for m, p, r in [(21845, 2, 1), (105, 2, 1), (4369, 2, 1), (105, 17, 1), (45, 17, 2), (57, 7, 1)]:
+        e, ep = po.set_ae(m, p, r, 120)
+        phim = po.euler_phi(m)
+        k = len({f for f in range(2, m + 1) if m % f == 0 and all(f % g for g in range(2, int(f ** 0.5) + 1))})
+        B = 0.5 + 10.0 * math.sqrt(phim / m * 120 * (1 << k) / 3.0) * 0.5
+        assert e > ep >= 0 and e >= r + 1
+        if ep > 0:
+            assert p ** e >= (p ** ep * po.compute_fudge(p ** ep, p ** e) + 2 * p ** r + 2) * B * 2
+        else:
+            assert p ** e >= (2 * p ** r + 2) * B * 2
+    ckks = Chain(1 << 13, -1, 1, 119, 2, bootstrappable=True)   # ignored for CKKS (src/Context.cpp:1051-1052)
+    assert ckks.e_param == 0 and ckks.primes == Chain(1 << 13, -1, 1, 119, 2).primes
+
+
 def test_survey_shapes():
     """SURVEY.md section 8 header: the shapes the reference's chain logic yields."""
     ch = po.build_mod_chain(1 << 17, -1, 1, 1190, 2)
