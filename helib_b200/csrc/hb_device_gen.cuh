@@ -124,6 +124,41 @@ __global__ void __launch_bounds__(HB_THREADS) k_conv_plain(const HbPrimeDev* __r
   }
 }
 
+// Canonical-embedding norm for general m: basic_embeddingLargestCoeff (src/norms.cpp:129-157) -- max over i in Z_m^*, i <= m/2,
+// of |sum_k f_k W^(ik)|, W = e^(2 pi I/m) -- evaluated directly in FP64 (phi(m)^2/2 multiply-adds per polynomial: ~1.3e8 for
+// m = 21845, tens of microseconds of the B200's FP64 rate; no length-m FFT plan needed).  W is a host-built table of m entries.
+struct HbGenNormJob { u64 m, phim; const double* frac; const double2* W; const int* rep; unsigned long long* maxbits; };
+__global__ void __launch_bounds__(HB_THREADS) k_gen_norm(HbGenNormJob J) {
+  HB_SMEM_DECL
+  double* F = (double*)HB_SMEM;   // [1024] tile of the coefficients
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double* f = J.frac + (size_t)blockIdx.y * J.phim;
+  const u64 i = t < J.phim ? (u64)J.rep[t] : 0;
+  const bool live = t < J.phim && 2 * i <= J.m;   // i and m - i give conjugate values
+  double re = 0, im = 0;
+  u64 idx = 0;   // i*k mod m
+  for (size_t k0 = 0; k0 < J.phim; k0 += 1024) {
+    __syncthreads();
+    for (size_t k = threadIdx.x; k < 1024; k += blockDim.x) F[k] = k0 + k < J.phim ? f[k0 + k] : 0.0;
+    __syncthreads();
+    if (live) {
+      const size_t kn = J.phim - k0 < 1024 ? J.phim - k0 : 1024;
+      for (size_t k = 0; k < kn; k++) {
+        const double2 w = J.W[idx];
+        re += F[k] * w.x; im += F[k] * w.y;
+        idx += i; if (idx >= J.m) idx -= J.m;
+      }
+    }
+  }
+  double mx = live ? re * re + im * im : 0.0;
+#ifdef HB_SIM
+  unsigned long long bits; memcpy(&bits, &mx, 8);
+  if (bits > J.maxbits[blockIdx.y]) J.maxbits[blockIdx.y] = bits;
+#else
+  atomicMax(J.maxbits + blockIdx.y, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order like integers
+#endif
+}
+
 // automorphism for general m: new[j] = old[idx(rep(j)*k mod m)] (src/DoubleCRT.cpp:1160-1202)
 struct HbGenAutoJob { u64 m, phim, k; const int* rep; const int* irep; HbRows rows; int nitems; const u64* src[HB_MAXB]; u64* dst[HB_MAXB]; };
 __global__ void __launch_bounds__(HB_THREADS) k_gen_automorph(HbGenAutoJob J) {

@@ -94,6 +94,7 @@ struct hb_ctx {
     HbGenPrime* d_gp = nullptr;
     HbPrimeDev* d_primes_cyc = nullptr;
     void* tab = nullptr;
+    double2* d_W = nullptr;                             // e^(2 pi I j/m), j < m (embedding norms; built on first use)
     u64 *w0 = nullptr, *w1 = nullptr, *wt = nullptr;   // [HB_MAXB][nprimes][L]
     u64 *cA = nullptr, *cB = nullptr;                   // [HB_MAXB][nprimes][phim]
   } gen;
@@ -312,6 +313,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   cudaFree(c->pw.d_cube_to_poly); cudaFree(c->pw.d_short_to_long); cudaFree(c->pw.cube); cudaFree(c->pw.rows);
   cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max); cudaFree(c->d_bcast);
   cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
+  cudaFree(c->gen.d_W);
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
   for (HbTmap* sl : c->tmap_slabs) cudaFree(sl);
@@ -1073,18 +1075,40 @@ static int gen_inv(hb_ctx* c, const u64* const* src, u64* const* dst, int nit, c
   return gen_k(c, HB_GEN_FIN, 0, nullptr, dst, nit, idx, n);
 }
 // exact conversion on coefficient rows: rows src of polys -> x mod q_t as evaluation rows tgt in cB
-static int gen_conv(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p) {
+static int gen_conv(hb_ctx* c, u64* const* polys, int nit, const int32_t* src, int n, const int32_t* tgt, int nt, u64 p, bool want_frac = false) {
+  if (want_frac) HB_TRY(norm_scratch(c));
   ConvEntry* E; HB_TRY(get_conv(c, src, n, tgt, nt, p, &E));
   u64 *A[HB_MAXB], *B[HB_MAXB];
   for (int i = 0; i < nit; i++) { A[i] = c->gen.cA + (size_t)i * c->nprimes * c->N; B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N; }
   HB_TRY(gen_inv(c, (const u64* const*)polys, A, nit, src, n));
   HbPlainConvJob J; memset(&J, 0, sizeof(J));
   J.cv = E->d; J.t = E->d_t; J.t_s = E->d_t_s; J.N = c->N; J.nitems = nit; J.stats = c->d_stats;
-  for (int i = 0; i < nit; i++) { J.src[i] = A[i]; J.dst[i] = B[i]; }
+  for (int i = 0; i < nit; i++) { J.src[i] = A[i]; J.dst[i] = B[i]; if (want_frac) J.frac[i] = c->d_frac + (size_t)i * c->N; }
   pre_launch(c);
   HB_LAUNCH(k_conv_plain, dim3((unsigned)((c->N + HB_THREADS - 1) / HB_THREADS), nit), dim3(HB_THREADS), 0, c->stream, c->d_primes, J);
   HB_TRY(post_launch(c, "k_conv_plain", (u64)(n + nt) * nit * c->N * 8));
   return gen_fwd(c, (const u64* const*)B, B, nit, tgt, nt);
+}
+
+// general m: max over Z_m^* of |f(W^i)| for the nit fraction polynomials in c->d_frac -> out[0..nit)   (synchronises)
+static int gen_norm_chunk(hb_ctx* c, int nit, double* out) {
+  hb_ctx::Gen& g = c->gen;
+  if (!g.d_W) {
+    std::vector<double2> W(g.m);
+    for (u64 j = 0; j < g.m; j++) { const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)g.m; W[j].x = (double)cosl(a); W[j].y = (double)sinl(a); }
+    HB_TRY(ctx_alloc(c, (void**)&g.d_W, sizeof(double2) * g.m));
+    HB_CUDA(cudaMemcpy(g.d_W, W.data(), sizeof(double2) * g.m, cudaMemcpyHostToDevice));
+  }
+  HB_CUDA(cudaMemsetAsync(c->d_max, 0, nit * sizeof(unsigned long long), c->stream));
+  HbGenNormJob J; J.m = g.m; J.phim = g.phim; J.frac = c->d_frac; J.W = g.d_W; J.rep = g.d_rep; J.maxbits = c->d_max;
+  pre_launch(c);
+  HB_LAUNCH(k_gen_norm, dim3((unsigned)((g.phim + HB_THREADS - 1) / HB_THREADS), nit), dim3(HB_THREADS), 1024 * sizeof(double), c->stream, J);
+  HB_TRY(post_launch(c, "k_gen_norm", (u64)nit * g.phim * 8));
+  unsigned long long bits[HB_MAXB];
+  HB_CUDA(cudaMemcpyAsync(bits, c->d_max, nit * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nit; i++) { double m2; memcpy(&m2, &bits[i], 8); out[i] = std::sqrt(m2); }
+  return HB_OK;
 }
 
 static int gen_init(hb_ctx* c, const uint64_t* psi) {
@@ -1273,13 +1297,18 @@ static int add_primes_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimes"));
   if (ncur == 0) return hb_zero_rows(polys, nitems, add, nadd);  // src/DoubleCRT.cpp:577-583
   if (c->gen.on) {
-    if (log_norms) return hb_fail(HB_ERR_UNSUPPORTED, "embedding norms are only computed for power-of-two m");
+    double logQg = 0; for (int j = 0; j < ncur; j++) logQg += std::log((double)c->q[cur[j]]);
     return for_items(nitems, [&](int i0, int nit) {
       u64* P[HB_MAXB]; u64* B[HB_MAXB]; ptrs_of(polys, i0, nit, P);
       for (int i = 0; i < nit; i++) B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N;
-      HB_TRY(gen_conv(c, P, nit, cur, ncur, add, nadd, 1));
+      HB_TRY(gen_conv(c, P, nit, cur, ncur, add, nadd, 1, log_norms != nullptr));
       PwArgs A; memset(&A, 0, sizeof(A)); A.op = HB_PW_COPY; A.dst = P; A.a = (const u64* const*)B;
-      return launch_pw(c, A, nit, add, nadd);
+      HB_TRY(launch_pw(c, A, nit, add, nadd));
+      if (log_norms) {   // basic_embeddingLargestCoeff (src/norms.cpp:129-157) of x/Q, then + ln Q
+        double mm[HB_MAXB]; HB_TRY(gen_norm_chunk(c, nit, mm));
+        for (int i = 0; i < nit; i++) log_norms[i0 + i] = (mm[i] > 0 ? std::log(mm[i]) : -INFINITY) + logQg;
+      }
+      return HB_OK;
     });
   }
   HB_TRY(ctx_scratch(c));
@@ -1317,13 +1346,14 @@ static int scale_down_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   if (kept.empty()) return hb_fail(HB_ERR_INDEX_SET, "scaleDownToSet: s and the index set must have some intersection");  // :1474-1476
   std::vector<u64> sc; HB_TRY(scalars_by_primes(c, kept.data(), (int)kept.size(), diff.data(), (int)diff.size(), 1, sc));
   if (c->gen.on) {
-    if (norms) return hb_fail(HB_ERR_UNSUPPORTED, "embedding norms are only computed for power-of-two m");
     return for_items(nitems, [&](int i0, int nit) {
       u64* P[HB_MAXB]; u64* B[HB_MAXB]; ptrs_of(polys, i0, nit, P);
       for (int i = 0; i < nit; i++) B[i] = c->gen.cB + (size_t)i * c->nprimes * c->N;
-      HB_TRY(gen_conv(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space));
+      HB_TRY(gen_conv(c, P, nit, diff.data(), (int)diff.size(), kept.data(), (int)kept.size(), ptxt_space, norms != nullptr));
       PwArgs A; memset(&A, 0, sizeof(A)); A.op = HB_PW_SUBSCALE; A.dst = P; A.a = (const u64* const*)B; A.scal = sc.data();
-      return launch_pw(c, A, nit, kept.data(), (int)kept.size());
+      HB_TRY(launch_pw(c, A, nit, kept.data(), (int)kept.size()));
+      if (norms) HB_TRY(gen_norm_chunk(c, nit, norms + i0));
+      return HB_OK;
     });
   }
   HB_TRY(ctx_scratch(c));

@@ -654,9 +654,18 @@ def embedding_largest_coeff(coeffs, m: int):
     :204-261 max over j in Z_m^* of |f(zeta^j)|, zeta = e^(2 pi i/m)).  Returns (mantissa, log2 factor):
     norm = mantissa * 2^shift, as the reference returns an xdouble."""
     import numpy as np
-    n = m // 2
     size = max((abs(int(c)).bit_length() for c in coeffs), default=0)
     shift = max(0, size - 400)
+    if m & (m - 1):
+        # general m: basic_embeddingLargestCoeff (src/norms.cpp:129-157): length-m DFT of the zero-padded coefficients,
+        # max of |.| over i in Z_m^*, 1 <= i <= m/2
+        ff = np.zeros(m)
+        for i, c in enumerate(coeffs):
+            ff[i] = float(int(c) >> shift) if c >= 0 else -float((-int(c)) >> shift)
+        vals = np.fft.fft(ff)
+        idx = [i for i in range(1, m // 2 + 1) if math.gcd(i, m) == 1]
+        return float(np.max(np.abs(vals[idx]))), shift
+    n = m // 2
     ff = np.array([float(int(c) >> shift) if c >= 0 else -float((-int(c)) >> shift) for c in coeffs] + [0.0] * (n - len(coeffs)))
     k = np.arange(n)
     tw = np.exp(1j * np.pi * k / n)                 # zeta^k, zeta = e^(i pi / n)

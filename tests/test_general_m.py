@@ -135,6 +135,35 @@ def test_general_m_doublecrt_ops(lib, cfg):
         acc = [a + e * scale for a, e in zip(acc, Ei)]
         scale *= ch.product(ch.digits[dnum])
     assert [po.bal(a, ch.product(S)) for a in acc] == poly
+    # noise metadata for general m: basic_embeddingLargestCoeff (src/norms.cpp:129-157) next to the integer
+    # results -- breakIntoDigits (ln of each digit's norm), addPrimes and scaleDownToSet (norm of delta / P).  FP64, rel. tol 1e-9.
+    import math
+    from fractions import Fraction
+    P2 = E.poly(P.download(S), S)
+    digs2, lognorms = E.break_into_digits_norm([P2], S)
+    for dnum, D in enumerate(digs2[0]):
+        dset = [i for i in S if i in ch.digits[dnum]]
+        drow = D.download(dset)
+        Ei = GenD({i: [int(v) for v in drow[i]] for i in dset}).to_poly(dset)
+        mant, shift = po.embedding_largest_coeff(Ei, m)
+        ref_log = math.log(mant) + shift * math.log(2.0)
+        assert abs(lognorms[0, dnum] - ref_log) <= 1e-9 * abs(ref_log) + 1e-9, (dnum, lognorms[0, dnum], ref_log)
+    y = {i: [rnd.randrange(ch.primes[i]) for _ in range(n)] for i in Sp}
+    Yp = E.poly(dense(ch, y), Sp)
+    norms = E.scale_down_norm([Yp], Sp, S, p)
+    dl = GenD(y).to_poly(ch.special)
+    for k_, d in enumerate(dl):
+        u = d % p
+        if u:
+            u = u * pinv % p
+            if u > p // 2 or (p % 2 == 0 and u == p // 2 and d < 0):
+                u -= p
+            dl[k_] = d - Pd * u
+    ff = np.zeros(m)
+    ff[:n] = [float(Fraction(d, Pd)) for d in dl]          # fdelta = delta / diffProd (src/Ctxt.cpp:482-485)
+    vals = np.fft.fft(ff)
+    want_n = float(np.max(np.abs(vals[[i for i in range(1, m // 2 + 1) if math.gcd(i, m) == 1]])))
+    assert abs(norms[0] - want_n) <= 1e-9 * want_n, (norms[0], want_n)
     # automorph: F(X) -> F(X^k)
     k = [t for t in range(2, m) if np.gcd(t, m) == 1][1]
     D = E.poly()
