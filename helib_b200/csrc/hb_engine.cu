@@ -1816,15 +1816,30 @@ extern "C" int hb_automorph_keyswitch_digits(hb_poly* const* digits, int maxdig,
                                              hb_poly* const* out0, hb_poly* const* out1) {
   hb_ctx* c = nullptr; HB_TRY(check_polys(c0, nitems, &c, "hb_automorph_keyswitch_digits"));
   HB_TRY(check_idx(c, S, nS, "hb_automorph_keyswitch_digits"));
-  if (c->gen.on) return hb_fail(HB_ERR_UNSUPPORTED, "hoisted automorphisms are only built for power-of-two m");
-  if ((k & 1) == 0 || k >= c->m) return hb_fail(HB_ERR_INDEX_SET, "automorph: k not in Zm*");
+  if (k == 0 || k >= c->m || h_gcd((long)k, (long)c->m) != 1) return hb_fail(HB_ERR_INDEX_SET, "automorph: k not in Zm*");
+  if (ndig <= 0 || ndig > maxdig) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph_keyswitch_digits: ndig=%d out of range", ndig);
   for (int i = 0; i < nitems; i++) if (c0[i] == out0[i] || c0[i] == out1[i]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph_keyswitch_digits: outputs must not alias c0");
   for (int i = 0; i < nitems * maxdig; i++) for (int j = 0; j < nitems; j++) if (digits[i] == out0[j] || digits[i] == out1[j]) return hb_fail(HB_ERR_BAD_ARG, "hb_automorph_keyswitch_digits: outputs must not alias the digits");
   std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
   std::vector<u64> sc(Sp.size(), 0);
   for (size_t r = 0; r < Sp.size(); r++)
     if (std::find(S, S + nS, Sp[r]) != S + nS) sc[r] = prod_mod(c, c->special.data(), (int)c->special.size(), c->q[Sp[r]]);
-  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, out0, out1, sc.data(), k, c0);
+  if (c->gen.on) {
+    // general m: sigma_k is a gather over Z_m^* (src/DoubleCRT.cpp:1160-1202), applied to the digits and to c0 in scratch
+    // polynomials (the digits themselves stay reusable for the next amount), then the same inner product
+    HB_TRY(check_polys(digits, nitems * maxdig, &c, "hb_automorph_keyswitch_digits(digits)"));
+    std::vector<hb_poly*> tmp; HB_TRY(pool_get(c, nitems * ndig, tmp));
+    std::vector<hb_poly*> col(nitems), dcol(nitems);
+    for (int i = 0; i < ndig; i++) {
+      for (int it = 0; it < nitems; it++) { col[it] = tmp[(size_t)it * ndig + i]; dcol[it] = digits[(size_t)it * maxdig + i]; }
+      HB_TRY(hb_automorph(col.data(), dcol.data(), nitems, Sp.data(), (int)Sp.size(), k));
+    }
+    HB_TRY(hb_automorph(out0, c0, nitems, S, nS, k));
+    HB_TRY(hb_zero_rows(out1, nitems, Sp.data(), (int)Sp.size()));
+    return keyswitch_digits_impl(tmp.data(), ndig, ndig, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, out0, out1, sc.data(), 0, nullptr, nullptr, nullptr);
+  }
+  if ((k & 1) == 0) return hb_fail(HB_ERR_INDEX_SET, "automorph: k not in Zm*");
+  return keyswitch_digits_impl(digits, maxdig, ndig, nitems, Sp.data(), (int)Sp.size(), evk_a, evk_b, out0, out1, sc.data(), k, c0, nullptr, nullptr);
 }
 // scal (optional, [n]): out = scal[r]*out + sum (0 => out = sum): addPrimesAndScale folded in.
 // autok != 0: digits and c0 are read through the automorphism sigma_autok (hoisting), out0/out1 are pure outputs.

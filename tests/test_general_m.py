@@ -173,6 +173,26 @@ def test_general_m_doublecrt_ops(lib, cfg):
     cur = P.download(S)
     for i in S:
         assert [int(v) for v in got[i]] == [int(cur[i][rep.index(rep[j] * k % m)]) for j in range(n)]
+    # hoisting for general m (BasicAutomorphPrecon::automorph, src/matmul.cpp:112-184): one breakIntoDigits, then per amount
+    # sigma_k on the digits and on c0 + the evk inner product == the same steps done one by one through the engine
+    full = sorted(ch.ctxt + ch.special)
+    nd = len(digs)
+    evk = [E.poly(dense(ch, {i: [rnd.randrange(ch.primes[i]) for _ in range(n)] for i in full}), full) for _ in range(2 * nd)]
+    c0rows = {i: [rnd.randrange(ch.primes[i]) for _ in range(n)] for i in S}
+    C0 = E.poly(dense(ch, c0rows), S)
+    for kk in [t for t in range(2, m) if np.gcd(t, m) == 1][:2] + [m - 1]:
+        O0, O1 = E.poly(), E.poly()
+        E.automorph_keyswitch_digits([digs], S, [C0], kk, evk[:nd], evk[nd:], [O0], [O1])
+        R0, R1 = E.poly(), E.poly()
+        E.automorph([R0], [C0], S, kk)
+        E.add_primes_and_scale([R0], S, ch.special)
+        rot = []
+        for D in digs:
+            T = E.poly()
+            E.automorph([T], [D], full, kk)
+            rot.append(T)
+        E.keyswitch_digits([rot], full, evk[:nd], evk[nd:], [R0], [R1])
+        assert (O0.download(full)[full] == R0.download(full)[full]).all() and (O1.download(full)[full] == R1.download(full)[full]).all(), kk
 
 
 @pytest.mark.gpu
