@@ -522,30 +522,18 @@ struct Hb1ConvJob {
   double* frac[HB_MAXB];   // optional x/Q per coefficient for the embedding norm
 };
 
-// COLS = 4: 64-thread groups (named barriers), one 20-warp CTA per SM.  COLS = 2: a group is ONE warp (2 columns x 16, __syncwarp),
-// half-size tiles, so two CTAs fit an SM -- the same resident warps, but a CTA with few target rows (the prime-sharded path: each
-// rank converts to its own rows only) no longer leaves the rest of the SM idle while its few groups work.
-template <int COLS> struct Hb1ConvGeom {
-  static constexpr int CBS = COLS == 4 ? HB1C_BS : 280;    // column stride: 2*276 mod 32 = 8 (4 cols x 4 rows) / 280 mod 16 = 8 (2 cols x 8 rows)
-  static constexpr int TS = COLS * CBS;                     // u64 per row tile
-  static constexpr int VS = COLS == 4 ? HB1_VS : 264;      // column stride of the quotient tile
-  static constexpr int GT = 16 * COLS;                      // threads per group
-};
-template <bool SP, int COLS>
-__global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_conv(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb1ConvJob J) {
+template <bool SP>
+__global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb1ConvJob J) {
   HB_SMEM_DECL
   const HbConvDev* cv = J.cv;
   const int n = cv->n, nt = cv->nt, NG = J.ngroups;
-  typedef Hb1ConvGeom<COLS> G;
-  constexpr int CBS = G::CBS, TS = G::TS, VS = G::VS, GT = G::GT;
-  u64* Y = HB_SMEM;                               // [n][TS]
-  i64* Vb = (i64*)(Y + (size_t)n * TS);           // [COLS][VS]  index c*VS + i1 (padded: the columns of a half-warp hit different banks)
-  u64* W = (u64*)(Vb + COLS * VS);                // [NG][TS]
+  u64* Y = HB_SMEM;                               // [n][HB1_TS]
+  i64* Vb = (i64*)(Y + (size_t)n * HB1_TS);       // [4][HB1_VS]  index c*HB1_VS + i1 (padded: the 4 columns of a half-warp hit different banks)
+  u64* W = (u64*)(Vb + 4 * HB1_VS);               // [NG][HB1_TS]
   const int tid = threadIdx.x;
-  const int grp = tid / GT, gt = tid % GT;
-  const int c = gt % COLS, x = gt / COLS;         // x in [0,16)
-  const unsigned c0 = blockIdx.x * COLS;
-  auto gsync = [&]() { if (COLS == 2) __syncwarp(); else hb_group_sync(grp, GT); };
+  const int grp = tid >> 6, gt = tid & 63;
+  const int c = gt & 3, x = gt >> 2;              // x in [0,16)
+  const unsigned c0 = blockIdx.x << 2;
   const u64* src = J.src[blockIdx.y];
   u64* dst = J.dst[blockIdx.y];
 
@@ -555,7 +543,7 @@ __global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_c
     const HbPrimeDev P = primes[pi];
     const u64 q = P.q; HB1_MOD(M, P);
     const u64* s = src + ((size_t)pi << J.logN) + c0 + c;
-    u64* Yj = Y + (size_t)j * TS + c * CBS;
+    u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS;
     u64 a[16];
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = s[(size_t)(16 * x + l) << 8];
@@ -571,7 +559,7 @@ __global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_c
     }
 #pragma unroll
     for (int l = 0; l < 16; l++) Yj[HB1_RS * x + l] = a[l];
-    gsync();
+    hb_group_sync(grp, 64);
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = Yj[HB1_RS * r + x];
     {
@@ -585,16 +573,16 @@ __global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_c
   }
   __syncthreads();
   // ---- v (multiple of Q to subtract, incl. the BGV correction) per coefficient
-  for (int e = tid; e < 256 * COLS; e += blockDim.x) {
+  for (int e = tid; e < 1024; e += blockDim.x) {
     const int cc = e >> 8, i1 = e & 255;
     double* fr = J.frac[blockIdx.y];
     double f;
-    Vb[cc * VS + i1] = hb_conv_v(cv, Y + cc * CBS + HB1_RS * (i1 >> 4) + (i1 & 15), TS, J.stats, fr ? &f : nullptr);
+    Vb[cc * HB1_VS + i1] = hb_conv_v(cv, Y + cc * HB1C_BS + HB1_RS * (i1 >> 4) + (i1 & 15), HB1_TS, J.stats, fr ? &f : nullptr);
     if (fr) fr[((size_t)i1 << 8) + c0 + cc] = f;
   }
   __syncthreads();
   // ---- targets: x mod q_t in registers, forward cols phase, store
-  u64* Wg = W + (size_t)grp * TS + c * CBS;
+  u64* Wg = W + (size_t)grp * HB1_TS + c * HB1C_BS;
   for (int t = grp; t < nt; t += NG) {
     const int pi = cv->tgt_prime[t];
     const HbPrimeDev P = primes[pi];
@@ -608,14 +596,14 @@ __global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_c
         u64 ahi[8], alo[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-          const i64 v = Vb[c * VS + 16 * (8 * h + r) + x];
+          const i64 v = Vb[c * HB1_VS + 16 * (8 * h + r) + x];
           const u64 m = v >= 0 ? (u64)v : (u64)(-v);
           const u64 f = v >= 0 ? negq : posq;
           alo[r] = m * f; ahi[r] = __umul64hi(m, f);
         }
         for (int j = 0; j < n; j++) {
           const u64 cj = ct[j];
-          const u64* Yj = Y + (size_t)j * TS + c * CBS + x + HB1_RS * 8 * h;
+          const u64* Yj = Y + (size_t)j * HB1_TS + c * HB1C_BS + x + HB1_RS * 8 * h;
 #pragma unroll
           for (int r = 0; r < 8; r++) hb1_mac128(ahi[r], alo[r], Yj[HB1_RS * r], cj);
         }
@@ -628,10 +616,10 @@ __global__ void __launch_bounds__(COLS == 4 ? 640 : 320, COLS == 4 ? 1 : 2) k1_c
       tw.p[0] = P.fw + 1; tw.p[1] = P.fw + 2; tw.p[2] = P.fw + 4; tw.p[3] = P.fw + 8;
       hb1_r16_fwd<SP>(a, tw, M);
     }
-    gsync();   // previous target's pass-2 reads of Wg are complete
+    hb_group_sync(grp, 64);   // previous target's pass-2 reads of Wg are complete
 #pragma unroll
     for (int r = 0; r < 16; r++) Wg[HB1_RS * r + x] = a[r];
-    gsync();
+    hb_group_sync(grp, 64);
 #pragma unroll
     for (int l = 0; l < 16; l++) a[l] = Wg[HB1_RS * x + l];
     {

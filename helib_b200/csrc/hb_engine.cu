@@ -294,10 +294,8 @@ static int ctx_build(hb_ctx* c, hb_ctx** out, int device, uint64_t m, int nprime
   HB_CUDA(cudaFuncSetAttribute(k2_inv_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB2_SMEM_BYTES));
   HB_CUDA(cudaFuncSetAttribute(k1_conv1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_conv1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  HB_CUDA(cudaFuncSetAttribute((k1_conv<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  HB_CUDA(cudaFuncSetAttribute((k1_conv<false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  HB_CUDA(cudaFuncSetAttribute((k1_conv<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-  HB_CUDA(cudaFuncSetAttribute((k1_conv<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  HB_CUDA(cudaFuncSetAttribute(k1_conv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_fwd_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   HB_CUDA(cudaFuncSetAttribute(k1_inv_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
@@ -954,32 +952,14 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
       double score = balance * (0.5 + 0.5 * warps / 20.0) * (ctas >= 2 ? 1.15 : 1.0);
       if (score > best) { best = score; ng = g; smem1 = sm; }
     }
-    // two-column variant (a group = one warp, two CTAs per SM): HB_CONV_COLS=2
-    static const int conv_cols = [] { const char* e = getenv("HB_CONV_COLS"); return e && e[0] == '2' ? 2 : 4; }();
-    if (conv_cols == 2) {
-      typedef Hb1ConvGeom<2> G2;
-      int g2 = std::min(10, (int)(((227 * 1024 - 2 * 1024) / 2 / sizeof(u64) - 2 * G2::VS) / G2::TS) - n);
-      if (g2 >= 4) {
-        g2 = std::min(g2, std::max(4, nt));   // no more warps than target rows (idle warps only cost registers)
-        const size_t sm2 = ((size_t)(n + g2) * G2::TS + 2 * G2::VS) * sizeof(u64);
-        Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
-        J1.cv = E->d; J1.logN = c->logN; J1.ngroups = g2; J1.nitems = nit; J1.stats = c->d_stats; J1.src_is_y = src_is_y;
-        if (want_frac) for (int i = 0; i < nit; i++) J1.frac[i] = c->d_frac + (size_t)i * c->N;
-        for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
-        pre_launch(c);
-        if (all_special(c)) HB_LAUNCH((k1_conv<true, 2>), dim3(128, nit), dim3(32 * g2), sm2, c->stream, c->d_primes, J1);
-        else HB_LAUNCH((k1_conv<false, 2>), dim3(128, nit), dim3(32 * g2), sm2, c->stream, c->d_primes, J1);
-        return post_launch(c, "k1_conv", (u64)(n + nt) * nit * c->N * 8);
-      }
-    }
     if (ng > 0) {
       Hb1ConvJob J1; memset(&J1, 0, sizeof(J1));
       J1.cv = E->d; J1.logN = c->logN; J1.ngroups = ng; J1.nitems = nit; J1.stats = c->d_stats; J1.src_is_y = src_is_y;
       if (want_frac) for (int i = 0; i < nit; i++) J1.frac[i] = c->d_frac + (size_t)i * c->N;
       for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }
       pre_launch(c);
-      if (all_special(c)) HB_LAUNCH((k1_conv<true, 4>), dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
-      else HB_LAUNCH((k1_conv<false, 4>), dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+      if (all_special(c)) HB_LAUNCH(k1_conv<true>, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
+      else HB_LAUNCH(k1_conv<false>, dim3(64, nit), dim3(64 * ng), smem1, c->stream, c->d_primes, J1);
       return post_launch(c, "k1_conv", (u64)(n + nt) * nit * c->N * 8);
     }
   }
