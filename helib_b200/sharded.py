@@ -32,8 +32,13 @@ def owner_map(ctxt, special, world):
 
 
 class ShardedKeySwitch:
-    def __init__(self, eng, ctxt, special, digits, rank=None, world=None, device="cuda", p2p=False):
+    def __init__(self, eng, ctxt, special, digits, rank=None, world=None, device="cuda", p2p=False, group=None):
+        """group (optional): a torch.distributed process group -- the rows are sharded over ITS ranks only (rank / world are then
+        the rank and size inside the group), so a box can run several independent prime-sharded groups side by side."""
         self.E = eng
+        self.group = group
+        if group is not None:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.ctxt, self.special, self.digits = list(ctxt), list(special), [list(d) for d in digits]
@@ -54,7 +59,7 @@ class ShardedKeySwitch:
             if self.p2p:   # engine-owned buffer, exported to / imported from every peer (collective: same key order on all ranks)
                 mine = self.E.poly()
                 handles = [None] * self.world
-                dist.all_gather_object(handles, self.E.ipc_export(mine))
+                dist.all_gather_object(handles, self.E.ipc_export(mine), group=self.group)
                 peers = [self.E.ipc_open(h) for r, h in enumerate(handles) if r != self.rank]
                 self._bufs[key] = (None, mine, peers)
             else:
@@ -69,7 +74,7 @@ class ShardedKeySwitch:
             npeer = self.world - 1
             peers = [[y[2][p] for y in ys] for p in range(npeer)]
             E.conv_make_y_bcast(polys, D, self.owned(D), [y[1] for y in ys], peers)
-            dist.all_reduce(self._flag)          # stream-ordered cross-rank barrier: all peers' stores have landed
+            dist.all_reduce(self._flag, group=self.group)          # stream-ordered cross-rank barrier: all peers' stores have landed
         else:
             E.conv_make_y(polys, D, self.owned(D), [y[1] for y in ys])
             self._all_gather_rows([y[0] for y in ys], D)
@@ -94,7 +99,7 @@ class ShardedKeySwitch:
         if mine:
             for k, t in enumerate(tensors):
                 send[k, :len(mine)] = t.index_select(0, rowt[self.rank])
-        dist.all_gather_into_tensor(flat, send.view(-1))
+        dist.all_gather_into_tensor(flat, send.view(-1), group=self.group)
         recv = flat.view((self.world,) + tuple(send.shape))
         for r in range(self.world):
             if r == self.rank or not per[r]:

@@ -53,7 +53,12 @@ def main():
     evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
     p = 1 if ch.p == -1 else ch.p ** ch.r
     p2p = len(sys.argv) > 3 and sys.argv[3] == "p2p"
-    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, device=device, p2p=p2p)
+    gsz = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # > 0: independent prime-sharded groups of gsz ranks side by side
+    group = None
+    if gsz and gsz < world:
+        groups = [dist.new_group(list(range(i, i + gsz))) for i in range(0, world, gsz)]
+        group = groups[rank // gsz]
+    KS = ShardedKeySwitch(E, ch.ctxt, ch.special, ch.digits, device=device, p2p=p2p, group=group)
     own_full = KS.owned(full)
     EA = [E.poly(evk_a[i], own_full) for i in range(nd)]   # evk sharded identically: only owned rows uploaded
     EB = [E.poly(evk_b[i], own_full) for i in range(nd)]

@@ -10,9 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "mp", "sharded_worker.py")
 
 
-def run(backend, world, cfg, port, mode="gather"):
+def run(backend, world, cfg, port, mode="gather", group_size=0):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, backend, cfg, mode]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, backend, cfg, mode, str(group_size)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
@@ -23,6 +23,11 @@ def run(backend, world, cfg, port, mode="gather"):
 @pytest.mark.parametrize("world,cfg,port", [(2, "64,257,1,120,2", 29611), (3, "4096,17,1,160,3", 29612)])
 def test_sharded_keyswitch_gloo_sim(sim_lib, world, cfg, port):
     run("sim", world, cfg, port)
+
+
+def test_sharded_keyswitch_in_independent_groups_gloo_sim(sim_lib):
+    """Four ranks as two prime-sharded groups of two (the grouping bench.py reports next to the pure sharding)."""
+    run("sim", 4, "64,257,1,120,2", 29618, "gather", group_size=2)
 
 
 def test_owner_map_balances_digits():
