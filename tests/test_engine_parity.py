@@ -379,6 +379,26 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
         assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
 
 
+def test_tma_inverse_blk_kernel(lib, monkeypatch):
+    """k2_inv_blk (TMA-staged inverse blk phase, HB_INV_V2=1; the cp.async kernel is the default for the inverse direction):
+    transform round trip and a full mod-down through it, bit-exact against the oracle."""
+    monkeypatch.setenv("HB_INV_V2", "1")
+    cfg = (1 << 17, 257, 1, 230, 2)
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    rng = np.random.default_rng(77)
+    S, Sp = ch.ctxt, sorted(ch.ctxt + ch.special)
+    x = O.random(rng, Sp)
+    P = E.poly(x, Sp)
+    E.ntt_inv([P], Sp)
+    ref = x.copy(); O.ntt_inv_rows(ref, Sp)
+    assert rows_equal(P.download(Sp), ref, Sp)
+    E.ntt_fwd([P], Sp)
+    assert rows_equal(P.download(Sp), x, Sp)
+    E.scale_down([P], Sp, S, ch.p ** ch.r)
+    O.scale_down(x, Sp, S, ch.p ** ch.r)
+    assert rows_equal(P.download(S), x, S)
+
+
 def test_single_source_conversion_kernel(lib, monkeypatch):
     """Mod-downs that drop ONE prime (no plaintext correction: the CKKS rescale) run through the dedicated
     kernel k1_conv1 (default; HB_CONV1=0 disables it); results must equal the oracle's scaleDownToSet bit for bit -- dropping a 60-bit ctxt prime, a special
