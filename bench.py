@@ -202,6 +202,63 @@ def bench_keyswitch_block(args, np, torch, dist, local, rank, world, peak):
     return out
 
 
+def bench_general_m_block(np, torch, local):
+    """BASELINE config 5's ring (m = 21845, phi(m) = 16384, Bluestein rows of length 2^16; p=2, bits=580, c=2 as
+    tests/GTestThinBootstrapping.cpp:102, bootstrappable chain): row transforms/s, relinearise + mod-down/s and hoisted
+    rotations/s of the DoubleCRT layer underneath recryption (the linear maps and digit extraction of thinReCrypt are callers
+    above the boundary).  Rank 0 only."""
+    from helib_b200 import Chain, Engine
+    m, p, r, bits, c = 21845, 2, 1, 580, 2
+    ch = Chain(m, p, r, bits, c, bootstrappable=True)
+    E = Engine(m, ch.primes, None, ch.digits, ch.special, device=local)
+    N, npr = E.N, E.np
+    S, full = ch.ctxt, ch.ctxt + ch.special
+    Sp = sorted(full)
+    nd = len(ch.digits)
+    rng = np.random.Generator(np.random.Philox(20260922 + 5))
+    B = 8
+
+    def rand(idx):
+        out = np.zeros((npr, N), dtype=np.uint64)
+        for i in idx:
+            out[i] = rng.integers(0, ch.primes[i], size=N, dtype=np.uint64)
+        return out
+
+    EA = [E.poly(rand(full), full) for _ in range(nd)]
+    EB = [E.poly(rand(full), full) for _ in range(nd)]
+    C = [[E.poly(rand(S), S) for _ in range(3)] for _ in range(B)]
+    C0, C1, C2 = ([x[k] for x in C] for k in range(3))
+    O0, O1 = [E.poly() for _ in range(B)], [E.poly() for _ in range(B)]
+
+    def timed(fn, steps):
+        for _ in range(2):
+            fn()
+        E.sync()
+        E.mark_begin()
+        for _ in range(steps):
+            fn()
+        return E.mark_end() / steps
+
+    t_f = timed(lambda: E.ntt_fwd(C0, S), 5)
+    t_i = timed(lambda: E.ntt_inv(C0, S), 5)
+
+    def ks():
+        E.relinearize(C0, C1, C2, S, EA, EB)
+        E.scale_down(C0 + C1, Sp, S, p)
+    t_ks = timed(ks, 3)
+    digs = E.break_into_digits(C1, S)
+    k = next(t for t in range(2, m) if np.gcd(t, m) == 1)
+    t_rot = timed(lambda: E.automorph_keyswitch_digits(digs, S, C0, k, EA, EB, O0, O1), 3)
+    rows = B * len(S)
+    out = {"workload": "bgv_m21845_p2_bits580_c2_bootstrappable", "m": m, "phim": N, "bluestein_length": 65536, "e": ch.e_param, "e_prime": ch.e_prime_param,
+           "primes": {"ctxt": len(S), "special": len(ch.special), "digits": nd}, "batch": B,
+           "fwd_rows_per_s": rows / (t_f / 1e3), "inv_rows_per_s": rows / (t_i / 1e3),
+           "relin_moddown_per_s": B / (t_ks / 1e3), "hoisted_rotations_per_s": B / (t_rot / 1e3),
+           "ms": {"fwd": t_f, "inv": t_i, "relin_moddown": t_ks, "hoisted_rotation": t_rot}}
+    del EA, EB, C, C0, C1, C2, O0, O1, digs
+    return out
+
+
 def bench_sharded_block(args, np, torch, dist, local, rank, world, peak):
     """BASELINE config 4: ONE stream of ciphertexts, every ciphertext's rows sharded by RNS prime index over the ranks
     (helib_b200/sharded.py): key-switches/s (strong scaling), exchange bytes, and a bit-exact check of the rows each rank
@@ -621,6 +678,12 @@ def main():
         sharded = bench_sharded_block(args, np, torch, dist if world > 1 else None, local, rank, world, peak)
     if rank != 0:
         return _leave(world)
+    general_m = None
+    if not args.no_ks:
+        try:
+            general_m = bench_general_m_block(np, torch, local)
+        except Exception as ex:   # a secondary block must not take the headline line down
+            general_m = {"error": f"{type(ex).__name__}: {ex}"}
     st = st_mult
     bmul = alg_bytes_per_mult(l_in, l, K, d)
     cpu = None
@@ -638,7 +701,7 @@ def main():
         "alg_roofline": {"achieved_GBps": value / world * bmul / 1e9, "peak_GBps": peak, "frac": value / world * bmul / 1e9 / peak, "peak_kind": peak_kind},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
         "exact_crt_fallbacks": st["exact_fallbacks"],
-        "keyswitch": ks, "sharded_keyswitch": sharded,
+        "keyswitch": ks, "sharded_keyswitch": sharded, "general_m": general_m,
     }
     print(json.dumps(line))
     _leave(world)
