@@ -8,10 +8,17 @@
 // and GMP >= 6.2.0 are fetched by URL at configure time: CMakeLists.txt:75-77,241) and its
 // tests hold no golden integer vectors for this path.  This file
 // restates the reference's algorithms function by function (citations are paths relative
-// to /root/reference); it is pinned by oracle/pyoracle.py (Python big-int arithmetic) and
-// the psi-independent algebraic invariants in tests/.  Two *inputs* are "parity unpinned"
-// (psi per prime, and the PRG-derived a_i rows of a key-switching matrix): both are taken
-// as arguments.
+// to /root/reference) and is pinned three ways (tests/test_oracle.py):
+//   * against oracle/pyoracle.py (Python big-int arithmetic) and psi-independent invariants;
+//   * against REFERENCE OUTPUT: the rows a real HElib build wrote into its own I/O fixtures
+//     tests/test_resources/iotest_* (tests/golden/helib_iotest_m12.json) -- secret key, public
+//     key and four key-switching matrices whose a_i are regenerated from the stored prgSeed
+//     (oracle/ntl_prg.py + randomize), and the key-switch path (breakIntoDigits,
+//     keySwitchDigits, addPrimesAndScale, scaleDownToSet, toPoly) run with the reference's own
+//     matrices decrypts correctly under the fixture's secret key.
+// Still "parity unpinned": the choice of the 2N-th root psi for power-of-two m (NTL's root
+// tables; an argument of the engine and of this oracle) and the prime chain of modern
+// parameter sets (restated, never compared with primes printed by HElib).
 //
 // Threading mirrors the reference: across primes for the transforms
 // (src/DoubleCRT.cpp:79-84) and across coefficients for the CRT (src/DoubleCRT.cpp:1062-1102).

@@ -10,18 +10,19 @@ CUDA engine on small cases.  Every function cites the reference file:line
 whose semantics it restates (paths relative to /root/reference).
 
 Parity status: the reference publishes no golden integer vectors for this
-path and cannot be built here (NTL/GMP not vendored),
-so two inputs are "parity unpinned": the per-prime 2N-th root psi (NTL derives
-it from its PRG, src/CModulus.cpp:93-98,118-119) and the pseudo-random a_i
-rows of a key-switching matrix (NTL PRG, src/Ctxt.cpp:196-206).  Both are
-taken as *inputs* by the engine.  Everything else is a pure function of
-(primes, psi, inputs) and is pinned by this restatement plus the
-psi-independent algebraic invariants in tests/.
+path and cannot be built here (NTL/GMP not vendored).
 
-Pinned by reference output: the general-m conventions (FindPrimitiveRoot root,
-row order over Z_m^*) reproduce the evaluation-form rows a real HElib build
-wrote into the reference's own fixtures tests/test_resources/iotest_ascii*.txt
-(tests/golden/helib_iotest_m12.json, tests/test_oracle.py).
+Pinned by reference output (tests/test_oracle.py over tests/golden/helib_iotest_m12.json,
+the rows a real HElib build wrote into tests/test_resources/iotest_*):
+  * the general-m conventions (FindPrimitiveRoot root, row order over Z_m^*): secret-key and
+    public-key rows invert to one ternary polynomial / one small multiple of p on every prime;
+  * NTL's PRG stream (oracle/ntl_prg.py), DoubleCRT::randomize and the key-switching formula
+    (src/keys.cpp:1239-1242): the a_i of four stored matrices are regenerated from their prgSeed;
+  * breakIntoDigits / keySwitchDigits / addPrimesAndScale / scaleDownToSet / toPoly / automorph:
+    a ciphertext relinearised and rotated with the REFERENCE's matrices decrypts correctly.
+Still "parity unpinned": the per-prime 2N-th root psi for power-of-two m (NTL derives it from
+its root tables, src/CModulus.cpp:93-98,118-119; an input of the engine) and the prime chain of
+modern parameter sets (two restatements by the same reader, never compared with HElib's output).
 """
 from __future__ import annotations
 
