@@ -428,6 +428,12 @@ struct Hb1ColsJob {
   int nitems;
   const u64* src[HB_MAXB];
   u64* dst[HB_MAXB];
+  // inverse phase of the prime-sharded conversion (hb_conv_make_y[_bcast]): the final factor is scal[row] (= N^-1 * (Q_D/q_j)^-1,
+  // Shoup companion in scal_s) instead of N^-1, and every result is also stored into the same place of up to 8 peer GPUs' buffers
+  // (CUDA-IPC mappings, the stores travel over NVLink): the y rows cross the fabric once, straight from the producing kernel
+  int has_scal, npeers;
+  u64 scal[HB_MAXROWS], scal_s[HB_MAXROWS];
+  u64* peer[8][HB_MAXB];
 };
 
 // "cols" phases for n1 = 8 (N = 2^16): tile [256][16 columns].  grid = (16, nrows, item-groups).
@@ -498,8 +504,14 @@ __global__ void __launch_bounds__(256, 2) k1_inv_cols(const HbPrimeDev* __restri
 #pragma unroll
     for (int r = 0; r < 16; r++) a[r] = T[c * HB1_BS + HB1_RS * r + x];
     hb1_r16_inv<SP>(a, tw1, M);
+    const u64 fm = J.has_scal ? J.scal[blockIdx.y] : P.ninv, fs = J.has_scal ? J.scal_s[blockIdx.y] : P.ninv_s;
 #pragma unroll
-    for (int r = 0; r < 16; r++) dst[(size_t)(16 * r + x) << 8] = hb_mul_shoup(a[r], P.ninv, P.ninv_s, q);
+    for (int r = 0; r < 16; r++) {
+      const u64 v = hb_mul_shoup(a[r], fm, fs, q);
+      const size_t o = (size_t)(16 * r + x) << 8;
+      dst[o] = v;
+      for (int p = 0; p < J.npeers; p++) J.peer[p][it][rowoff + c0 + c + o] = v;
+    }
     __syncthreads();
   }
 }

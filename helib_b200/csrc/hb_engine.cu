@@ -694,7 +694,9 @@ static int launch_blk_v2(hb_ctx* c, int dir, const u64* const* src, u64* const* 
   }
   return HB_OK;
 }
-static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n) {
+// scal (inverse only, optional): per-row factor that replaces N^-1 (the caller folds N^-1 in); peers / npeers: extra destinations
+static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const* dst, int nitems, const int32_t* idx, int n,
+                          const u64* scal = nullptr, u64* const* const* peers = nullptr, int npeers = 0) {
   const size_t smem = (16 * HB1_BS + 8) * sizeof(u64);
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
     int nr = std::min(HB_MAXROWS, n - r0);
@@ -703,11 +705,14 @@ static int launch_cols_v1(hb_ctx* c, int dir, const u64* const* src, u64* const*
     fill_rows(J.rows, idx + r0, nr);
     J.nitems = nitems;
     for (int i = 0; i < nitems; i++) { J.src[i] = src[i]; J.dst[i] = dst[i]; }
+    if (scal) { J.has_scal = 1; for (int i = 0; i < nr; i++) { J.scal[i] = scal[r0 + i]; J.scal_s[i] = h_shoup(scal[r0 + i], c->q[idx[r0 + i]]); } }
+    J.npeers = npeers;
+    for (int p = 0; p < npeers; p++) for (int i = 0; i < nitems; i++) J.peer[p][i] = peers[p][i];
     dim3 grid(16, nr, pick_item_groups(c, 16L * nr, nitems));
     pre_launch(c);
     const bool sp = all_special(c);
     if (dir > 0) { if (sp) HB_LAUNCH(k1_fwd_cols<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_fwd_cols<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_fwd_cols", (u64)2 * nr * nitems * c->N * 8)); }
-    else { if (sp) HB_LAUNCH(k1_inv_cols<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_inv_cols<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, "k1_inv_cols", (u64)2 * nr * nitems * c->N * 8)); }
+    else { if (sp) HB_LAUNCH(k1_inv_cols<true>, grid, dim3(256), smem, c->stream, c->d_primes, J); else HB_LAUNCH(k1_inv_cols<false>, grid, dim3(256), smem, c->stream, c->d_primes, J); HB_TRY(post_launch(c, npeers ? "k1_inv_cols_bcast" : "k1_inv_cols", (u64)(2 + npeers) * nr * nitems * c->N * 8)); }
   }
   return HB_OK;
 }
@@ -1639,6 +1644,15 @@ extern "C" int hb_conv_make_y(hb_poly* const* polys, int nitems, const int32_t* 
     sc[k] = h_powmod(r, q - 2, q);   // (Q_D / q_j)^-1 mod q_j   (src/DoubleCRT.cpp:1033-1041)
   }
   HB_TRY(ctx_scratch(c));
+  if (v1_cols_ok(c)) {   // the scaling rides on the N^-1 multiplication of the inverse cols phase
+    std::vector<u64> f(nOwned);
+    for (int k = 0; k < nOwned; k++) f[k] = h_mulmod(sc[k], c->h_primes[owned[k]].ninv, c->q[owned[k]]);
+    return for_items(nitems, [&](int i0, int nit) {
+      u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
+      HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
+      return launch_cols_v1(c, -1, (const u64* const*)tA, Y, nit, owned, nOwned, f.data());
+    });
+  }
   HB_TRY(for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
     HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
@@ -1663,6 +1677,17 @@ extern "C" int hb_conv_make_y_bcast(hb_poly* const* polys, int nitems, const int
     sc[k] = h_powmod(r, q - 2, q);
   }
   HB_TRY(ctx_scratch(c));
+  if (v1_cols_ok(c) && npeers <= 8) {   // one kernel: inverse cols phase, scaling, local + peer stores
+    std::vector<u64> f(nOwned);
+    for (int k = 0; k < nOwned; k++) f[k] = h_mulmod(sc[k], c->h_primes[owned[k]].ninv, c->q[owned[k]]);
+    return for_items(nitems, [&](int i0, int nit) {
+      u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
+      u64* PE[8][HB_MAXB]; u64* const* PEp[8];
+      for (int p = 0; p < npeers; p++) { for (int i = 0; i < nit; i++) PE[p][i] = peer_ypolys[(size_t)p * nitems + i0 + i]->d; PEp[p] = PE[p]; }
+      HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
+      return launch_cols_v1(c, -1, (const u64* const*)tA, Y, nit, owned, nOwned, f.data(), PEp, npeers);
+    });
+  }
   return for_items(nitems, [&](int i0, int nit) {
     u64* P[HB_MAXB]; u64* Y[HB_MAXB]; u64* tA[HB_MAXB]; ptrs_of(polys, i0, nit, P); ptrs_of(ypolys, i0, nit, Y); tmp_ptrs(c, c->tmpA, nit, tA);
     HB_TRY(launch_blk(c, -1, (const u64* const*)P, tA, nit, owned, nOwned, 0, nullptr));
