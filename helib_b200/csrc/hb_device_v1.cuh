@@ -656,6 +656,7 @@ struct Hb1Conv1Job {
   int src_prime, nt;
   int tgt_prime[HB_MAXROWS];
   u64 qs_mod[HB_MAXROWS];      // q_s mod q_t
+  unsigned char nored[HB_MAXROWS];   // q_s <= 7 q_t: y (< q_s) needs no reduction modulo q_t before the lazy forward network
   u64 ninv, ninv_s;            // N^-1 mod q_s (+Shoup): the (Q/q_j)^-1 factor is 1 for a single prime
   const u64* src[HB_MAXB];
   u64* dst[HB_MAXB];
@@ -710,12 +711,13 @@ __global__ void __launch_bounds__(640, 1) k1_conv1(const HbPrimeDev* __restrict_
     HB1_MOD(M, P);
     const u64 adj = P.q - J.qs_mod[t];          // -(q_s mod q_t) mod q_t, in (0, q_t]
     const u64* Yq = Y + (size_t)qd * HB1_TS + c * HB1C_BS + x;
+    const bool nored = J.nored[t] != 0;         // uniform per target: same-size primes (every ctxt / special prime of a chain)
     u64 a[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) {
       const u64 y = Yq[HB1_RS * r];
-      u64 v = y - __umul64hi(y, P.one_s) * P.q;   // y mod q_t, in [0, 2 q_t)
-      if (y > qs_half) v += adj;                  // balanced representative: subtract q_s   -> [0, 3 q_t]
+      u64 v = nored ? y : y - __umul64hi(y, P.one_s) * P.q;   // y < 7 q_t as it is, or y mod q_t in [0, 2 q_t)
+      if (y > qs_half) v += adj;                  // balanced representative: subtract q_s   -> below 8 q_t: fine for the CT network
       a[r] = v;
     }
     {

@@ -934,7 +934,7 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
     const int cq = 2, ng = 10;
     J1.logN = c->logN; J1.ngroups = ng; J1.cq = cq; J1.nitems = nit; J1.src_prime = src[0]; J1.nt = nt;
     const u64 qs = c->q[src[0]];
-    for (int t = 0; t < nt; t++) { J1.tgt_prime[t] = tgt[t]; J1.qs_mod[t] = qs % c->q[tgt[t]]; }
+    for (int t = 0; t < nt; t++) { J1.tgt_prime[t] = tgt[t]; J1.qs_mod[t] = qs % c->q[tgt[t]]; J1.nored[t] = (u128)qs <= (u128)7 * c->q[tgt[t]] ? 1 : 0; }
     u64 ninv; if (!h_invmod(c->N % qs, qs, &ninv)) return hb_fail(HB_ERR_BAD_ARG, "N not invertible");
     J1.ninv = ninv; J1.ninv_s = h_shoup(ninv, qs);
     for (int i = 0; i < nit; i++) { J1.src[i] = tA[i]; J1.dst[i] = tB[i]; }

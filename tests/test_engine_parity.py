@@ -411,6 +411,8 @@ def test_single_source_conversion_kernel(lib, monkeypatch):
     cases = [(ch.ctxt, ch.ctxt[:-1]), (ch.ctxt + ch.special[:1], ch.ctxt)]
     if ch.small:
         cases.append((sorted(ch.small[:1] + ch.ctxt), ch.ctxt))
+        # a 60-bit source with a much smaller target among the kept rows: the only case where y must be reduced modulo q_t
+        cases.append((sorted(ch.small[:1] + ch.ctxt), sorted(ch.small[:1] + ch.ctxt[:-1])))
     for cur, keep in cases:
         x = O.random(rng, cur)
         drop = [i for i in cur if i not in keep][0]
