@@ -391,6 +391,55 @@ def find_psi(q: int, two_n: int) -> int:
     return psi
 
 
+HELIB_ROOT_SEED = 84547180875373941534287406458029      # src/CModulus.cpp:94
+NTL_FFT_MAX_ROOT = 25                                    # NTL_FFTMaxRoot (NTL include/NTL/FFT.h)
+
+
+def ntl_fft_root(q: int, two_n: int) -> int:
+    """The root a real HElib build uses for power-of-two m = two_n: `RootTable[0][log2 m]` of the `zz_pContext(INIT_USER_FFT, q)`
+    it constructs right after `SetSeed(84547180875373941534287406458029)` (src/CModulus.cpp:93-98,118-119).  NTL is not in the
+    reference tree; this restates its published algorithm (NTL src/FFT.cpp `IsFFTPrime` + `InitFFTPrimeInfo`, src/ZZ.cpp
+    `RandomBnd(long)`): write q - 1 = 2^k * t (t odd); draw x = RandomBnd(q) from the seeded stream until x != 0,
+    z = x^t != 1 and z has order exactly 2^k; square it down to order 2^min(k, 25) (= w, RootTable[0][mr]); entry j of the table
+    is w^(2^(mr-j)).  The stream itself (SetSeed / ChaCha20) and RandomBnd's byte consumption are pinned by the reference's
+    key-switching fixtures (oracle/ntl_prg.py, tests/test_oracle.py); the root derivation is restated from memory of NTL's
+    sources and NOT pinned by any reference output (no power-of-two-m row exists in the reference tree): the engine therefore
+    keeps psi an input, and this function is what a shim without NTL would pass."""
+    from ntl_prg import random_bnd, set_seed
+    assert two_n & (two_n - 1) == 0 and (q - 1) % two_n == 0
+    t, k = q - 1, 0
+    while t % 2 == 0:
+        t //= 2
+        k += 1
+    stream = set_seed(HELIB_ROOT_SEED)
+    while True:
+        x = random_bnd(stream, q)
+        if x == 0:
+            continue
+        z = pow(x, t, q)
+        if z == 1:
+            continue
+        x, j = z, 0
+        while True:
+            y = z
+            z = y * y % q
+            j += 1
+            if j == k or z == 1:
+                break
+        if z != 1 or y != q - 1:
+            raise ValueError("not an FFT prime")
+        if j == k:
+            break
+    for _ in range(NTL_FFT_MAX_ROOT, k):
+        x = x * x % q
+    mr = min(k, NTL_FFT_MAX_ROOT)
+    lg = two_n.bit_length() - 1
+    assert lg <= mr, "Roots count exceeds maximum rootTables size"       # src/CModulus.cpp:108-110
+    psi = pow(x, 1 << (mr - lg), q)
+    assert pow(psi, two_n // 2, q) == q - 1
+    return psi
+
+
 def ntt_fwd(coeffs, q: int, psi: int):
     """Cmodulus::FFT pow-2 branch (src/CModulus.cpp:362-429): y[i]=x[i]*psi^i, cyclic
     length-N DFT with omega=psi^2, natural order out => row[j] = f(psi^(2j+1)) mod q."""

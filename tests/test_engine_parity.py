@@ -10,6 +10,7 @@ import pytest
 import orc
 import pyoracle as po
 from common import make, rows_equal, ptxt_space
+from helib_b200.engine import Engine
 
 SMALL = [  # (m, p, r, bits, c)
     (64, 257, 1, 120, 2),      # N=32, single-phase transform
@@ -41,6 +42,31 @@ def test_ntt_rows_match_oracle(lib, cfg):
     assert rows_equal(P.download(allp), ref, allp)
     E.ntt_fwd([P], allp)
     assert rows_equal(P.download(allp), data, allp)   # iNTT(NTT(x)) == x
+
+
+def test_rows_with_the_reference_style_roots(lib):
+    """psi is an input of the engine: with the roots NTL derives under HElib's fixed seed (pyoracle.ntl_fft_root, restating
+    src/CModulus.cpp:93-98 + NTL's IsFFTPrime on the pinned stream) engine and oracle still agree row for row, and the
+    psi-independent results (toPoly) equal the ones computed under the default roots."""
+    cfg = (8192, 257, 1, 160, 2)
+    ch, psis0, O0, E0 = make(lib, *cfg)
+    psis = [po.ntl_fft_root(q, ch.m) for q in ch.primes]
+    assert psis != psis0
+    O = orc.Oracle(ch.phim, ch.m, ch.primes, psis, ch.digits, ch.special, nthreads=4)
+    E = Engine(ch.m, ch.primes, psis, ch.digits, ch.special, lib=lib)
+    assert E.psis == psis
+    rng = np.random.default_rng(9)
+    S = ch.ctxt
+    f = rng.integers(-50, 50, size=ch.phim).astype(np.int64)
+    P = E.poly(); P0 = E0.poly()
+    E.from_i64([P], S, f); E0.from_i64([P0], S, f)
+    ref = O.zeros()
+    for i in S:
+        ref[i] = np.array([int(v) % ch.primes[i] for v in f], dtype=np.uint64)
+    O.ntt_fwd_rows(ref, S)
+    assert rows_equal(P.download(S), ref, S)
+    assert not rows_equal(P.download(S), P0.download(S), S)                        # another root, another evaluation order
+    assert (E.to_poly(P, S) == E0.to_poly(P0, S)).all()                             # the polynomial itself is the same
 
 
 @pytest.mark.parametrize("cfg", SMALL)

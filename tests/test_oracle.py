@@ -369,3 +369,21 @@ def test_keyswitch_path_semantics_pinned_by_reference_evk():
                 mu5[k - (len(phi) - 1) + j] -= ck * pj
             mu5[k] = 0
     assert decrypt(r0, r1, S) == [c % p for c in mu5[:n]]
+
+
+def test_ntl_fft_root_restatement_is_a_valid_deterministic_root():
+    """The root derivation of NTL's zz_pContext(INIT_USER_FFT, q) under HElib's fixed seed (src/CModulus.cpp:93-98), restated on top
+    of the PINNED stream: deterministic, a primitive m-th root for every chain prime, consistent across m (RootTable entries are
+    squares of each other), and usable as the engine/oracle root -- rows computed with it satisfy row[j] = f(psi^(2j+1))."""
+    ch = po.build_mod_chain(1 << 17, -1, 1, 230, 2)
+    for q in ch.primes:
+        psi = po.ntl_fft_root(q, 1 << 17)
+        assert psi == po.ntl_fft_root(q, 1 << 17)
+        assert pow(psi, 1 << 16, q) == q - 1
+        assert po.ntl_fft_root(q, 1 << 16) == psi * psi % q            # RootTable[0][16] = RootTable[0][17]^2
+    q = po.build_mod_chain(64, 257, 1, 120, 2).primes[-1]
+    psi = po.ntl_fft_root(q, 64)
+    f = [3, 1, 4, 1, 5, 9, 2, 6] + [0] * 24
+    row = po.ntt_fwd(f, q, psi)
+    for j in (0, 1, 7, 31):
+        assert row[j] == sum(c * pow(psi, (2 * j + 1) * i, q) for i, c in enumerate(f)) % q
