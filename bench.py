@@ -84,6 +84,31 @@ class ClockSampler:
         return out
 
 
+def bind_near_gpu(gpu):
+    """Run this rank on the CPU cores next to its GPU (sysfs local_cpulist of the GPU's PCI device) before the pinned host
+    buffers are allocated, so first-touch places them on that NUMA node: with 8 ranks streaming 640 MiB per step each, staging
+    buffers on the far socket put the inter-socket link in the H2D path.  Best effort; returns the core list or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        dom, rest = out.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def mult_config(B):
     """The workload both arms are run on (identical dict in `config` of the GPU arm and of --impl reference)."""
     l_in, l, K, d = 20, 19, 10, 2
@@ -511,6 +536,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    near = bind_near_gpu(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -633,7 +660,8 @@ def main():
             ems = float(t.item())
         e2e = {"value": world * B * args.steps / (ems / 1000.0), "unit": "mult/s",
                "h2d_bytes_per_step": B * 4 * len(S_in) * ROW_BYTES, "d2h_bytes_per_step": B * 2 * len(S) * ROW_BYTES,
-               "ms_per_step": ems / args.steps, "streams": len(ctxs), "timing": "host perf_counter around synchronised streams"}
+               "ms_per_step": ems / args.steps, "streams": len(ctxs), "timing": "host perf_counter around synchronised streams",
+               "host_cores_near_gpu": len(near) if near else None}
 
     clocks = sampler.stop() if sampler else {}   # sampled from warm-up through the timed region and the e2e loop
     # ---- per-kernel profile (one extra step bracketed by events per launch) -> roofline
@@ -686,6 +714,10 @@ def main():
             general_m = {"error": f"{type(ex).__name__}: {ex}"}
     st = st_mult
     bmul = alg_bytes_per_mult(l_in, l, K, d)
+    try:
+        os.sched_setaffinity(0, all_cpus)     # the CPU baseline uses every host core
+    except Exception:
+        pass
     cpu = None
     if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
