@@ -2,7 +2,7 @@
 """bench.py -- Ctxt x Ctxt multiply (+ rescale, relinearise, mod-down) throughput on B200.
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): CKKS m=2^17 (N=2^16),
-bits=1190, c=2 -> 20 ctxt + 10 special 60-bit primes ("L~30").  One *step* = one batch of B
+bits=1190, c=2 -> 20 ctxt + 10 special 60-bit primes ("L~30").  One *step* = one batch of B (default 32)
 independent ciphertext pairs through the hot path
     modDownToSet(20 -> 19 ctxt primes) of both operands  ->  tensorProduct  ->  reLinearize
     (breakIntoDigits, keySwitchDigits over 29 rows)  ->  modDownToSet (drop the 10 special primes)
@@ -509,7 +509,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="independent ciphertext pairs per step and GPU")
+    ap.add_argument("--batch", type=int, default=32, help="independent ciphertext pairs per step and GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=48, help="multiplies timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
