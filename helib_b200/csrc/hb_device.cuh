@@ -34,7 +34,7 @@ typedef long long i64;
 
 #define HB_MAXROWS 64   // rows per launch (larger sets are chunked by the host)
 #ifndef HB_MAXB
-#define HB_MAXB 32      // batch items per launch
+#define HB_MAXB 64      // batch items per launch (job descriptors above 4 KB rely on the 32 KB kernel-parameter space of CUDA 12.1+)
 #endif
 #define HB_MAXDIG 8     // digits per key-switching matrix
 #define HB_THREADS 256
