@@ -519,7 +519,7 @@ def main():
     ap.add_argument("--ks-count", type=int, default=1024, help="config 3: ciphertexts resident per GPU (one step switches all of them)")
     ap.add_argument("--ks-group", type=int, default=64, help="config 3: ciphertexts per hb_relinearize / hb_scale_down call")
     ap.add_argument("--ks-steps", type=int, default=3, help="config 3: timed passes over the resident ciphertexts (at most --steps)")
-    ap.add_argument("--sharded-batch", type=int, default=16, help="config 4: ciphertexts per step of the prime-sharded key switch")
+    ap.add_argument("--sharded-batch", type=int, default=32, help="config 4: ciphertexts per step of the prime-sharded key switch")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
