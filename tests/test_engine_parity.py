@@ -405,6 +405,58 @@ def test_hoisted_automorph_keyswitch(lib, cfg):
         assert rows_equal(O0.download(Sp), r0, Sp) and rows_equal(O1.download(Sp), r1, Sp), k
 
 
+@pytest.mark.parametrize("cfg", [(4096, 17, 1, 160, 3), (1 << 17, 257, 1, 230, 2)])
+def test_fused_inner_product_and_mixed_radix_step(lib, cfg):
+    """hb_keyswitch_digits_fused (addPrimesAndScale folded in, own digit rows read from the switched part) and
+    hb_sub_div_by_primes (the mixed-radix step of breakIntoDigits) against the same steps done one by one by the oracle
+    (src/Ctxt.cpp:191-230,764-768; src/DoubleCRT.cpp:551-556)."""
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    rng = np.random.default_rng(41)
+    S, full = ch.ctxt, ch.ctxt + ch.special
+    Sp = sorted(full)
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    c0, c1, c2 = (O.random(rng, S) for _ in range(3))
+    # oracle: digits, scale c0 / c1 up to S | special, inner product
+    digs = O.break_into_digits(c2, S)
+    r0, r1 = c0.copy(), c1.copy()
+    O.add_primes_and_scale(r0, S, ch.special); O.add_primes_and_scale(r1, S, ch.special)
+    O.keyswitch_digits(digs, Sp, evk_a, evk_b, r0, r1)
+    # engine: digit polynomials hold only the EXTENDED rows, the own rows of digit i are read from `own`
+    dsets = [[i for i in S if i in ch.digits[d]] for d in range(nd)]
+    own = O.zeros()
+    D = []
+    for d in range(nd):
+        ext = digs[d].copy()
+        for i in dsets[d]:
+            own[i] = digs[d][i]
+            ext[i] = 0          # must not be read
+        D.append(E.poly(ext, Sp))
+    OWN = E.poly(own, S)
+    P = 1
+    for i in ch.special:
+        P *= ch.primes[i]
+    scal = [P % ch.primes[r] if r in S else 0 for r in Sp]
+    own_dig = [next(d for d in range(nd) if r in dsets[d]) if r in S else -1 for r in Sp]
+    garbage = O.random(rng, ch.special)      # rows with scal == 0 are pure outputs: whatever they held is ignored
+    g0 = c0.copy(); g1 = c1.copy()
+    for i in ch.special:
+        g0[i] = garbage[i]; g1[i] = garbage[i]
+    C0, C1 = E.poly(g0, Sp), E.poly(g1, Sp)
+    E.keyswitch_digits_fused([D], Sp, EA, EB, [C0], [C1], scal, own=[OWN], own_dig=own_dig)
+    assert rows_equal(C0.download(Sp), r0, Sp) and rows_equal(C1.download(Sp), r1, Sp)
+    # mixed-radix step: dst = (dst - src) / prod(digit 0) on the rows of digit 1
+    if nd > 1:
+        a, b = O.random(rng, S), O.random(rng, S)
+        A, B = E.poly(a, S), E.poly(b, S)
+        E.sub_div_by_primes([A], [B], dsets[1], ch.digits[0])
+        ref = a.copy(); O.pointwise("sub", ref, b, dsets[1]); O.scale_by_primes(ref, dsets[1], ch.digits[0], inv=True)
+        assert rows_equal(A.download(dsets[1]), ref, dsets[1])
+
+
 def test_tma_inverse_blk_kernel(lib, monkeypatch):
     """k2_inv_blk (TMA-staged inverse blk phase, HB_INV_V2=1; the cp.async kernel is the default for the inverse direction):
     transform round trip and a full mod-down through it, bit-exact against the oracle."""
