@@ -199,6 +199,7 @@ class Ctxt {
     if (!verifyPrimeSet()) throw LogicError("primeSet is no longer valid");
   }
   void modDownToSet(const IndexSet& s) {   // src/Ctxt.cpp:393-562 ("real mod switching" branch)
+    HB_TIMER_START(context.handle());
     IndexSet intersection = primeSet & s;
     if (empty(intersection)) throw RuntimeError("modDownToSet called with a disjoint set");
     IndexSet setDiff = primeSet / intersection;
@@ -215,6 +216,7 @@ class Ctxt {
     noiseBound = noiseBound / f;
     noiseBound = noiseBound + addedNoise;
     lastModSwitchRatio = (addedNoise / addedNoiseBound).to_double();   // the reference's "mod-switch-added-noise" statistic
+    HB_STATS_UPDATE("mod-switch-added-noise", lastModSwitchRatio);      // src/Ctxt.cpp:537
     primeSet.remove(setDiff);
     if (!verifyPrimeSet()) throw LogicError("primeSet is no longer valid");
   }
@@ -266,6 +268,7 @@ class Ctxt {
   }
   // src/Ctxt.cpp:191-230 -- the two products per digit and their accumulation run as ONE engine launch
   void keySwitchDigits(const KeySwitch& W, std::vector<DoubleCRT>& digits) {
+    HB_NTIMER_START(KS_loop, context.handle());   // src/Ctxt.cpp:205
     long j0 = getPartIndexByHandle(SKHandle()), j1 = getPartIndexByHandle(SKHandle(1, 1, W.toKeyID));
     if (j0 < 0) { parts.emplace_back(DoubleCRT(context, primeSet), SKHandle()); j0 = (long)parts.size() - 1; }
     if (j1 < 0) { parts.emplace_back(DoubleCRT(context, primeSet), SKHandle(1, 1, W.toKeyID)); j1 = (long)parts.size() - 1; }
@@ -276,6 +279,7 @@ class Ctxt {
     check(hb_keyswitch_digits(dg.data(), (int)digits.size(), (int)digits.size(), 1, idx.data(), (int)idx.size(), ea.data(), eb.data(), o0, o1));
   }
   void keySwitchPart(const CtxtPart& p, const KeySwitch& W) {   // src/Ctxt.cpp:805-842
+    HB_TIMER_START(context.handle());
     if (!context.getSpecialPrimes().disjointFrom(p.dcrt.getIndexSet())) throw LogicError("Special primes and CtxtPart's index set have non-empty intersection");
     if (p.skHandle.isOne() || p.skHandle.isBase(W.toKeyID)) {
       CtxtPart pp = p;
@@ -290,9 +294,11 @@ class Ctxt {
     addedNoise = addedNoise * W.noiseBound;
     keySwitchDigits(W, polyDigits);
     lastKSNoiseRatio = (addedNoise / noiseBound).to_double();   // "KS-noise-ratio"
+    HB_STATS_UPDATE("KS-noise-ratio", lastKSNoiseRatio);         // src/Ctxt.cpp:835
     noiseBound = noiseBound + addedNoise;
   }
   void reLinearize(long keyID = 0) {   // src/Ctxt.cpp:720-786
+    HB_TIMER_START(context.handle());
     if (isEmpty() || inCanonicalForm(keyID)) return;
     dropSmallAndSpecialPrimes();
     relin_CKKS_adjust();
@@ -317,6 +323,7 @@ class Ctxt {
     *this = tmp;
   }
   void tensorProduct(const Ctxt& c1, const Ctxt& c2) {   // src/Ctxt.cpp:1563-1608
+    HB_TIMER_START(context.handle());
     parts.clear();
     primeSet = c1.primeSet;
     long ptxtSp = c1.ptxtSpace;
@@ -350,6 +357,7 @@ class Ctxt {
     else { hi = std::min(cap1 + adn1, cap2 + adn2) - safety; lo = hi - slack; }
   }
   void multLowLvl(const Ctxt& other_orig) {   // src/Ctxt.cpp:1681-1753 (non-destructive, distinct operands)
+    HB_TIMER_START(context.handle());
     if (isEmpty()) return;
     if (other_orig.isEmpty()) { *this = other_orig; return; }
     if (isCKKS() != other_orig.isCKKS()) throw LogicError("Scheme mismatch");
@@ -686,6 +694,7 @@ class Ctxt {
     if (!str || std::memcmp(eye, "]CX|", 4) != 0) throw RuntimeError("Could not find post-ciphertext eye catcher");
   }
   void multiplyBy(const Ctxt& other) {   // src/Ctxt.cpp:1757-1774
+    HB_TIMER_START(context.handle());
     if (isEmpty()) return;
     if (other.isEmpty()) { *this = other; return; }
     multLowLvl(other);

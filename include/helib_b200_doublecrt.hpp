@@ -19,6 +19,9 @@
 #include <ostream>
 #include <istream>
 #include <cstring>
+#include <chrono>
+#include <map>
+#include <mutex>
 
 #include "helib_b200.h"
 #include "helib_b200_chain.h"
@@ -38,6 +41,68 @@ inline void check(int rc) {
   if (rc == HB_ERR_UNSUPPORTED) throw LogicError(msg);
   throw RuntimeError(msg);
 }
+
+
+// helib's timers and statistics (include/helib/timing.h:44-128, src/timing.cpp:21-110, include/helib/fhe_stats.h:38-52) under the
+// reference's own names on the host wrappers (FFT, toPoly, addPrimes, breakIntoDigits, scaleDownToSet, KS_loop, reLinearize, ...):
+// getTimerByName / printAllTimers / fhe_stats keep working for a caller that reads them.  Engine calls are asynchronous, so a
+// timer measures real time only in timing mode (setTimersOn(): every timed wrapper synchronises its context before it stops --
+// a profiling mode, like the reference's always-on CPU timers); off by default (call counts only, no synchronisation).
+// Per-kernel device times come from hb_ctx_profile.
+struct FHEtimer {
+  const char* name; const char* loc;
+  long counter = 0;      // microseconds
+  long numCalls = 0;
+  FHEtimer(const char* n, const char* l);
+  double getTime() const { return counter / 1e6; }
+  long getNumCalls() const { return numCalls; }
+};
+inline std::vector<FHEtimer*>& timerMap() { static std::vector<FHEtimer*> v; return v; }
+inline std::mutex& timerMutex() { static std::mutex m; return m; }
+inline FHEtimer::FHEtimer(const char* n, const char* l) : name(n), loc(l) { std::lock_guard<std::mutex> g(timerMutex()); timerMap().push_back(this); }
+inline bool& timersOn() { static bool on = false; return on; }
+inline void setTimersOn() { timersOn() = true; }
+inline void setTimersOff() { timersOn() = false; }
+inline const FHEtimer* getTimerByName(const char* name) {
+  std::lock_guard<std::mutex> g(timerMutex());
+  for (FHEtimer* t : timerMap()) if (std::strcmp(t->name, name) == 0) return t;
+  return nullptr;
+}
+inline void resetAllTimers() { std::lock_guard<std::mutex> g(timerMutex()); for (FHEtimer* t : timerMap()) { t->counter = 0; t->numCalls = 0; } }
+inline void printAllTimers(std::ostream& str) {   // name: total / calls = avg [location]   (src/timing.cpp:92-110)
+  std::lock_guard<std::mutex> g(timerMutex());
+  for (const FHEtimer* t : timerMap())
+    if (t->numCalls > 0)
+      str << "  " << t->name << ": " << t->getTime() << " / " << t->numCalls << " = " << t->getTime() / t->numCalls << "   [" << t->loc << "]\n";
+}
+struct auto_timer {
+  FHEtimer* t; hb_ctx* ctx; std::chrono::steady_clock::time_point t0; bool running;
+  auto_timer(FHEtimer* t_, hb_ctx* c) : t(t_), ctx(c), running(true) { t->numCalls++; if (timersOn()) t0 = std::chrono::steady_clock::now(); }
+  void stop() {
+    if (!running) return;
+    running = false;
+    if (!timersOn()) return;
+    if (ctx) hb_ctx_sync(ctx);
+    t->counter += (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+  ~auto_timer() { stop(); }
+};
+#define HB_STR2(x) #x
+#define HB_STR(x) HB_STR2(x)
+#define HB_AT __FILE__ ":" HB_STR(__LINE__)
+#define HB_TIMER_START(ctx) static hb::FHEtimer _local_timer(__func__, HB_AT); hb::auto_timer _local_auto_timer(&_local_timer, (ctx))
+#define HB_NTIMER_START(n, ctx) static hb::FHEtimer _named_local_timer##n(#n, HB_AT); hb::auto_timer _named_local_auto_timer##n(&_named_local_timer##n, (ctx))
+// HELIB_STATS_UPDATE (include/helib/fhe_stats.h:38-52): gated by the global switch, keeps count / sum / max per name
+struct fhe_stats_record { long count = 0; double sum = 0, max = 0; };
+inline bool& fhe_stats() { static bool on = false; return on; }
+inline std::map<std::string, fhe_stats_record>& fhe_stats_map() { static std::map<std::string, fhe_stats_record> m; return m; }
+inline void stats_update(const char* name, double val) {
+  if (!fhe_stats()) return;
+  std::lock_guard<std::mutex> g(timerMutex());
+  fhe_stats_record& r = fhe_stats_map()[name];
+  r.count++; r.sum += val; if (val > r.max) r.max = val;
+}
+#define HB_STATS_UPDATE(name, val) hb::stats_update((name), (val))
 
 // helib::IndexSet (include/helib/IndexSet.h) restricted to what the hot path uses
 class IndexSet {
@@ -137,6 +202,7 @@ class DoubleCRT {
   // DoubleCRT(zzX poly, context, indexSet): small-coefficient polynomial (DoubleCRT.h:140-151)
   // One copy of the coefficients crosses the bus; the per-prime reduction and the transforms run on the device.
   DoubleCRT(const std::vector<long>& poly, const Context& ctx, const IndexSet& s) : context_(&ctx), set_(s) {
+    HB_NTIMER_START(FFT, ctx.handle());   // DoubleCRT::FFT (src/DoubleCRT.cpp:68-105)
     alloc();
     const long N = ctx.getPhiM();
     if ((long)poly.size() > N) throw InvalidArgument("polynomial degree >= phi(m)");
@@ -176,6 +242,7 @@ class DoubleCRT {
 
   // Op<Add/Sub/Mul> (src/DoubleCRT.cpp:216-337): other must cover this's primes
   DoubleCRT& Op(const DoubleCRT& other, int op, bool matchIndexSets) {
+    HB_TIMER_START(context_->handle());
     if (context_ != other.context_) throw RuntimeError("DoubleCRT::Op: incompatible objects");
     if (matchIndexSets && !(set_ >= other.set_)) throw RuntimeError("DoubleCRT::Op: matchIndexSets not honored");
     if (!(set_ <= other.set_)) throw RuntimeError("DoubleCRT::Op: !(map.getIndexSet() <= other.map.getIndexSet())");
@@ -225,6 +292,7 @@ class DoubleCRT {
   }
   // automorph / complexConj (src/DoubleCRT.cpp:1160-1255)
   void automorph(long k) {
+    HB_TIMER_START(context_->handle());
     DoubleCRT tmp(*this);
     auto idx = set_.vec();
     if (idx.empty()) return;
@@ -235,6 +303,7 @@ class DoubleCRT {
   // removePrimes / addPrimes / addPrimesAndScale (src/DoubleCRT.cpp:565-647)
   void removePrimes(const IndexSet& s) { set_.remove(s); }
   void addPrimes(const IndexSet& s1) {
+    HB_TIMER_START(context_->handle());
     if (empty(s1)) return;
     auto cur = set_.vec(), add = s1.vec();
     hb_poly* d[1] = {p_};
@@ -254,6 +323,7 @@ class DoubleCRT {
   }
   // scaleDownToSet (src/DoubleCRT.cpp:1464-1516)
   void scaleDownToSet(const IndexSet& s, long ptxtSpace) {
+    HB_TIMER_START(context_->handle());
     IndexSet diff = set_ / s;
     if (empty(diff)) return;
     if (ptxtSpace < 1) throw InvalidArgument("ptxtSpace must be at least 1");
@@ -264,6 +334,7 @@ class DoubleCRT {
   }
   // breakIntoDigits (src/DoubleCRT.cpp:479-561); the FP64 noise norm it returns is host metadata (not computed)
   void breakIntoDigits(std::vector<DoubleCRT>& digits) const {
+    HB_TIMER_START(context_->handle());
     const long maxdig = (long)context_->getDigits().size();
     digits.clear();
     IndexSet all = set_ | context_->getSpecialPrimes();
@@ -352,6 +423,7 @@ class DoubleCRT {
   }
   // toPoly (src/DoubleCRT.cpp:925-1113): N x L little-endian two's-complement limbs
   std::vector<uint64_t> toPoly(const IndexSet& s, bool positive, int& L) const {
+    HB_TIMER_START(context_->handle());
     auto idx = (set_ & s).vec();
     L = (int)idx.size() + 1;
     std::vector<uint64_t> out((size_t)context_->getPhiM() * L);

@@ -91,7 +91,16 @@ int main() {
     const double ln2 = std::log(2.0);
     double logq0 = pk.logOfProduct(ca.primeSet);
     // ---- first product: fresh operands, getSet4Size picks a set inside [lo, hi] (may even add small primes)
+    hb::setTimersOn(); hb::fhe_stats() = true;     // the reference's timers / statistics under their own names (src/timing.cpp)
     ca.multiplyBy(cb);
+    hb::setTimersOff();
+    {
+      const hb::FHEtimer* tm = hb::getTimerByName("multiplyBy");
+      const hb::FHEtimer* tk = hb::getTimerByName("KS_loop");
+      const hb::FHEtimer* tr = hb::getTimerByName("reLinearize");
+      if (!tm || !tk || !tr || tm->getNumCalls() != 1 || tk->getNumCalls() < 1 || tm->getTime() <= 0 || tm->getTime() < tr->getTime()) { std::printf("timers: multiplyBy / reLinearize / KS_loop not recorded\n"); return 1; }
+      if (hb::fhe_stats_map().count("KS-noise-ratio") != 1 || hb::fhe_stats_map()["KS-noise-ratio"].count < 1) { std::printf("stats: KS-noise-ratio not recorded\n"); return 1; }
+    }
     if (!ca.inCanonicalForm()) { std::printf("result not canonical\n"); return 1; }
     if (!(ctx.getSpecialPrimes() <= ca.primeSet)) { std::printf("special primes missing after reLinearize\n"); return 1; }
     double logq1 = pk.logOfProduct(ca.lastCommonPrimeSet);
