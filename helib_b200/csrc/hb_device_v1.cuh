@@ -780,3 +780,30 @@ __global__ void __launch_bounds__(256) k1_ks_inner(const HbPrimeDev* __restrict_
     hb1_st2(J.out1[it] + o, hb_reduce128(h1x, l1x, P), hb_reduce128(h1y, l1y, P));
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Ctxt::tensorProduct (src/Ctxt.cpp:1563-1608), streaming form for power-of-two m: two adjacent coefficients per thread,
+// 128-bit loads and stores (the generic k_pointwise moves 8 bytes per access).  Inputs may be lazy (any 64-bit values:
+// the 128-bit products are reduced exactly); outputs canonical.  In place is allowed (every thread reads its four inputs
+// before it writes).     grid = (N / 512, nrows, nitems)
+struct Hb1TensorJob {
+  u64 N;
+  HbRows rows;
+  int nitems;
+  const u64* a0[HB_MAXB]; const u64* a1[HB_MAXB]; const u64* b0[HB_MAXB]; const u64* b1[HB_MAXB];
+  u64* o0[HB_MAXB]; u64* o1[HB_MAXB]; u64* o2[HB_MAXB];
+};
+__global__ void __launch_bounds__(256) k1_tensor(const HbPrimeDev* __restrict__ primes, const HB_GRID_CONSTANT Hb1TensorJob J) {
+  const int pi = J.rows.prime[blockIdx.y];
+  const HbPrimeDev P = primes[pi];
+  const int it = blockIdx.z;
+  const size_t o = (size_t)pi * (size_t)J.N + 2 * ((size_t)blockIdx.x * 256 + threadIdx.x);
+  const ulonglong2 a0 = hb1_ld2(J.a0[it] + o), a1 = hb1_ld2(J.a1[it] + o), b0 = hb1_ld2(J.b0[it] + o), b1 = hb1_ld2(J.b1[it] + o);
+  u64 hx = 0, lx = 0, hy = 0, ly = 0;
+  hb1_mac128(hx, lx, a0.x, b1.x); hb1_mac128(hx, lx, a1.x, b0.x);
+  hb1_mac128(hy, ly, a0.y, b1.y); hb1_mac128(hy, ly, a1.y, b0.y);
+  hb1_st2(J.o0[it] + o, hb_mulmod(a0.x, b0.x, P), hb_mulmod(a0.y, b0.y, P));
+  hb1_st2(J.o1[it] + o, hb_reduce128(hx, lx, P), hb_reduce128(hy, ly, P));
+  hb1_st2(J.o2[it] + o, hb_mulmod(a1.x, b1.x, P), hb_mulmod(a1.y, b1.y, P));
+}
+

@@ -1937,6 +1937,19 @@ extern "C" int hb_tensor(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const*
     u64 *A0[HB_MAXB], *A1[HB_MAXB], *B0[HB_MAXB], *B1[HB_MAXB], *O0[HB_MAXB], *O1[HB_MAXB], *O2[HB_MAXB];
     ptrs_of(a0, i0, nit, A0); ptrs_of(a1, i0, nit, A1); ptrs_of(b0, i0, nit, B0); ptrs_of(b1, i0, nit, B1);
     ptrs_of(o0, i0, nit, O0); ptrs_of(o1, i0, nit, O1); ptrs_of(o2, i0, nit, O2);
+    if (!c->gen.on && c->N % 512 == 0 && !c->force_v0) {   // streaming kernel: 128-bit accesses
+      for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
+        const int nr = std::min(HB_MAXROWS, n - r0);
+        Hb1TensorJob J; memset(&J, 0, sizeof(J));
+        J.N = c->N; J.nitems = nit;
+        fill_rows(J.rows, idx + r0, nr);
+        for (int i = 0; i < nit; i++) { J.a0[i] = A0[i]; J.a1[i] = A1[i]; J.b0[i] = B0[i]; J.b1[i] = B1[i]; J.o0[i] = O0[i]; J.o1[i] = O1[i]; J.o2[i] = O2[i]; }
+        pre_launch(c);
+        HB_LAUNCH(k1_tensor, dim3((unsigned)(c->N / 512), nr, nit), dim3(256), 0, c->stream, c->d_primes, J);
+        HB_TRY(post_launch(c, "k1_tensor", (u64)7 * nr * nit * c->N * 8));
+      }
+      return HB_OK;
+    }
     PwArgs A; memset(&A, 0, sizeof(A));
     A.op = HB_PW_TENSOR; A.dst = O0; A.dst1 = O1; A.dst2 = O2;
     A.a = (const u64* const*)A0; A.b = (const u64* const*)A1; A.cc = (const u64* const*)B0; A.d = (const u64* const*)B1;
