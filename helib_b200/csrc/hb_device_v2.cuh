@@ -22,6 +22,10 @@
 //     16 resident compute warps per SM as two 9-warp CTAs, but 112 registers per thread instead of 96 (register
 //     allocation rounds a 288-thread CTA up to 320).
 //
+// Measured (profiles/r02_summary.md): the forward kernel is 22 % faster than k1_fwd_blk and is the default; the inverse kernel is
+// 1-6 % slower than k1_inv_blk (its natural-order INPUT tile arrives as 256 separate 128-byte rows) and is selected with
+// HB_INV_V2=1 only.  compute-sanitizer memcheck / synccheck / racecheck: clean.
+//
 // smem per team (1024-byte aligned): IN[2][4096] | OUT[4096] | TW1[16][16] | 7 mbarriers  (101 KB; 203 KB per CTA)
 #pragma once
 #include "hb_device_v1.cuh"
