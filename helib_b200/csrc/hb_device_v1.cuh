@@ -611,7 +611,11 @@ __global__ void __launch_bounds__(640, 1) k1_conv(const HbPrimeDev* __restrict__
           const i64 v = Vb[c * HB1_VS + 16 * (8 * h + r) + x];
           const u64 m = v >= 0 ? (u64)v : (u64)(-v);
           const u64 f = v >= 0 ? negq : posq;
-          alo[r] = m * f; ahi[r] = __umul64hi(m, f);
+          if ((m >> 32) == 0) {   // |v| <= n/2 + p/2: one word unless the plaintext modulus is huge -- 32x64 product, two wide multiplies
+            const u64 p0 = hb1_mulwide((unsigned)m, (unsigned)f);
+            const u64 p1 = hb1_mulwide((unsigned)m, (unsigned)(f >> 32)) + (p0 >> 32);
+            alo[r] = (p1 << 32) | (unsigned)p0; ahi[r] = p1 >> 32;
+          } else { alo[r] = m * f; ahi[r] = __umul64hi(m, f); }
         }
         for (int j = 0; j < n; j++) {
           const u64 cj = ct[j];
