@@ -30,3 +30,21 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_workload():
+    """The driver compares the `config` dicts of the two arms: both come from bench.mult_config with the default batch."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    cfg = bench.mult_config(32)
+    assert cfg["workload"].startswith("ckks_m2^17") and (cfg["l_in"], cfg["l"], cfg["K"], cfg["digits"]) == (20, 19, 10, 2)
+    assert cfg["alg_bytes_per_mult"] == bench.ROW_BYTES * (4 * 20 + 2 * 2 * 29 + 2 * 19) == 122683392      # SURVEY 8d
+    assert bench.alg_bytes_per_keyswitch(26, 9, 3) == bench.ROW_BYTES * 340                                   # config 3: 178.3 MB
+    assert bench.alg_bytes_per_keyswitch(29, 15, 2) == bench.ROW_BYTES * 321                                  # config 4: 168.3 MB
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert json.loads(r.stdout.strip().splitlines()[-1])["config"] == cfg
+    for cores in (1, 8, 16, 128, 192):
+        w, per = bench.cpu_layout(cores)
+        assert w >= 1 and per >= 1 and w * per <= max(cores, 1)
