@@ -275,7 +275,7 @@ def bench_general_m_block(np, torch, local):
     k = next(t for t in range(2, m) if np.gcd(t, m) == 1)
     t_rot = timed(lambda: E.automorph_keyswitch_digits(digs, S, C0, k, EA, EB, O0, O1), 3)
     rows = B * len(S)
-    out = {"workload": "bgv_m21845_p2_bits580_c2_bootstrappable", "m": m, "phim": N, "bluestein_length": 65536, "e": ch.e_param, "e_prime": ch.e_prime_param,
+    out = {"workload": "bgv_m21845_p2_bits580_c2_bootstrappable", "m": m, "phim": N, "bluestein_length": 65536, "division_length": 1 << (max(N, 2 * (m - N) - 1) - 1).bit_length(), "e": ch.e_param, "e_prime": ch.e_prime_param,
            "primes": {"ctxt": len(S), "special": len(ch.special), "digits": nd}, "batch": B,
            "fwd_rows_per_s": rows / (t_f / 1e3), "inv_rows_per_s": rows / (t_i / 1e3),
            "relin_moddown_per_s": B / (t_ks / 1e3), "hoisted_rotations_per_s": B / (t_rot / 1e3),

@@ -57,7 +57,7 @@ def main():
         E.scale_down(C0 + C1, Sp, S, p)
     t_ks = timed(ks, 3)
     rows = B * len(S)
-    print(json.dumps({"metric": "general_m_rows", "m": m, "phim": N, "bluestein_length": 65536, "primes": {"ctxt": len(S), "special": len(ch.special), "digits": nd},
+    print(json.dumps({"metric": "general_m_rows", "m": m, "phim": N, "bluestein_length": 65536, "division_length": 1 << (max(N, 2 * (m - N) - 1) - 1).bit_length(), "primes": {"ctxt": len(S), "special": len(ch.special), "digits": nd},
                       "fwd_rows_per_s": rows / (t_f / 1e3), "inv_rows_per_s": rows / (t_i / 1e3),
                       "relin_moddown_per_s": B / (t_ks / 1e3), "ms": {"fwd": t_f, "inv": t_i, "relin_moddown": t_ks}, "batch": B, "n_gpus": 1}))
 

@@ -5,10 +5,14 @@
 // Cmodulus::FFT_aux / iFFT (src/CModulus.cpp:148-180,431-443,555-577).
 //   forward : X_k = root^(k^2) * sum_i (x_i root^(i^2)) * root^(-(k-i)^2), k in Z_m^*  (row[j] = X_rep(j))
 //   inverse : scatter the row into Z_m^* positions, the same DFT with root^-1, reduce mod Phi_m(X), times m^-1.
-// The two chirp convolutions, and the two products of the division by Phi_m, are cyclic convolutions of
-// length L = 2^ceil(log2(2m-1)) done with the power-of-two transform kernels on *cyclic* twiddle tables
-// (same butterfly network, tables omega^brev instead of psi^brev).  The remainder mod Phi_m uses
-// rev(Phi)^-1 = rev((X^m-1)/Phi_m) mod X^(m-phi(m)), so no per-prime power-series inversion is needed.
+// The two chirp convolutions are cyclic convolutions of length L = 2^ceil(log2(2m-1)) done with the power-of-two
+// transform kernels on *cyclic* twiddle tables (same butterfly network, tables omega^brev instead of psi^brev).
+// The remainder mod Phi_m uses rev(Phi)^-1 = rev((X^m-1)/Phi_m) mod X^d, d = m - phi(m), so no per-prime power-series
+// inversion is needed, and both of its products run at the shorter cyclic length L2 = 2^ceil(log2 max(phi(m), 2d-1)):
+// the quotient is a product of two length-d polynomials; q*Phi_m (degree < m) is only needed in its low phi(m)
+// coefficients, and everything that wraps around modulo X^L2 - 1 lands on coefficients >= phi(m) of q*Phi_m, which equal
+// those of the dividend A because the remainder has degree < phi(m) -- so (A mod Phi_m)[k] = A[k] + sum_{j>=1} A[k + j*L2]
+// - (q*Phi_m mod X^L2 - 1)[k].  For m = 21845 this is L2 = 2^14 against L = 2^16.
 #pragma once
 #include "hb_device.cuh"
 
@@ -17,20 +21,20 @@ struct HbGenPrime {
   const ulonglong2* ipw;   // [m]  root^(-i^2)     (+Shoup)
   const u64* RbHat;        // [L]  cyclic transform of b[j] = root^(-(j-(m-1))^2), j = 0..2m-2
   const u64* iRbHat;       // [L]  same for root^-1
-  const u64* invHat;       // [L]  cyclic transform of rev((X^m-1)/Phi_m) mod X^d
-  const u64* phiHat;       // [L]  cyclic transform of Phi_m
+  const u64* invHat;       // [L2] cyclic transform (length L2) of rev((X^m-1)/Phi_m) mod X^d
+  const u64* phiHat;       // [L2] cyclic transform (length L2) of Phi_m mod X^L2 - 1
   u64 minv, minv_s;        // m^-1 mod q
 };
 
 struct HbGenJob {
-  u64 m, phim, L, d;       // d = m - phi(m)
+  u64 m, phim, L, L2, d;   // d = m - phi(m); L2 = cyclic length of the division by Phi_m
   const int* rep;          // [phim] j-th unit of Z_m^*
   const int* irep;         // [m]    index of unit i, or -1
   HbRows rows;
   int nitems;
   const u64* src[HB_MAXB];  // polynomial rows, stride phim
   u64* dst[HB_MAXB];
-  u64* w0[HB_MAXB];         // work buffers, row stride L
+  u64* w0[HB_MAXB];         // work buffers, row stride L (chirp convolutions) or L2 (division by Phi_m)
   u64* w1[HB_MAXB];
   int which;                // selects the fixed vector in k_gen_mulvec: 0 RbHat, 1 iRbHat, 2 invHat, 3 phiHat
 };
@@ -48,9 +52,12 @@ __global__ void __launch_bounds__(HB_THREADS) k_gen(const HbPrimeDev* __restrict
   const u64* src = J.src[it] ? J.src[it] + prow : nullptr;
   u64* dst = J.dst[it] ? J.dst[it] + prow : nullptr;
   u64* w0 = J.w0[it] + wrow;
-  u64* w1 = J.w1[it] ? J.w1[it] + wrow : nullptr;
-  const size_t m = J.m, phim = J.phim, L = J.L, d = J.d;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t m = J.m, phim = J.phim, L = J.L, L2 = J.L2, d = J.d;
+  u64* w0s = J.w0[it] + (size_t)pi * L2;                          // the same buffers addressed as rows of the short plan
+  u64* w1s = J.w1[it] ? J.w1[it] + (size_t)pi * L2 : nullptr;
+  const bool short_op = op == HB_GEN_QREV || op == HB_GEN_FIN || (op == HB_GEN_MULVEC && J.which >= 2);
+  const size_t lim = short_op ? L2 : L;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lim; i += (size_t)gridDim.x * blockDim.x) {
     switch (op) {
       case HB_GEN_PRE_FWD:   // y_i = x_i * root^(i^2), zero padded (src/bluestein.cpp:151-155)
         w0[i] = i < phim ? hb_mul_shoup(src[i], G.pw[i].x, G.pw[i].y, q) : 0;
@@ -63,21 +70,28 @@ __global__ void __launch_bounds__(HB_THREADS) k_gen(const HbPrimeDev* __restrict
         if (i < m) { const int j = J.irep[i]; if (j >= 0) v = hb_mul_shoup(src[j], G.ipw[i].x, G.ipw[i].y, q); }
         w0[i] = v;
       } break;
-      case HB_GEN_POST_INV:  // A_k = z[k+m-1] * root^(-k^2); keep A_0..A_(phim-1) in dst, w1 = first d coefficients of rev(A)
-        if (i < phim) dst[i] = hb_mul_shoup(w0[i + m - 1], G.ipw[i].x, G.ipw[i].y, q);
-        if (i < d) { const size_t k = m - 1 - i; w1[i] = hb_mul_shoup(w0[k + m - 1], G.ipw[k].x, G.ipw[k].y, q); }
-        else w1[i] = 0;
+      case HB_GEN_POST_INV:  // A_k = z[k+m-1] * root^(-k^2), k < m; dst_k = A_k + A_(k+L2) + ... (k < phim), w1 = first d coefficients of rev(A)
+        if (i < phim) {
+          u64 s = hb_mul_shoup(w0[i + m - 1], G.ipw[i].x, G.ipw[i].y, q);
+          for (size_t k = i + L2; k < m; k += L2) s = hb_addmod(s, hb_mul_shoup(w0[k + m - 1], G.ipw[k].x, G.ipw[k].y, q), q);
+          dst[i] = s;
+        }
+        if (i < L2) {
+          u64 v = 0;
+          if (i < d) { const size_t k = m - 1 - i; v = hb_mul_shoup(w0[k + m - 1], G.ipw[k].x, G.ipw[k].y, q); }
+          w1s[i] = v;
+        }
         break;
       case HB_GEN_QREV:      // quotient by Phi_m: q_k = (rev(A) * rev(Phi)^-1 mod X^d)[d-1-k]
-        w0[i] = i < d ? w1[d - 1 - i] : 0;
+        w0s[i] = i < d ? w1s[d - 1 - i] : 0;
         break;
       case HB_GEN_FIN:       // coefficients = (A - q*Phi) * m^-1 (src/CModulus.cpp:566-577)
-        if (i < phim) dst[i] = hb_mul_shoup(hb_submod(dst[i], w0[i], q), G.minv, G.minv_s, q);
+        if (i < phim) dst[i] = hb_mul_shoup(hb_submod(dst[i], w0s[i], q), G.minv, G.minv_s, q);
         break;
       case HB_GEN_MULVEC: {
-        const u64* v = J.which == 0 ? G.RbHat : (J.which == 1 ? G.iRbHat : (J.which == 2 ? G.invHat : G.phiHat));
-        u64* w = J.which == 2 ? w1 : w0;   // the quotient product runs in w1
-        w[i] = hb_mulmod(w[i], v[i], P);
+        if (J.which < 2) { const u64* v = J.which == 0 ? G.RbHat : G.iRbHat; w0[i] = hb_mulmod(w0[i], v[i], P); }
+        else if (J.which == 2) w1s[i] = hb_mulmod(w1s[i], G.invHat[i], P);   // the quotient product runs in w1
+        else w0s[i] = hb_mulmod(w0s[i], G.phiHat[i], P);
       } break;
     }
   }

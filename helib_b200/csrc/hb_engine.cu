@@ -90,9 +90,10 @@ struct hb_ctx {
   struct Gen {
     bool on = false;
     u64 m = 0, phim = 0, L = 0, d = 0; int logL = 0, log_blk_L = 0;
+    u64 L2 = 0; int logL2 = 0, log_blk_L2 = 0;        // short cyclic plan of the division by Phi_m: L2 = 2^ceil(log2 max(phi(m), 2d-1)) <= L
     int* d_rep = nullptr; int* d_irep = nullptr;
     HbGenPrime* d_gp = nullptr;
-    HbPrimeDev* d_primes_cyc = nullptr;
+    HbPrimeDev* d_primes_cyc = nullptr; HbPrimeDev* d_primes_cyc2 = nullptr;
     void* tab = nullptr;
     double2* d_W = nullptr;                             // e^(2 pi I j/m), j < m (embedding norms; built on first use)
     u64 *w0 = nullptr, *w1 = nullptr, *wt = nullptr;   // [HB_MAXB][nprimes][L]
@@ -312,7 +313,7 @@ extern "C" void hb_ctx_destroy(hb_ctx* c) {
   for (hb_poly* p : c->pool) { cudaFree(p->d); delete p; }
   cudaFree(c->pw.d_cube_to_poly); cudaFree(c->pw.d_short_to_long); cudaFree(c->pw.cube); cudaFree(c->pw.rows);
   cudaFree(c->d_frac); cudaFree(c->d_z); cudaFree(c->d_max); cudaFree(c->d_bcast);
-  cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.tab);
+  cudaFree(c->gen.d_rep); cudaFree(c->gen.d_irep); cudaFree(c->gen.d_gp); cudaFree(c->gen.d_primes_cyc); cudaFree(c->gen.d_primes_cyc2); cudaFree(c->gen.tab);
   cudaFree(c->gen.d_W);
   cudaFree(c->gen.w0); cudaFree(c->gen.w1); cudaFree(c->gen.wt); cudaFree(c->gen.cA); cudaFree(c->gen.cB);
   cudaFree(c->tmpA); cudaFree(c->tmpB); cudaFree(c->d_tw); cudaFree(c->d_primes); cudaFree(c->d_stats);
@@ -991,10 +992,11 @@ static int conv_chunk(hb_ctx* c, u64* const* polys, int nit, const int32_t* src,
 
 // ------------------------------------------------------------------------------------------
 // general m (Bluestein rows)
-struct PlanScope {   // run the power-of-two transform launchers on the cyclic length-L plan
+struct PlanScope {   // run the power-of-two transform launchers on a cyclic plan: 0 = length L (chirp convolutions), 1 = length L2 (division by Phi_m)
   hb_ctx* c; int logN, log_blk; HbPrimeDev* dp; size_t N;
-  explicit PlanScope(hb_ctx* c_) : c(c_), logN(c_->logN), log_blk(c_->log_blk), dp(c_->d_primes), N(c_->N) {
-    c->logN = c->gen.logL; c->log_blk = c->gen.log_blk_L; c->d_primes = c->gen.d_primes_cyc; c->N = c->gen.L;
+  PlanScope(hb_ctx* c_, int plan) : c(c_), logN(c_->logN), log_blk(c_->log_blk), dp(c_->d_primes), N(c_->N) {
+    if (plan == 0) { c->logN = c->gen.logL; c->log_blk = c->gen.log_blk_L; c->d_primes = c->gen.d_primes_cyc; c->N = c->gen.L; }
+    else { c->logN = c->gen.logL2; c->log_blk = c->gen.log_blk_L2; c->d_primes = c->gen.d_primes_cyc2; c->N = c->gen.L2; }
   }
   ~PlanScope() { c->logN = logN; c->log_blk = log_blk; c->d_primes = dp; c->N = N; }
 };
@@ -1029,8 +1031,8 @@ static std::vector<long> h_cyclotomic(long m) {
   return a;
 }
 
-static int gen_cyc_ntt(hb_ctx* c, int dir, u64* const* w, u64* const* tmp, int nit, const int32_t* idx, int n) {
-  PlanScope ps(c);
+static int gen_cyc_ntt(hb_ctx* c, int dir, u64* const* w, u64* const* tmp, int nit, const int32_t* idx, int n, int plan = 0) {
+  PlanScope ps(c, plan);
   if (dir > 0) { HB_TRY(launch_cols(c, +1, (const u64* const*)w, tmp, nit, idx, n)); return launch_blk(c, +1, (const u64* const*)tmp, w, nit, idx, n, 0, nullptr); }
   HB_TRY(launch_blk(c, -1, (const u64* const*)w, tmp, nit, idx, n, 0, nullptr));
   return launch_cols(c, -1, (const u64* const*)tmp, w, nit, idx, n);
@@ -1040,7 +1042,7 @@ static int gen_k(hb_ctx* c, int op, int which, const u64* const* src, u64* const
   for (int r0 = 0; r0 < n; r0 += HB_MAXROWS) {
     int nr = std::min(HB_MAXROWS, n - r0);
     HbGenJob J; memset(&J, 0, sizeof(J));
-    J.m = g.m; J.phim = g.phim; J.L = g.L; J.d = g.d; J.rep = g.d_rep; J.irep = g.d_irep; J.which = which;
+    J.m = g.m; J.phim = g.phim; J.L = g.L; J.L2 = g.L2; J.d = g.d; J.rep = g.d_rep; J.irep = g.d_irep; J.which = which;
     fill_rows(J.rows, idx + r0, nr);
     J.nitems = nit;
     for (int i = 0; i < nit; i++) {
@@ -1073,13 +1075,15 @@ static int gen_inv(hb_ctx* c, const u64* const* src, u64* const* dst, int nit, c
   HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n));
   HB_TRY(gen_k(c, HB_GEN_POST_INV, 0, nullptr, dst, nit, idx, n));
   if (c->gen.d > 0) {   // remainder modulo Phi_m(X)
-    HB_TRY(gen_cyc_ntt(c, +1, W1, WT, nit, idx, n));
+    // both products run on the short plan (rows of stride L2 inside the same work buffers): the quotient is a product of two
+    // length-d polynomials, and q*Phi_m is taken modulo X^L2 - 1 -- POST_INV has already folded the known wrapped part into dst
+    HB_TRY(gen_cyc_ntt(c, +1, W1, WT, nit, idx, n, 1));
     HB_TRY(gen_k(c, HB_GEN_MULVEC, 2, nullptr, nullptr, nit, idx, n));
-    HB_TRY(gen_cyc_ntt(c, -1, W1, WT, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, -1, W1, WT, nit, idx, n, 1));
     HB_TRY(gen_k(c, HB_GEN_QREV, 0, nullptr, nullptr, nit, idx, n));
-    HB_TRY(gen_cyc_ntt(c, +1, W0, WT, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, +1, W0, WT, nit, idx, n, 1));
     HB_TRY(gen_k(c, HB_GEN_MULVEC, 3, nullptr, nullptr, nit, idx, n));
-    HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n));
+    HB_TRY(gen_cyc_ntt(c, -1, W0, WT, nit, idx, n, 1));
   } else {
     HB_CUDA(cudaMemsetAsync(c->gen.w0, 0, (size_t)nit * c->nprimes * c->gen.L * sizeof(u64), c->stream));
   }
@@ -1128,9 +1132,11 @@ static int gen_init(hb_ctx* c, const uint64_t* psi) {
   g.on = true; g.m = m; g.phim = h_phi(m); g.d = g.m - g.phim;
   g.logL = 0; while ((1L << g.logL) < 2 * m - 1) g.logL++;
   g.L = 1ULL << g.logL; g.log_blk_L = g.logL >= 11 ? 8 : 0;
+  g.logL2 = 0; while ((1UL << g.logL2) < std::max<u64>(g.phim, 2 * g.d - 1)) g.logL2++;
+  g.L2 = 1ULL << g.logL2; g.log_blk_L2 = g.logL2 >= 11 ? 8 : 0;
   c->N = g.phim; c->logN = -1; c->log_blk = 0;
   const u64 e = m % 2 == 0 ? 2 * m : m;
-  const int np = c->nprimes; const size_t L = g.L;
+  const int np = c->nprimes; const size_t L = g.L, L2 = g.L2;
   std::vector<int> rep, irep(m, -1);
   for (long i = 1; i < m; i++) if (h_gcd(i, m) == 1) { irep[i] = (int)rep.size(); rep.push_back((int)i); }
   HB_TRY(ctx_alloc(c, (void**)&g.d_rep, sizeof(int) * rep.size()));
@@ -1148,7 +1154,7 @@ static int gen_init(hb_ctx* c, const uint64_t* psi) {
   std::vector<unsigned char> tab(per * np);
   HB_TRY(ctx_alloc(c, &g.tab, tab.size()));
   std::vector<HbGenPrime> gp(np);
-  std::vector<HbPrimeDev> pc(np);
+  std::vector<HbPrimeDev> pc(np), pc2(np);
   std::vector<unsigned> brev(L);
   for (size_t k = 0; k < L; k++) { unsigned r = 0; for (int b = 0; b < g.logL; b++) if (k >> b & 1) r |= 1u << (g.logL - 1 - b); brev[k] = r; }
   for (int i = 0; i < np; i++) {
@@ -1172,7 +1178,10 @@ static int gen_init(hb_ctx* c, const uint64_t* psi) {
       vec[1 * L + (m - 1 + k)] = a; vec[1 * L + (m - 1 - k)] = a;
     }
     for (size_t k = 0; k < g.d; k++) { long v = psiq[g.d - k] % (long)q; vec[2 * L + k] = (u64)(v < 0 ? v + (long)q : v); }   // rev(Psi) mod X^d
-    for (size_t k = 0; k <= g.phim; k++) { long v = phi[k] % (long)q; vec[3 * L + k] = (u64)(v < 0 ? v + (long)q : v); }
+    for (size_t k = 0; k <= g.phim; k++) {   // Phi_m modulo X^L2 - 1 (phi(m) = L2 folds the leading 1 onto the constant term)
+      long v = phi[k] % (long)q; u64& slot = vec[3 * L + k % L2];
+      slot = (slot + (u64)(v < 0 ? v + (long)q : v)) % q;
+    }
     // cyclic twiddles: fw[2^s + i] = omega^((L / 2^(s+1)) * brev_s(i))
     u64 gnr = 2; while (h_powmod(gnr, (q - 1) / 2, q) != q - 1) gnr++;
     const u64 om = h_powmod(gnr, (q - 1) / L, q), iom = h_powmod(om, q - 2, q);
@@ -1194,12 +1203,16 @@ static int gen_init(hb_ctx* c, const uint64_t* psi) {
     pc[i] = c->h_primes[i];
     pc[i].fw = (const ulonglong2*)(dvec + 4 * L); pc[i].iw = pc[i].fw + L;
     pc[i].ninv = h_powmod((u64)L % q, q - 2, q); pc[i].ninv_s = h_shoup(pc[i].ninv, q);
+    pc2[i] = pc[i];   // the twiddles of a shorter cyclic length are a prefix of the same table: fw[2^s + i] does not depend on L
+    pc2[i].ninv = h_powmod((u64)L2 % q, q - 2, q); pc2[i].ninv_s = h_shoup(pc2[i].ninv, q);
   }
   HB_CUDA(cudaMemcpy(g.tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
   HB_TRY(ctx_alloc(c, (void**)&g.d_gp, sizeof(HbGenPrime) * np));
   HB_CUDA(cudaMemcpy(g.d_gp, gp.data(), sizeof(HbGenPrime) * np, cudaMemcpyHostToDevice));
   HB_TRY(ctx_alloc(c, (void**)&g.d_primes_cyc, sizeof(HbPrimeDev) * np));
   HB_CUDA(cudaMemcpy(g.d_primes_cyc, pc.data(), sizeof(HbPrimeDev) * np, cudaMemcpyHostToDevice));
+  HB_TRY(ctx_alloc(c, (void**)&g.d_primes_cyc2, sizeof(HbPrimeDev) * np));
+  HB_CUDA(cudaMemcpy(g.d_primes_cyc2, pc2.data(), sizeof(HbPrimeDev) * np, cudaMemcpyHostToDevice));
   const size_t wsz = (size_t)HB_MAXB * np * L * sizeof(u64), csz = (size_t)HB_MAXB * np * c->N * sizeof(u64);
   HB_TRY(ctx_alloc(c, (void**)&g.w0, wsz)); HB_TRY(ctx_alloc(c, (void**)&g.w1, wsz)); HB_TRY(ctx_alloc(c, (void**)&g.wt, wsz));
   HB_TRY(ctx_alloc(c, (void**)&g.cA, csz)); HB_TRY(ctx_alloc(c, (void**)&g.cB, csz));
@@ -1207,11 +1220,12 @@ static int gen_init(hb_ctx* c, const uint64_t* psi) {
   for (int i = 0; i < np; i++) {
     for (int v = 0; v < 4; v++) {
       u64* dv = (u64*)((unsigned char*)g.tab + per * i + (size_t)2 * m * 16) + (size_t)v * L;
-      // stage through w0 row i so that the launchers' row addressing (prime index * L) applies
-      HB_CUDA(cudaMemcpyAsync(g.w0 + (size_t)i * L, dv, L * 8, cudaMemcpyDeviceToDevice, c->stream));
+      // stage through w0 row i so that the launchers' row addressing (prime index * plan length) applies
+      const size_t Lv = v < 2 ? L : L2;   // the chirp kernels on the long plan, the two division vectors on the short one
+      HB_CUDA(cudaMemcpyAsync(g.w0 + (size_t)i * Lv, dv, Lv * 8, cudaMemcpyDeviceToDevice, c->stream));
       u64* W0[1] = {g.w0}; u64* WT[1] = {g.wt}; int32_t one[1] = {i};
-      HB_TRY(gen_cyc_ntt(c, +1, W0, WT, 1, one, 1));
-      HB_CUDA(cudaMemcpyAsync(dv, g.w0 + (size_t)i * L, L * 8, cudaMemcpyDeviceToDevice, c->stream));
+      HB_TRY(gen_cyc_ntt(c, +1, W0, WT, 1, one, 1, v < 2 ? 0 : 1));
+      HB_CUDA(cudaMemcpyAsync(dv, g.w0 + (size_t)i * Lv, Lv * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));

@@ -30,7 +30,7 @@ def lib(request):
     return request.getfixturevalue("sim_lib" if request.param == "sim" else "cuda_lib")
 
 
-@pytest.mark.parametrize("cfg", SMALL)
+@pytest.mark.parametrize("cfg", SMALL + [(1 << 15, 257, 1, 120, 2)])   # + N = 2^14: the blk kernels with 64 columns, generic cols kernels
 def test_ntt_rows_match_oracle(lib, cfg):
     ch, psis, O, E = make(lib, *cfg)
     rng = np.random.default_rng(1)

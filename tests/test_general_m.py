@@ -236,6 +236,34 @@ def test_thinboot_ring_m21845_rows(cuda_lib):
     assert (P.download(S)[S] == before[S]).all()
 
 
+def test_thinboot_ring_short_division_plan_on_the_simulator(sim_lib):
+    """The same ring on the CPU simulator, two rows: here the division by Phi_m runs at cyclic length L2 = phi(m) = 2^14 (a quarter
+    of the chirp length 2^16), so Phi_m's leading coefficient folds onto its constant term and the dividend's coefficients
+    k + L2 < m are folded into the remainder -- the case the small rings of CFGS only reach with m = 1285."""
+    m = 21845
+    ch = po.build_mod_chain(m, 2, 1, 580, 2)
+    E = Engine(m, ch.primes, None, ch.digits, ch.special, lib=sim_lib)
+    idx = [ch.ctxt[0], ch.special[-1]]
+    rng = np.random.default_rng(11)
+    coef = np.zeros((len(ch.primes), ch.phim), dtype=np.uint64)
+    for i in idx:
+        coef[i] = rng.integers(0, ch.primes[i], size=ch.phim, dtype=np.uint64)
+    P = E.poly(coef, idx)
+    E.ntt_fwd([P], idx)
+    got = P.download(idx)
+    rep = po.zms_rep(m)
+    i = idx[0]
+    q, zeta = ch.primes[i], E.psis[i] * E.psis[i] % ch.primes[i]
+    f = [int(v) for v in coef[i]]
+    for j in (0, 5, ch.phim - 1):
+        x, acc = pow(zeta, rep[j], q), 0
+        for cf in reversed(f):
+            acc = (acc * x + cf) % q
+        assert int(got[i][j]) == acc
+    E.ntt_inv([P], idx)
+    assert (P.download(idx)[idx] == coef[idx]).all()
+
+
 # ---- SURVEY 8f-4: powerful basis and the recryption mod-switch ----
 
 @pytest.mark.parametrize("m,mvec,p,bits", [(105, [3, 5, 7], 2, 100), (45, [9, 5], 2, 100), (45, [5, 9], 7, 100), (64, None, 3, 100), (25, None, 2, 80)])
