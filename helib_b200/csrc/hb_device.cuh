@@ -415,15 +415,12 @@ __global__ void __launch_bounds__(HB_THREADS) k_inv_cols(const HbPrimeDev* __res
 // Exact balanced reconstruction of one coefficient (the multi-precision part of DoubleCRT::toPoly,
 // src/DoubleCRT.cpp:1076-1100).  y[j*ystride] = r_j * (Q/q_j)^-1 mod q_j.  Returns v with
 // x = sum_j y_j*(Q/q_j) - v*Q in [-(Q-1)/2,(Q-1)/2]; *sign = sign(x); optionally writes x.
-__device__ __forceinline__ u64 hb_unpack30(u64 p) { return (p & 0xffffffffULL) | ((p >> 32) << 30); }
-__device__ __forceinline__ u64 hb_pack30(u64 y) { return (y & 0x3fffffffULL) | ((y >> 30) << 32); }
-__device__ HB_NOINLINE int hb_crt_exact(const HbConvDev* cv, const u64* y, int ystride, int* sign, u64* xout, int Lout, int positive, int packed = 0) {
+__device__ HB_NOINLINE int hb_crt_exact(const HbConvDev* cv, const u64* y, int ystride, int* sign, u64* xout, int Lout, int positive) {
   const int n = cv->n, L = cv->L;  // L limbs hold Q; X needs L+1
   u64 X[HB_MAXL + 1];
   for (int l = 0; l <= L; l++) X[l] = 0;
   for (int j = 0; j < n; j++) {
-    u64 yj = y[(size_t)j * ystride];
-    if (packed) yj = hb_unpack30(yj);
+    const u64 yj = y[(size_t)j * ystride];
     const u64* Qj = cv->Qj + (size_t)j * L;
     u64 carry = 0;
     for (int l = 0; l < L; l++) {
@@ -474,13 +471,11 @@ __device__ HB_NOINLINE int hb_crt_exact(const HbConvDev* cv, const u64* y, int y
 // v = round(sum_j y_j/q_j) via 0.64 fixed point; exact fallback when within the error margin of
 // the rounding boundary.  With has_p: also the BGV correction of DoubleCRT::scaleDownToSet
 // (src/DoubleCRT.cpp:1485-1511) folded into the returned multiple of Q.
-template <bool PACKED = false>
 __device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int ystride, u64* stats, double* frac = nullptr, bool bgv = true) {
   const int n = cv->n;
   u64 shi = 0, slo = 0;
   for (int j = 0; j < n; j++) {
-    u64 yj = y[(size_t)j * ystride];
-    if (PACKED) yj = hb_unpack30(yj);
+    const u64 yj = y[(size_t)j * ystride];
     u64 m = cv->fmul[j];
     int sh = cv->fshift[j];
     u64 lo = yj * m, hi = __umul64hi(yj, m);
@@ -493,13 +488,13 @@ __device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int 
   const u64 margin = 4ULL * (u64)n;
   int sign = 2;  // unknown
   if (F >= 0 - margin) {  // could round up once the truncation error is added back: decide exactly
-    v = hb_crt_exact(cv, y, ystride, &sign, nullptr, 0, 0, PACKED ? 1 : 0);
+    v = hb_crt_exact(cv, y, ystride, &sign, nullptr, 0, 0);
     if (stats) atomicAdd(stats, 1ULL);
   }
   if (bgv && cv->has_p) {
     const u64 p = cv->p;
     u64 hi = 0, lo = 0;
-    for (int j = 0; j < n; j++) { u64 yj = y[(size_t)j * ystride]; if (PACKED) yj = hb_unpack30(yj); hb_mac128(hi, lo, yj, cv->cp[j]); }
+    for (int j = 0; j < n; j++) hb_mac128(hi, lo, y[(size_t)j * ystride], cv->cp[j]);
     hb_mac128(hi, lo, (u64)v, cv->negQ_p);
     u64 u = hb_reduce128(hi, lo, p, cv->p_c64, cv->p_c64_s, cv->p_one_s);
     if (u != 0) {
@@ -510,7 +505,7 @@ __device__ __forceinline__ i64 hb_conv_v(const HbConvDev* cv, const u64* y, int 
         if (sign == 2) {
           if (F >= 0x8000000000000000ULL) sign = 1;             // x > 0 (x != 0 because u != 0)
           else if (F < 0x8000000000000000ULL - margin) sign = -1;
-          else { hb_crt_exact(cv, y, ystride, &sign, nullptr, 0, 0, PACKED ? 1 : 0); if (stats) atomicAdd(stats, 1ULL); }
+          else { hb_crt_exact(cv, y, ystride, &sign, nullptr, 0, 0); if (stats) atomicAdd(stats, 1ULL); }
         }
         minus = sign < 0;
       }
