@@ -77,6 +77,8 @@ class Oracle:
 
     def __init__(self, N, m, primes, psis, digits=None, special=None, nthreads=1):
         self.N, self.m = int(N), int(m)
+        if self.m < 4 or self.m & (self.m - 1) or self.N != self.m // 2:
+            raise ValueError("the C++ oracle restates the power-of-two path only (m = 2N); general m is checked against pyoracle")
         self.primes = [int(q) for q in primes]
         self.psis = [int(p) for p in psis]
         self.np = len(self.primes)

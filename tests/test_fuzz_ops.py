@@ -1,0 +1,107 @@
+"""Differential fuzz of the DoubleCRT operations: random index sets and random sequences of addPrimes / addPrimesAndScale /
+scaleDownToSet (several plaintext spaces) / automorph / scale-by-primes / pointwise / transform round trips / breakIntoDigits on
+the CPU kernel-logic simulator, every intermediate state compared row for row with the C++ oracle.  The index sets the parity
+tests use are the ones the multiply path produces; this walks through arbitrary subsets of the chain (one source prime, more
+sources than targets, small primes mixed with special ones), which is what DoubleCRT's interface allows
+(src/DoubleCRT.cpp:565-647,1464-1516)."""
+import random
+from math import gcd
+
+import numpy as np
+import pytest
+
+from common import make
+
+SMALL = [(64, 257, 1, 200, 3), (2048, 17, 2, 250, 3), (4096, 257, 1, 300, 2), (8192, -1, 1, 300, 3), (8192, 2, 3, 200, 2)]
+BIG = [(1 << 17, 257, 1, 330, 3), (1 << 17, -1, 1, 400, 2)]
+
+
+def walk(lib, cfg, rnd, nops):
+    m, p, r, bits, c = cfg
+    ch, psis, O, E = make(lib, *cfg, nthreads=8)
+    rng = np.random.default_rng(rnd.randrange(1 << 30))
+    allp = list(range(len(ch.primes)))
+    p2r = 1 if p == -1 else p ** r
+    cur = sorted(rnd.sample(allp, rnd.randint(1, len(allp))))
+    x = O.random(rng, cur)
+    P = E.poly(x, cur)
+    log = [("init", cfg, cur)]
+    done = 0
+    while done < nops:
+        op = rnd.choice(["add_primes", "add_primes_and_scale", "scale_down", "scale_down", "automorph", "scale_by_primes", "pointwise", "roundtrip", "digits"])
+        if op in ("add_primes", "add_primes_and_scale"):
+            rest = [i for i in allp if i not in cur]
+            if not rest:
+                continue
+            add = sorted(rnd.sample(rest, rnd.randint(1, len(rest))))
+            log.append((op, list(cur), add))
+            getattr(E, op)([P], cur, add)
+            getattr(O, op)(x, cur, add)
+            cur = sorted(cur + add)
+        elif op == "scale_down":
+            if len(cur) < 2:
+                continue
+            keep = sorted(rnd.sample(cur, rnd.randint(1, len(cur) - 1)))
+            ps = 1 if p == -1 else rnd.choice([1, p2r, p2r, 2, 3, 4, 65537])
+            if any(gcd(ps, ch.primes[i]) != 1 for i in cur if i not in keep):
+                continue
+            log.append((op, list(cur), keep, ps))
+            E.scale_down([P], cur, keep, ps)
+            O.scale_down(x, cur, keep, ps)
+            cur = keep
+        elif op == "automorph":
+            k = rnd.randrange(1, m, 2)
+            log.append((op, list(cur), k))
+            Pd = E.poly()
+            E.automorph([Pd], [P], cur, k)
+            O.automorph(x, cur, k)
+            P = Pd
+        elif op == "scale_by_primes":
+            f = sorted(rnd.sample(allp, rnd.randint(1, min(4, len(allp)))))
+            inv = rnd.random() < 0.5
+            if inv and any(i in cur for i in f):
+                continue                                   # q_i has no inverse modulo itself
+            log.append((op, list(cur), f, inv))
+            E.scale_by_primes([P], cur, f, inv)
+            O.scale_by_primes(x, cur, f, inv)
+        elif op == "pointwise":
+            y = O.random(rng, cur)
+            o = rnd.choice(["add", "sub", "mul"])
+            log.append((op, list(cur), o))
+            E.pointwise(o, [P], [E.poly(y, cur)], cur)
+            O.pointwise(o, x, y, cur)
+        elif op == "roundtrip":
+            sub = sorted(rnd.sample(cur, rnd.randint(1, len(cur))))
+            log.append((op, sub))
+            E.ntt_inv([P], sub)
+            E.ntt_fwd([P], sub)
+        else:
+            if not cur or any(i not in ch.ctxt for i in cur):
+                continue
+            log.append((op, list(cur)))
+            ref = O.break_into_digits(x, cur)
+            full = sorted(set(cur) | set(ch.special))
+            D = E.break_into_digits([P], cur)[0]
+            assert len(D) == len(ref), log
+            for di in range(len(ref)):
+                assert (D[di].download(full)[full] == ref[di][full]).all(), (di, log)
+            done += 1
+            continue
+        done += 1
+        got = P.download(cur)
+        bad = [i for i in cur if not (got[i] == x[i]).all()]
+        assert not bad, (bad, log)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_walks_small_rings(sim_lib, seed):
+    rnd = random.Random(seed)
+    for _ in range(6):
+        walk(sim_lib, rnd.choice(SMALL), rnd, 25)
+
+
+def test_random_walk_full_size_ring(sim_lib):
+    """N = 2^16: the register-blocked and TMA-staged kernels and the fused conversions with arbitrary source/target splits."""
+    rnd = random.Random(11)
+    for cfg in BIG:
+        walk(sim_lib, cfg, rnd, 14)
