@@ -105,3 +105,101 @@ def test_random_walk_full_size_ring(sim_lib):
     rnd = random.Random(11)
     for cfg in BIG:
         walk(sim_lib, cfg, rnd, 14)
+
+
+GENERAL = [(12, 7, 1, 150, 2), (45, 2, 1, 150, 2), (28, 3, 1, 150, 3), (105, 2, 1, 180, 2), (45, 7, 2, 150, 2), (63, 2, 1, 150, 2), (85, 2, 1, 150, 2)]
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_walks_general_m(sim_lib, seed):
+    """The same for Bluestein rows (general m, incl. rings no other test uses: m = 63, 85), against a big-integer model:
+    toPoly by CRT over the current set, addPrimes = residues of the balanced polynomial, scaleDownToSet with the reference's
+    delta correction and tie rule, automorph as the permutation of Z_m^*."""
+    import pyoracle as po
+    from helib_b200.engine import Engine
+    rnd = random.Random(seed)
+    for _ in range(8):
+        m, p, r, bits, c = rnd.choice(GENERAL)
+        ch = po.build_mod_chain(m, p, r, bits, c)
+        roots = [po.cmod_root(q, m) for q in ch.primes]
+        E = Engine(m, ch.primes, None, ch.digits, ch.special, lib=sim_lib)
+        n, allp, rep = ch.phim, list(range(len(ch.primes))), po.zms_rep(m)
+
+        def to_poly(rows, idx):
+            Q = ch.product(idx)
+            cs = {i: po.gen_ifft(rows[i], ch.primes[i], m, roots[i]) for i in idx}
+            out = []
+            for k in range(n):
+                acc = 0
+                for i in idx:
+                    q = ch.primes[i]
+                    Qi = Q // q
+                    acc += Qi * (cs[i][k] * pow(Qi % q, -1, q) % q)
+                out.append(po.bal(acc, Q))
+            return out
+
+        def rows_of_poly(poly, idx):
+            return {i: po.gen_fft([cc % ch.primes[i] for cc in poly], ch.primes[i], m, roots[i]) for i in idx}
+
+        def dense(rows):
+            out = np.zeros((len(ch.primes), n), dtype=np.uint64)
+            for i, rr in rows.items():
+                out[i] = np.array(rr, dtype=np.uint64)
+            return out
+
+        cur = sorted(rnd.sample(allp, rnd.randint(1, len(allp))))
+        x = {i: [rnd.randrange(ch.primes[i]) for _ in range(n)] for i in cur}
+        P = E.poly(dense(x), cur)
+        log = [("init", (m, p, r, bits, c), cur)]
+        done = 0
+        while done < 6:
+            op = rnd.choice(["add_primes", "scale_down", "scale_down", "automorph", "roundtrip"])
+            if op == "add_primes":
+                rest = [i for i in allp if i not in cur]
+                if not rest:
+                    continue
+                add = sorted(rnd.sample(rest, rnd.randint(1, len(rest))))
+                log.append((op, list(cur), add))
+                x.update(rows_of_poly(to_poly(x, cur), add))
+                E.add_primes([P], cur, add)
+                cur = sorted(cur + add)
+            elif op == "scale_down":
+                if len(cur) < 2:
+                    continue
+                keep = sorted(rnd.sample(cur, rnd.randint(1, len(cur) - 1)))
+                ps = rnd.choice([1, p ** r, p ** r, 2, 3, 4, 65537])
+                diff = [i for i in cur if i not in keep]
+                if any(gcd(ps, ch.primes[i]) != 1 for i in diff):
+                    continue
+                log.append((op, list(cur), keep, ps))
+                Pd = ch.product(diff)
+                delta = to_poly(x, diff)
+                if ps > 1:
+                    pinv = pow(Pd % ps, -1, ps)
+                    for k, d in enumerate(delta):
+                        u = d % ps
+                        if u:
+                            u = u * pinv % ps
+                            if u > ps // 2 or (ps % 2 == 0 and u == ps // 2 and d < 0):
+                                u -= ps
+                            delta[k] = d - Pd * u
+                drows = rows_of_poly(delta, keep)
+                x = {i: [((a - b) * pow(Pd % ch.primes[i], -1, ch.primes[i])) % ch.primes[i] for a, b in zip(x[i], drows[i])] for i in keep}
+                E.scale_down([P], cur, keep, ps)
+                cur = keep
+            elif op == "automorph":
+                k = rnd.choice([t for t in range(1, m) if gcd(t, m) == 1])
+                log.append((op, list(cur), k))
+                x = {i: [x[i][rep.index(rep[j] * k % m)] for j in range(n)] for i in cur}
+                D = E.poly()
+                E.automorph([D], [P], cur, k)
+                P = D
+            else:
+                sub = sorted(rnd.sample(cur, rnd.randint(1, len(cur))))
+                log.append((op, sub))
+                E.ntt_inv([P], sub)
+                E.ntt_fwd([P], sub)
+            done += 1
+            got = P.download(cur)
+            bad = [i for i in cur if [int(v) for v in got[i]] != [int(v) for v in x[i]]]
+            assert not bad, (bad, log)
