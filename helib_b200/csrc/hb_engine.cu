@@ -2064,7 +2064,16 @@ extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* c
   const int maxdig = c->ndigits;
   std::vector<hb_poly*> dig; HB_TRY(pool_get(c, nitems * maxdig, dig));
   std::vector<int32_t> Sp(S, S + nS); Sp.insert(Sp.end(), c->special.begin(), c->special.end()); std::sort(Sp.begin(), Sp.end());
-  if (v1_blk_ok(c) && v1_cols_ok(c) && !c->gen.on && !getenv("HB_NO_FUSED_RELIN"))
+  // a digit below the last live one may have no live prime (an index set with a hole): the reference then carries a zero digit
+  // and still divides the later ones by that digit's full product (src/DoubleCRT.cpp:488-493,509-561); the fused path converts
+  // from the digit's own rows and has nothing to convert from, so such sets take the step-by-step path below
+  bool hole = false;
+  {
+    int last = -1; std::vector<char> live(c->ndigits > 0 ? c->ndigits : 1, 0);
+    for (int i = 0; i < nS; i++) { const int d = c->digit_of[S[i]]; if (d >= 0) { live[d] = 1; last = std::max(last, d); } }
+    for (int d = 0; d < last; d++) if (!live[d]) hole = true;
+  }
+  if (v1_blk_ok(c) && v1_cols_ok(c) && !c->gen.on && !hole && !getenv("HB_NO_FUSED_RELIN"))
     return relin_fused_v1(c, c0, c1, c2, nitems, S, nS, Sp, evk_a, evk_b, ndig_evk, dig);
   // keySwitchPart (src/Ctxt.cpp:805-842)
   int nd = 0;

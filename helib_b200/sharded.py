@@ -141,6 +141,16 @@ class ShardedKeySwitch:
                     E.pointwise("copy", [dp[d] for dp in dig_polys], c2, od)
         for d in range(nd):
             col = [dp[d] for dp in dig_polys]
+            if not dsets[d]:
+                # an index set with a hole: no live prime in this digit.  The reference carries the zero polynomial for it and
+                # still divides the later digits by the digit's full product (src/DoubleCRT.cpp:488-493,509-561)
+                if oSp:
+                    E.zero_rows(col, oSp)
+                for j in range(d + 1, nd):
+                    oj = self.owned(dsets[j])
+                    if oj:
+                        E.scale_by_primes(c2 if fused else [dp[j] for dp in dig_polys], oj, self.digits[d], inv=True)
+                continue
             ys = [self._ybuf(("dig", it)) for it in range(nit)]
             # fused: digit d's own rows ARE c2's rows by now (the mixed-radix steps update c2 in place)
             self._exchange(c2 if fused else col, dsets[d], ys)

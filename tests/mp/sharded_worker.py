@@ -63,7 +63,10 @@ def main():
     EA = [E.poly(evk_a[i], own_full) for i in range(nd)]   # evk sharded identically: only owned rows uploaded
     EB = [E.poly(evk_b[i], own_full) for i in range(nd)]
     ok = True
-    for S in (ch.ctxt, ch.ctxt[:-1]):
+    sets = [ch.ctxt, ch.ctxt[:-1]]
+    if backend == "sim" and len(ch.digits) >= 3:
+        sets.append([i for i in ch.ctxt if i not in ch.digits[1]])    # a hole: digit 1 has no live prime
+    for S in sets:
         nit = 2
         cs = [[O.random(rng, S) for _ in range(3)] for _ in range(nit)]
         oS = KS.owned(S)

@@ -203,3 +203,44 @@ def test_random_walks_general_m(sim_lib, seed):
             got = P.download(cur)
             bad = [i for i in cur if [int(v) for v in got[i]] != [int(v) for v in x[i]]]
             assert not bad, (bad, log)
+
+
+def oracle_mul_relin_moddown(O, ch, a0, a1, b0, b1, S_in, S, p, evk_a, evk_b):
+    parts = [x.copy() for x in (a0, a1, b0, b1)]
+    for x in parts:
+        O.scale_down(x, S_in, S, p)
+    t0, t1, t2 = O.tensor(parts[0], parts[1], parts[2], parts[3], S)
+    r0, r1 = O.relinearize(t0, t1, t2, S, evk_a, evk_b)
+    Sp = sorted(S + ch.special)
+    O.scale_down(r0, Sp, S, p)
+    O.scale_down(r1, Sp, S, p)
+    return r0, r1
+
+
+def test_multiply_on_level_sets_with_holes(sim_lib):
+    """Ctxt x Ctxt on arbitrary subsets of the ctxt primes.  A set that skips every prime of a middle digit makes breakIntoDigits
+    carry a zero digit whose full product still divides the later ones (src/DoubleCRT.cpp:488-493,509-561); the fused
+    relinearisation converts from a digit's own rows and used to run off the end of an empty one (found by this walk at
+    m = 2^17, bits = 500, c = 4, S = {7, 12, 13})."""
+    from common import ptxt_space
+    rnd = random.Random(5)
+    for cfg, fixed in (((1 << 17, 257, 1, 500, 4), [[7, 12, 13], [6, 13]]), ((4096, 257, 1, 300, 3), [])):
+        ch, psis, O, E = make(sim_lib, *cfg, nthreads=8)
+        p = ptxt_space(ch)
+        rng = np.random.default_rng(rnd.randrange(1 << 30))
+        full = ch.ctxt + ch.special
+        nd = len(ch.digits)
+        evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+        evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+        EA = [E.poly(evk_a[i], full) for i in range(nd)]
+        EB = [E.poly(evk_b[i], full) for i in range(nd)]
+        cases = [(s, s) for s in fixed if all(i in ch.ctxt for i in s)]
+        for _ in range(3):
+            S_in = sorted(rnd.sample(ch.ctxt, rnd.randint(2, len(ch.ctxt))))
+            cases.append((S_in, sorted(rnd.sample(S_in, len(S_in) - rnd.randint(0, min(2, len(S_in) - 1))))))
+        for S_in, S in cases:
+            o = [O.random(rng, S_in) for _ in range(4)]
+            A0, A1, B0, B1 = ([E.poly(o[k], S_in)] for k in range(4))
+            E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, p, EA, EB)
+            r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, p, evk_a, evk_b)
+            assert (A0[0].download(S)[S] == r0[S]).all() and (A1[0].download(S)[S] == r1[S]).all(), (cfg, S_in, S)
