@@ -2094,6 +2094,9 @@ extern "C" int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_p
   HB_TRY(check_polys(a0, nitems, &c, "hb_mul_relin_moddown")); HB_TRY(check_polys(a1, nitems, &c, "hb_mul_relin_moddown"));
   HB_TRY(check_polys(b0, nitems, &c, "hb_mul_relin_moddown")); HB_TRY(check_polys(b1, nitems, &c, "hb_mul_relin_moddown"));
   // bringToSet(common) on both operands: modDownToSet -> scaleDownToSet per part (src/Ctxt.cpp:393-562)
+  for (int i = 0; i < nS; i++)
+    if (std::find(S_in, S_in + nS_in, S[i]) == S_in + nS_in)
+      return hb_fail(HB_ERR_INDEX_SET, "hb_mul_relin_moddown: the common set must be a subset of the operands' set (prime %d)", S[i]);
   std::vector<hb_poly*> allp;
   for (int i = 0; i < nitems; i++) { allp.push_back(a0[i]); allp.push_back(a1[i]); allp.push_back(b0[i]); allp.push_back(b1[i]); }
   HB_TRY(scale_down_impl(allp.data(), (int)allp.size(), S_in, nS_in, S, nS, ptxt_space, nullptr, c->gen.on ? 0 : 1));   // lazy rows: the tensor product reduces exactly

@@ -222,7 +222,9 @@ int hb_ctx_set_stream(hb_ctx* ctx, void* cuda_stream);
 int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* const* c2, int nitems,
                    const int32_t* S, int nS, hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk);
 /* hb_mul_relin_moddown: operands (a0,a1),(b0,b1) over S_in; mod-down both to S (ptxt_space),
- * tensor, relinearise over S | special, mod-down the result to S.  Result in (a0,a1) rows S. */
+ * tensor, relinearise over S | special, mod-down the result to S.  Result in (a0,a1) rows S.
+ * S is the common set of Ctxt::multiplyBy / multLowLvl (src/Ctxt.cpp:1700-1712) and must be a subset of S_in
+ * (HB_ERR_INDEX_SET otherwise). */
 int hb_mul_relin_moddown(hb_poly* const* a0, hb_poly* const* a1, hb_poly* const* b0, hb_poly* const* b1, int nitems,
                          const int32_t* S_in, int nS_in, const int32_t* S, int nS, uint64_t ptxt_space,
                          hb_poly* const* evk_a, hb_poly* const* evk_b, int ndig_evk);

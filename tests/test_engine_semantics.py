@@ -108,6 +108,9 @@ def test_reference_error_behaviour(lib):
     with pytest.raises(HbError) as ei:          # ptxtSpace >= 1 (src/DoubleCRT.cpp:1472)
         E.scale_down([P], S + ch.special, S, 0)
     assert ei.value.code == -1
+    with pytest.raises(HbError) as ei:          # the common set of a multiply is a subset of both operands' sets
+        E.mul_relin_moddown([P], [Q], [E.poly()], [E.poly()], S[:-1], S, 1, [E.poly()] * len(ch.digits), [E.poly()] * len(ch.digits))
+    assert ei.value.code == -2
     # nothing-to-do cases return quietly (src/DoubleCRT.cpp:569-572, 1468-1470)
     E.add_primes([P], S, [])
     E.scale_down([P], S, S, 1)
