@@ -1320,7 +1320,10 @@ static int add_primes_impl(hb_poly* const* polys, int nitems, const int32_t* cur
   HB_TRY(check_idx(c, cur, ncur, "hb_add_primes", true)); HB_TRY(check_idx(c, add, nadd, "hb_add_primes", true));
   if (nadd == 0) return HB_OK;  // src/DoubleCRT.cpp:569-572
   HB_TRY(check_disjoint(cur, ncur, add, nadd, "addPrimes"));
-  if (ncur == 0) return hb_zero_rows(polys, nitems, add, nadd);  // src/DoubleCRT.cpp:577-583
+  if (ncur == 0) {   // the zero polynomial (src/DoubleCRT.cpp:577-583, 931-935); its norm is 0
+    if (log_norms) for (int i = 0; i < nitems; i++) log_norms[i] = -INFINITY;
+    return hb_zero_rows(polys, nitems, add, nadd);
+  }
   if (c->gen.on) {
     double logQg = 0; for (int j = 0; j < ncur; j++) logQg += std::log((double)c->q[cur[j]]);
     return for_items(nitems, [&](int i0, int nit) {

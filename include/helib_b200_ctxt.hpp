@@ -40,7 +40,10 @@ struct XD {
   XD() = default;
   XD(double v) { int ex = 0; m = std::frexp(v, &ex); e = ex; }
   static XD make(double m_, long e_) { XD r; int ex = 0; r.m = std::frexp(m_, &ex); r.e = e_ + ex; if (r.m == 0) r.e = 0; return r; }
-  static XD exp(double lnv) { double l2 = lnv / std::log(2.0); long fl = (long)std::floor(l2); return make(std::exp2(l2 - fl), fl); }
+  static XD exp(double lnv) {
+    if (!(lnv > -1e300)) return XD();   // ln 0 = -inf (the engine's answer for a zero polynomial) or ln() of a zero XD
+    double l2 = lnv / std::log(2.0); long fl = (long)std::floor(l2); return make(std::exp2(l2 - fl), fl);
+  }
   double ln() const { return m <= 0 ? -DBL_MAX : std::log(m) + e * std::log(2.0); }
   double to_double() const { return std::ldexp(m, (int)std::max(-2000L, std::min(2000L, e))); }
   XD operator*(const XD& o) const { return make(m * o.m, e + o.e); }
