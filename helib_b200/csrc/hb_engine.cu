@@ -2075,6 +2075,7 @@ extern "C" int hb_relinearize(hb_poly* const* c0, hb_poly* const* c1, hb_poly* c
     int last = -1; std::vector<char> live(c->ndigits > 0 ? c->ndigits : 1, 0);
     for (int i = 0; i < nS; i++) { const int d = c->digit_of[S[i]]; if (d >= 0) { live[d] = 1; last = std::max(last, d); } }
     for (int d = 0; d < last; d++) if (!live[d]) hole = true;
+    if (last + 1 > 4) hole = true;   // the fused inner product is instantiated for up to four digits (c <= 4)
   }
   if (v1_blk_ok(c) && v1_cols_ok(c) && !c->gen.on && !hole && !getenv("HB_NO_FUSED_RELIN"))
     return relin_fused_v1(c, c0, c1, c2, nitems, S, nS, Sp, evk_a, evk_b, ndig_evk, dig);

@@ -244,3 +244,24 @@ def test_multiply_on_level_sets_with_holes(sim_lib):
             E.mul_relin_moddown(A0, A1, B0, B1, S_in, S, p, EA, EB)
             r0, r1 = oracle_mul_relin_moddown(O, ch, *o, S_in, S, p, evk_a, evk_b)
             assert (A0[0].download(S)[S] == r0[S]).all() and (A1[0].download(S)[S] == r1[S]).all(), (cfg, S_in, S)
+
+
+def test_relinearize_with_six_digits(sim_lib):
+    """c = 6 at N = 2^16: more key-switching columns than the fused inner product is instantiated for (four); the call used to
+    answer HB_ERR_UNSUPPORTED on this ring while smaller rings accepted the same chain shape."""
+    cfg = (1 << 17, 257, 1, 600, 6)
+    ch, psis, O, E = make(sim_lib, *cfg, nthreads=8)
+    assert len(ch.digits) == 6
+    rng = np.random.default_rng(8)
+    full, S = ch.ctxt + ch.special, ch.ctxt
+    Sp = sorted(full)
+    nd = len(ch.digits)
+    evk_a = np.stack([O.random(rng, full) for _ in range(nd)])
+    evk_b = np.stack([O.random(rng, full) for _ in range(nd)])
+    EA = [E.poly(evk_a[i], full) for i in range(nd)]
+    EB = [E.poly(evk_b[i], full) for i in range(nd)]
+    c = [O.random(rng, S) for _ in range(3)]
+    C0, C1, C2 = ([E.poly(c[k], S)] for k in range(3))
+    E.relinearize(C0, C1, C2, S, EA, EB)
+    r0, r1 = O.relinearize(c[0], c[1], c[2], S, evk_a, evk_b)
+    assert (C0[0].download(Sp)[Sp] == r0[Sp]).all() and (C1[0].download(Sp)[Sp] == r1[Sp]).all()
