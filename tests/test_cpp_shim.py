@@ -124,3 +124,12 @@ def test_raw_mod_switch_through_mirror_on_simulator():
 def test_raw_mod_switch_through_mirror_on_gpu():
     r = subprocess.run([build_exe("test_rawmodswitch")], capture_output=True, text=True)
     assert r.returncode == 0 and "rawmodswitch OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_ctxt_random_walk_on_simulator(seed):
+    """Random sequences of +=, -=, multiplyBy, multByConstant, addConstant, negate, smartAutomorph and
+    dropSmallAndSpecialPrimes over a pool of BGV ciphertexts (tests/cpp/test_ctxt_walk.cpp): after every step the ciphertext
+    decrypts to the plaintext mirror and the tracked noise bound dominates the measured noise."""
+    r = subprocess.run([build_exe("test_ctxt_walk", sim=True), str(seed), "40"], capture_output=True, text=True)
+    assert r.returncode == 0 and "walk OK" in r.stdout, r.stdout + r.stderr
