@@ -133,3 +133,11 @@ def test_ctxt_random_walk_on_simulator(seed):
     decrypts to the plaintext mirror and the tracked noise bound dominates the measured noise."""
     r = subprocess.run([build_exe("test_ctxt_walk", sim=True), str(seed), "40"], capture_output=True, text=True)
     assert r.returncode == 0 and "walk OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_ckks_random_walk_on_simulator():
+    """The same for the CKKS branches (tests/cpp/test_ckks_walk.cpp): +=, -= across different scaling factors, multiplyBy,
+    negate, dropSmallAndSpecialPrimes; decode == real-valued mirror within the tracked noise bound, which in turn stays
+    small against the tracked plaintext magnitude."""
+    r = subprocess.run([build_exe("test_ckks_walk", sim=True), "1", "40"], capture_output=True, text=True)
+    assert r.returncode == 0 and "ckks walk OK" in r.stdout, r.stdout + r.stderr
