@@ -107,7 +107,8 @@ def test_random_walk_full_size_ring(sim_lib):
         walk(sim_lib, cfg, rnd, 14)
 
 
-GENERAL = [(12, 7, 1, 150, 2), (45, 2, 1, 150, 2), (28, 3, 1, 150, 3), (105, 2, 1, 180, 2), (45, 7, 2, 150, 2), (63, 2, 1, 150, 2), (85, 2, 1, 150, 2)]
+GENERAL = [(12, 7, 1, 150, 2), (45, 2, 1, 150, 2), (28, 3, 1, 150, 3), (105, 2, 1, 180, 2), (45, 7, 2, 150, 2), (63, 2, 1, 150, 2), (85, 2, 1, 150, 2),
+           (30, 7, 1, 150, 2)]   # m = 30: the division by Phi_m needs the full chirp length (2(m - phi(m)) - 1 > m)
 
 
 @pytest.mark.parametrize("seed", [1, 2])
