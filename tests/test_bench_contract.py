@@ -48,3 +48,17 @@ def test_both_arms_describe_the_same_workload():
     for cores in (1, 8, 16, 128, 192):
         w, per = bench.cpu_layout(cores)
         assert w >= 1 and per >= 1 and w * per <= max(cores, 1)
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback anywhere on the product path: without a CUDA device bench.py's own arm and smoke() stop with an error
+    instead of timing (or checking) something else."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is visible: the refusal path is not reachable")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and r.stdout.strip() == "" and "no CUDA device" in (r.stderr + r.stdout)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
